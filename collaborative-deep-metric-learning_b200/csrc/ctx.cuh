@@ -1,0 +1,21 @@
+// Host-side context shared by the translation units of libcdml.
+#pragma once
+#include "common.cuh"
+
+typedef CUresult (*cdml_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct cdml_ctx {
+  int device;
+  int num_sms;
+  int32_t* dev_flags;  // device error word
+  cdml_encode_tiled_fn encode_tiled;
+};
+
+namespace cdml {
+// 2-D tensor map over a row-major 16-bit matrix: `inner` contiguous elements, `outer` rows of pitch ld elements.
+// 128-byte swizzle, zero fill out of bounds.
+int make_tmap_2d(cdml_ctx* ctx, CUtensorMap* map, const void* ptr, int dtype16, uint64_t inner, uint64_t outer,
+                 uint64_t ld, uint32_t box_inner, uint32_t box_outer);
+}  // namespace cdml

@@ -1,0 +1,160 @@
+// Host launchers + C ABI for the tcgen05 GEMM family (cdml_gemm16).
+#include "../../include/cdml.h"
+#include "ctx.cuh"
+#include "gemm_sm100.cuh"
+
+namespace cdml {
+
+constexpr int kBN = 256;
+constexpr int kStages = 4;
+
+static int pick_splits(int num_sms, int tiles, int num_kb) {
+  // Few output tiles but a long K (weight gradients): split K so that tiles*S fills whole waves of SMs.
+  if (tiles >= 2 * num_sms || num_kb < 16) return 1;
+  const int smax = max(1, min(64, num_kb / 8));
+  int best = 1;
+  double best_eff = -1.0;
+  for (int s = 1; s <= smax; ++s) {
+    const int per = (num_kb + s - 1) / s;
+    const int seff = (num_kb + per - 1) / per;
+    if (seff != s) continue;
+    const long units = static_cast<long>(tiles) * s;
+    const long waves = (units + num_sms - 1) / num_sms;
+    double eff = static_cast<double>(units) / static_cast<double>(waves * num_sms);
+    if (units < num_sms) eff *= 0.5;          // leaves SMs idle
+    eff -= 0.002 * s;                          // partial-buffer traffic: prefer fewer splits on ties
+    if (eff > best_eff) best_eff = eff, best = s;
+  }
+  return best;
+}
+
+template <int AMN, int BMN, class Epi>
+static int launch_gemm(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
+                       int64_t K, int dtype16, int num_splits, const Epi& epi, cudaStream_t stream) {
+  using L = GemmSmem<kBN, kStages>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (AMN == 0) rc = make_tmap_2d(ctx, &ta, A, dtype16, K, M, lda, kBK, kBM);
+  else rc = make_tmap_2d(ctx, &ta, A, dtype16, M, K, lda, 64, kBK);
+  if (rc) return rc;
+  if (BMN == 0) rc = make_tmap_2d(ctx, &tb, B, dtype16, K, N, ldb, kBK, kBN);
+  else rc = make_tmap_2d(ctx, &tb, B, dtype16, N, K, ldb, 64, kBK);
+  if (rc) return rc;
+
+  GemmShape s;
+  s.M = static_cast<int>(M), s.N = static_cast<int>(N), s.K = static_cast<int>(K);
+  s.m_tiles = (s.M + kBM - 1) / kBM;
+  s.n_tiles = (s.N + kBN - 1) / kBN;
+  s.num_kb = (s.K + kBK - 1) / kBK;
+  num_splits = max(1, min(num_splits, s.num_kb));
+  s.kb_per_split = (s.num_kb + num_splits - 1) / num_splits;
+  s.num_splits = (s.num_kb + s.kb_per_split - 1) / s.kb_per_split;
+  s.idesc = make_idesc_f16(dtype16 == CDML_BF16 ? 1 : 0, AMN, BMN, kBM, kBN);
+
+  auto kern = gemm_tcgen05_kernel<AMN, BMN, kBN, kStages, Epi>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    CDML_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  const long units = static_cast<long>(s.m_tiles) * s.n_tiles * s.num_splits;
+  const int grid = static_cast<int>(units < ctx->num_sms ? units : ctx->num_sms);
+  kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, s, epi);
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return s.num_splits;
+}
+
+template <int AMN, int BMN>
+static int dispatch_epilogue(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
+                             int64_t K, int dtype16, int epilogue, void* out, int64_t ld_out, const float* bias,
+                             float alpha, void* aux0, void* aux1, int64_t ld_aux1, int num_splits, int64_t split_stride,
+                             cudaStream_t stream) {
+  const bool bf = dtype16 == CDML_BF16;
+  switch (epilogue) {
+    case 0: {
+      EpiStoreF32<kBN> e{static_cast<float*>(out), ld_out, split_stride, bias, alpha};
+      return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, num_splits, e, stream);
+    }
+    case 1: {
+      if (bf) {
+        EpiStore16<kBN, 1> e{static_cast<uint16_t*>(out), ld_out, bias, alpha};
+        return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+      }
+      EpiStore16<kBN, 0> e{static_cast<uint16_t*>(out), ld_out, bias, alpha};
+      return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+    }
+    case 2: {
+      CDML_REQUIRE(N <= kBN, "L2NORM epilogue needs the whole row in one tile (N=%lld > %d)", (long long)N, kBN);
+      if (bf) {
+        EpiL2Norm<kBN, 1> e{static_cast<float*>(out), ld_out, bias, alpha, static_cast<float*>(aux0),
+                            static_cast<uint16_t*>(aux1), ld_aux1};
+        return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+      }
+      EpiL2Norm<kBN, 0> e{static_cast<float*>(out), ld_out, bias, alpha, static_cast<float*>(aux0),
+                          static_cast<uint16_t*>(aux1), ld_aux1};
+      return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+    }
+    case 3: {
+      CDML_REQUIRE(aux1 != nullptr, "MASK_LEAKY epilogue needs aux1 (the forward activation)");
+      if (bf) {
+        EpiMaskLeaky<kBN, 1> e{static_cast<uint16_t*>(out), ld_out, static_cast<const uint16_t*>(aux1), ld_aux1, alpha};
+        return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+      }
+      EpiMaskLeaky<kBN, 0> e{static_cast<uint16_t*>(out), ld_out, static_cast<const uint16_t*>(aux1), ld_aux1, alpha};
+      return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+    }
+    default:
+      set_error("cdml_gemm16: unknown epilogue %d", epilogue);
+      return -1;
+  }
+}
+
+}  // namespace cdml
+
+extern "C" {
+
+int cdml_gemm16_auto_splits(cdml_ctx* ctx, int64_t M, int64_t N, int64_t K) {
+  if (ctx == nullptr || M <= 0 || N <= 0 || K <= 0) return 1;
+  const int tiles = static_cast<int>(((M + cdml::kBM - 1) / cdml::kBM) * ((N + cdml::kBN - 1) / cdml::kBN));
+  return cdml::pick_splits(ctx->num_sms, tiles, static_cast<int>((K + cdml::kBK - 1) / cdml::kBK));
+}
+
+int cdml_gemm16(cdml_ctx* ctx, const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
+                int64_t M, int64_t N, int64_t K, int dtype16, int epilogue, void* out, int64_t ld_out,
+                const float* bias, float alpha, void* aux0, void* aux1, int64_t ld_aux1, int num_splits,
+                int64_t split_stride, int* splits_used, void* stream) {
+  using namespace cdml;
+  CDML_REQUIRE(ctx != nullptr && A != nullptr && B != nullptr && out != nullptr, "cdml_gemm16: NULL argument");
+  CDML_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31),
+               "cdml_gemm16: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  CDML_REQUIRE(dtype16 == CDML_F16 || dtype16 == CDML_BF16, "cdml_gemm16: dtype16 must be 0 (fp16) or 1 (bf16)");
+  CDML_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "cdml_gemm16: out is not 16-byte aligned");
+  if (epilogue == 0) {
+    if (num_splits <= 0) num_splits = cdml_gemm16_auto_splits(ctx, M, N, K);
+    CDML_REQUIRE(num_splits == 1 || (bias == nullptr && alpha == 1.0f),
+                 "cdml_gemm16: split-K partials cannot carry bias/activation");
+    CDML_REQUIRE(num_splits == 1 || split_stride >= M * ld_out, "cdml_gemm16: split_stride too small");
+  } else {
+    num_splits = 1;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if (a_mn_major == 0 && b_mn_major == 1)
+    rc = dispatch_epilogue<0, 1>(ctx, A, lda, B, ldb, M, N, K, dtype16, epilogue, out, ld_out, bias, alpha, aux0, aux1,
+                                 ld_aux1, num_splits, split_stride, st);
+  else if (a_mn_major == 0 && b_mn_major == 0)
+    rc = dispatch_epilogue<0, 0>(ctx, A, lda, B, ldb, M, N, K, dtype16, epilogue, out, ld_out, bias, alpha, aux0, aux1,
+                                 ld_aux1, num_splits, split_stride, st);
+  else if (a_mn_major == 1 && b_mn_major == 1)
+    rc = dispatch_epilogue<1, 1>(ctx, A, lda, B, ldb, M, N, K, dtype16, epilogue, out, ld_out, bias, alpha, aux0, aux1,
+                                 ld_aux1, num_splits, split_stride, st);
+  else {
+    set_error("cdml_gemm16: operand layout (a_mn_major=%d, b_mn_major=%d) is not instantiated", a_mn_major, b_mn_major);
+    return -1;
+  }
+  if (rc < 0) return rc;
+  if (splits_used != nullptr) *splits_used = rc;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,410 @@
+// Persistent, warp-specialised tcgen05 GEMM core for sm_100a.
+//
+//   D[M,N] (fp32 accumulators in TMEM) = A[M,K] * B[N,K]^T     16-bit operands (fp16 | bf16)
+//
+// Operands may be K-major (row-major [rows,K]) or MN-major (row-major [K,rows]) independently, so the
+// tower's forward (x @ W), data-gradient (dz @ W^T) and weight-gradient (x^T @ dz) all run on this one
+// kernel without transposed copies.  TMA stages 128-byte-swizzled tiles into a kStages ring, a single
+// thread issues tcgen05.mma (M=128, N=BN, K=16), the accumulator is double-buffered in TMEM so the
+// epilogue warps (tcgen05.ld -> fused bias / leaky-ReLU / L2-norm / mask -> global) overlap the next
+// tile's main loop.  Optional split-K writes fp32 partials that a separate kernel reduces in fixed order.
+//
+// Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4..7 epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace cdml {
+
+constexpr int kBM = 128;  // tile rows   (TMEM lanes)
+constexpr int kBK = 64;   // 16-bit elements per k-block = one 128 B swizzle span
+constexpr int kUK = 16;   // K per tcgen05.mma (kind::f16)
+constexpr int kGemmThreads = 256;
+
+struct GemmShape {
+  int M, N, K;
+  int m_tiles, n_tiles;
+  int num_kb;        // ceil(K / 64)
+  int kb_per_split;  // k-blocks handled by one split
+  int num_splits;    // every split owns >= 1 k-block
+  uint32_t idesc;
+};
+
+template <int BN, int kStages>
+struct GemmSmem {
+  static constexpr uint32_t kABytes = kBM * kBK * 2;  // 16 KB
+  static constexpr uint32_t kBBytes = BN * kBK * 2;
+  static constexpr uint32_t kBarOff = kStages * (kABytes + kBBytes);
+  static constexpr uint32_t kNumBars = 2 * kStages + 4;
+  static constexpr uint32_t kTotal = kBarOff + kNumBars * 8 + 16 + 1024;  // +1024: manual 1 KB alignment
+};
+
+// ------------------------------------------------------------------------------------------------
+// Epilogues.  run() is executed by each of the 4 epilogue warps; thread <-> one output row.
+//   taddr : TMEM address of (lane quarter, first accumulator column of this tile)
+//   row   : global output row of this thread;  n0 : first global column of the tile
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float leaky(float v, float alpha) { return v > 0.f ? v : alpha * v; }
+
+// fp32 store (optionally bias + leaky).  Split-K partials land at out + split * split_stride.
+template <int BN>
+struct EpiStoreF32 {
+  float* out;
+  int64_t ld;
+  int64_t split_stride;
+  const float* bias;  // nullable
+  float alpha;        // 1.0f = identity
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int split, const GemmShape& s) const {
+    float* orow = out + static_cast<int64_t>(split) * split_stride + static_cast<int64_t>(row) * ld;
+    const bool row_ok = row < s.M;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nb = n0 + c * 32;
+      if (nb >= s.N) break;
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        if (bias != nullptr && nb + j < s.N) x += __ldg(bias + nb + j);
+        f[j] = leaky(x, alpha);
+      }
+      if (row_ok) {
+        if (nb + 32 <= s.N && (ld & 3) == 0) {
+          float4* p = reinterpret_cast<float4*>(orow + nb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < s.N) orow[nb + j] = f[j];
+        }
+      }
+    }
+  }
+};
+
+// 16-bit store of leaky(acc + bias): the hidden-layer forward epilogue (models.py:19-30).
+template <int BN, int kBf16>
+struct EpiStore16 {
+  uint16_t* out;
+  int64_t ld;
+  const float* bias;  // nullable
+  float alpha;
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
+    uint16_t* orow = out + static_cast<int64_t>(row) * ld;
+    const bool row_ok = row < s.M;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nb = n0 + c * 32;
+      if (nb >= s.N) break;
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+        if (bias != nullptr) {
+          if (nb + 2 * j < s.N) x0 += __ldg(bias + nb + 2 * j);
+          if (nb + 2 * j + 1 < s.N) x1 += __ldg(bias + nb + 2 * j + 1);
+        }
+        pk[j] = pack2<kBf16>(leaky(x0, alpha), leaky(x1, alpha));
+      }
+      if (row_ok) {
+        if (nb + 32 <= s.N && (ld & 7) == 0) {
+          uint4* p = reinterpret_cast<uint4*>(orow + nb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) p[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < s.N) orow[nb + j] = static_cast<uint16_t>(pk[j >> 1] >> ((j & 1) * 16));
+        }
+      }
+    }
+  }
+};
+
+// Last layer: y = leaky(acc + bias); e = y * rsqrt(max(sum y^2, 1e-12))  (models.py:60-61).
+// Requires the whole row in one tile (N <= BN).  Writes e (fp32), rinv[row], optional 16-bit e.
+template <int BN, int kBf16>
+struct EpiL2Norm {
+  float* out;  // [M, ld] fp32 embedding
+  int64_t ld;
+  const float* bias;
+  float alpha;
+  float* rinv;      // [M] nullable
+  uint16_t* out16;  // [M, ld16] nullable
+  int64_t ld16;
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
+    const bool row_ok = row < s.M;
+    float ss = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nb = n0 + c * 32;
+      if (nb >= s.N) break;
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (nb + j < s.N) {
+          float x = __uint_as_float(v[j]);
+          if (bias != nullptr) x += __ldg(bias + nb + j);
+          x = leaky(x, alpha);
+          ss = fmaf(x, x, ss);
+        }
+      }
+    }
+    const float r = rsqrtf(fmaxf(ss, 1e-12f));
+    if (row_ok && rinv != nullptr) rinv[row] = r;
+    float* orow = out + static_cast<int64_t>(row) * ld;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nb = n0 + c * 32;
+      if (nb >= s.N) break;
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        if (bias != nullptr && nb + j < s.N) x += __ldg(bias + nb + j);
+        f[j] = leaky(x, alpha) * r;
+      }
+      if (row_ok) {
+        if (nb + 32 <= s.N && (ld & 3) == 0) {
+          float4* p = reinterpret_cast<float4*>(orow + nb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < s.N) orow[nb + j] = f[j];
+        }
+        if (out16 != nullptr) {
+          uint16_t* o16 = out16 + static_cast<int64_t>(row) * ld16;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const uint32_t pk = pack2<kBf16>(f[j], f[j + 1]);
+            if (nb + j < s.N) o16[nb + j] = static_cast<uint16_t>(pk);
+            if (nb + j + 1 < s.N) o16[nb + j + 1] = static_cast<uint16_t>(pk >> 16);
+          }
+        }
+      }
+    }
+  }
+};
+
+// Data-gradient epilogue: out = acc * (mask > 0 ? 1 : alpha), mask = the layer's own (post-leaky)
+// forward output -- sign(leaky(z)) == sign(z), so no pre-activation stash is needed.
+template <int BN, int kBf16>
+struct EpiMaskLeaky {
+  uint16_t* out;
+  int64_t ld;
+  const uint16_t* mask;
+  int64_t ld_mask;
+  float alpha;
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
+    const bool row_ok = row < s.M;
+    uint16_t* orow = out + static_cast<int64_t>(row) * ld;
+    const uint16_t* mrow = mask + static_cast<int64_t>(row) * ld_mask;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nb = n0 + c * 32;
+      if (nb >= s.N) break;
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      const bool vec = nb + 32 <= s.N && (ld & 7) == 0 && (ld_mask & 7) == 0;
+      uint32_t mk[16];
+      if (row_ok) {
+        if (vec) {
+          const uint4* mp = reinterpret_cast<const uint4*>(mrow + nb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 t = __ldg(mp + j);
+            mk[4 * j] = t.x, mk[4 * j + 1] = t.y, mk[4 * j + 2] = t.z, mk[4 * j + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t lo = (nb + 2 * j < s.N) ? mrow[nb + 2 * j] : 0u;
+            const uint32_t hi = (nb + 2 * j + 1 < s.N) ? mrow[nb + 2 * j + 1] : 0u;
+            mk[j] = lo | (hi << 16);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mk[j] = 0u;
+      }
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 m = unpack2<kBf16>(mk[j]);
+        const float x0 = __uint_as_float(v[2 * j]) * (m.x > 0.f ? 1.f : alpha);
+        const float x1 = __uint_as_float(v[2 * j + 1]) * (m.y > 0.f ? 1.f : alpha);
+        pk[j] = pack2<kBf16>(x0, x1);
+      }
+      if (row_ok) {
+        if (vec) {
+          uint4* p = reinterpret_cast<uint4*>(orow + nb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) p[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < s.N) orow[nb + j] = static_cast<uint16_t>(pk[j >> 1] >> ((j & 1) * 16));
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------------
+template <int kAMajorMN, int kBMajorMN, int BN, int kStages, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const GemmShape s, const Epi epi) {
+  using L = GemmSmem<BN, kStages>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  const uint32_t bar0 = base + L::kBarOff;
+  auto a_smem = [&](int st) { return base + st * L::kABytes; };
+  auto b_smem = [&](int st) { return base + kStages * L::kABytes + st * L::kBBytes; };
+  auto full_bar = [&](int st) { return bar0 + 8u * st; };
+  auto empty_bar = [&](int st) { return bar0 + 8u * (kStages + st); };
+  auto tfull_bar = [&](int i) { return bar0 + 8u * (2 * kStages + i); };
+  auto tempty_bar = [&](int i) { return bar0 + 8u * (2 * kStages + 2 + i); };
+  const uint32_t tmem_slot = bar0 + 8u * L::kNumBars;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(full_bar(i), 1);
+      mbar_init(empty_bar(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int tiles = s.m_tiles * s.n_tiles;
+  const int units = tiles * s.num_splits;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int split = u / tiles, t = u - split * tiles;
+      const int m0 = (t / s.n_tiles) * kBM, n0 = (t % s.n_tiles) * BN;
+      const int kb0 = split * s.kb_per_split;
+      const int kb1 = min(s.num_kb, kb0 + s.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1, 100 + stage);
+        mbar_arrive_expect_tx(full_bar(stage), L::kABytes + L::kBBytes);
+        const int k0 = kb * kBK;
+        if constexpr (kAMajorMN == 0) {
+          tma_load_2d(a_smem(stage), &tma_a, full_bar(stage), k0, m0);
+        } else {
+#pragma unroll
+          for (int i = 0; i < kBM / 64; ++i)
+            tma_load_2d(a_smem(stage) + i * (kBK * 128), &tma_a, full_bar(stage), m0 + i * 64, k0);
+        }
+        if constexpr (kBMajorMN == 0) {
+          tma_load_2d(b_smem(stage), &tma_b, full_bar(stage), k0, n0);
+        } else {
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i)
+            tma_load_2d(b_smem(stage) + i * (kBK * 128), &tma_b, full_bar(stage), n0 + i * 64, k0);
+        }
+        if (++stage == kStages) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    // K-major: +32 B per UMMA_K inside the 128 B swizzle span; MN-major: +16 K-rows * 128 B.
+    constexpr uint32_t kAStep = kAMajorMN ? (kUK * 128) : (kUK * 2);
+    constexpr uint32_t kBStep = kBMajorMN ? (kUK * 128) : (kUK * 2);
+    constexpr uint32_t kALbo = kAMajorMN ? (kBK * 128) : 16;
+    constexpr uint32_t kBLbo = kBMajorMN ? (kBK * 128) : 16;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+      const int split = u / tiles;
+      const int kb0 = split * s.kb_per_split;
+      const int kb1 = min(s.num_kb, kb0 + s.kb_per_split);
+      const int as = it & 1;
+      const uint32_t ap = (it >> 1) & 1;
+      mbar_wait(tempty_bar(as), ap ^ 1, 200 + as);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase, 300 + stage);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kBK / kUK; ++k) {
+          const uint64_t ad = make_smem_desc(a_smem(stage) + k * kAStep, kALbo, 1024);
+          const uint64_t bd = make_smem_desc(b_smem(stage) + k * kBStep, kBLbo, 1024);
+          umma_f16(tmem_d, ad, bd, s.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+        if (kb == kb1 - 1) tc_commit(tfull_bar(as));
+        if (++stage == kStages) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+      const int split = u / tiles, t = u - split * tiles;
+      const int m0 = (t / s.n_tiles) * kBM, n0 = (t % s.n_tiles) * BN;
+      const int as = it & 1;
+      const uint32_t ap = (it >> 1) & 1;
+      mbar_wait(tfull_bar(as), ap, 400 + as);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      epi.run(taddr, m0 + q * 32 + lane, n0, split, s);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace cdml

@@ -1,0 +1,159 @@
+"""Thin tensor-level wrappers over the C ABI (one function per libcdml entry point).
+
+All tensors are CUDA tensors on the current device; outputs are allocated here with torch (plumbing) and filled by
+the hand-written kernels.  Nothing in this module computes on the host or with torch ops."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import BF16, EPI_L2NORM, EPI_MASK_LEAKY, EPI_STORE_16, EPI_STORE_F32, F16, check, ptr, stream_ptr
+
+TORCH16 = {F16: torch.float16, BF16: torch.bfloat16}
+
+
+def _ctx(t):
+  return _lib.context(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def dtype16_of(t):
+  if t.dtype == torch.float16:
+    return F16
+  if t.dtype == torch.bfloat16:
+    return BF16
+  raise TypeError("expected a float16/bfloat16 tensor, got %s" % t.dtype)
+
+
+def _row_major_2d(t, name):
+  if t.dim() != 2 or t.stride(1) != 1:
+    raise ValueError("%s must be a 2-D tensor with unit inner stride" % name)
+  return t.stride(0)
+
+
+def poll_errors(device_tensor):
+  flags = ctypes.c_int32(0)
+  check(_lib.load().cdml_ctx_poll_errors(_ctx(device_tensor), stream_ptr(), ctypes.byref(flags)))
+  return flags.value
+
+
+def gather_rows(table, idx, out=None):
+  """out[i] = table[idx[i]]  (inputs.py:158).  table [G,W] any dtype, idx int32/int64 (any shape) -> [*idx.shape, W]."""
+  pitch = _row_major_2d(table, "table") * table.element_size()
+  flat = idx.reshape(-1)
+  if flat.dtype not in (torch.int32, torch.int64):
+    raise TypeError("idx must be int32 or int64")
+  flat = flat.contiguous()
+  row_bytes = table.shape[1] * table.element_size()
+  if out is None:
+    out = torch.empty((flat.numel(), table.shape[1]), dtype=table.dtype, device=table.device)
+  out_pitch = _row_major_2d(out, "out") * out.element_size()
+  check(_lib.load().cdml_gather_rows(_ctx(table), ptr(table), table.shape[0], row_bytes, pitch, ptr(flat),
+                                     int(flat.dtype == torch.int64), flat.numel(), ptr(out), out_pitch, stream_ptr()))
+  return out
+
+
+def rows_normalize_cast(x, dtype16=F16, normalize=1, eps=1e-12, ld_out=None, want_fp32=False, want_sumsq=False,
+                        out16=None):
+  """fp32 [n,F] -> 16-bit [n,ld_out] rows, optionally L2-normalised (1: TF semantics, 2: numpy x/||x||)."""
+  ld_in = _row_major_2d(x, "x")
+  n, F = x.shape
+  if ld_out is None:
+    ld_out = (F + 7) // 8 * 8
+  if out16 is None:
+    out16 = torch.empty((n, ld_out), dtype=TORCH16[dtype16], device=x.device)
+  out32 = torch.empty((n, F), dtype=torch.float32, device=x.device) if want_fp32 else None
+  sumsq = torch.empty((n,), dtype=torch.float32, device=x.device) if want_sumsq else None
+  check(_lib.load().cdml_rows_normalize_cast(_ctx(x), ptr(x), n, F, ld_in, normalize, eps, ptr(out16), out16.stride(0),
+                                             dtype16, ptr(out32), F, ptr(sumsq), stream_ptr()))
+  return out16, out32, sumsq
+
+
+def gemm16(A, B, M, N, K, a_mn_major, b_mn_major, epilogue, out, bias=None, alpha=1.0, aux0=None, aux1=None,
+           num_splits=1, split_stride=0):
+  """Raw cdml_gemm16 call.  A/B are 16-bit 2-D tensors; shapes are passed explicitly (logical M,N,K)."""
+  lda, ldb = _row_major_2d(A, "A"), _row_major_2d(B, "B")
+  used = ctypes.c_int(0)
+  check(_lib.load().cdml_gemm16(_ctx(A), ptr(A), int(a_mn_major), lda, ptr(B), int(b_mn_major), ldb, M, N, K,
+                                dtype16_of(A), epilogue, ptr(out), out.stride(-2), ptr(bias), float(alpha), ptr(aux0),
+                                ptr(aux1), aux1.stride(0) if aux1 is not None else 0, num_splits, split_stride,
+                                ctypes.byref(used), stream_ptr()))
+  return used.value
+
+
+def auto_splits(ref, M, N, K):
+  return _lib.load().cdml_gemm16_auto_splits(_ctx(ref), M, N, K)
+
+
+def sum_partials(parts, num_parts, stride, n, out, scale=1.0):
+  check(_lib.load().cdml_sum_partials(_ctx(parts), ptr(parts), num_parts, stride, n, float(scale), ptr(out), stream_ptr()))
+  return out
+
+
+def colsum16(X, R, N, out, workspace=None):
+  need = _lib.load().cdml_colsum_workspace_floats(R, N)
+  if workspace is None or workspace.numel() < need:
+    workspace = torch.empty((need,), dtype=torch.float32, device=X.device)
+  check(_lib.load().cdml_colsum16(_ctx(X), ptr(X), R, N, X.stride(0), dtype16_of(X), ptr(workspace), ptr(out), stream_ptr()))
+  return out
+
+
+def colsum_workspace_floats(R, N):
+  return _lib.load().cdml_colsum_workspace_floats(R, N)
+
+
+def triplet_hinge(E, B, margin, neg_row=None, grad_scale=1.0, rinv=None, leaky_alpha=0.2, want_dE=False, dz16=None,
+                  workspace=None, out=None):
+  """HingeLoss forward (+ optional backward).  E fp32 [3B,D].  Returns dict of device tensors."""
+  D = E.shape[1]
+  dev = E.device
+  out = out or {}
+  pos = out.get("pos_dist") if "pos_dist" in out else torch.empty((B,), dtype=torch.float32, device=dev)
+  neg = out.get("neg_dist") if "neg_dist" in out else torch.empty((B,), dtype=torch.float32, device=dev)
+  hin = out.get("hinge_dist") if "hinge_dist" in out else torch.empty((B,), dtype=torch.float32, device=dev)
+  stats = out.get("stats") if "stats" in out else torch.empty((4,), dtype=torch.float32, device=dev)
+  dE = None
+  if want_dE:
+    dE = out.get("dE") if "dE" in out else torch.empty_like(E)
+  if dz16 is not None and dE is None and workspace is None:
+    workspace = torch.empty((3 * B * E.stride(0),), dtype=torch.float32, device=dev)
+  check(_lib.load().cdml_triplet_hinge(_ctx(E), ptr(E), B, D, E.stride(0), ptr(neg_row), float(margin), float(grad_scale),
+                                       ptr(rinv), float(leaky_alpha), ptr(pos), ptr(neg), ptr(hin), ptr(stats), ptr(dE),
+                                       ptr(dz16), dz16.stride(0) if dz16 is not None else 0,
+                                       dtype16_of(dz16) if dz16 is not None else F16, ptr(workspace), stream_ptr()))
+  return {"pos_dist": pos, "neg_dist": neg, "hinge_dist": hin, "stats": stats, "dE": dE, "dz16": dz16}
+
+
+def adam_prepare(step_counter, scalars, base_lr, decay_steps=1e6, decay_rate=0.96, staircase=True, beta1=0.9,
+                 beta2=0.999):
+  check(_lib.load().cdml_adam_prepare(_ctx(scalars), ptr(step_counter), float(base_lr), float(decay_steps),
+                                      float(decay_rate), int(staircase), float(beta1), float(beta2), ptr(scalars),
+                                      stream_ptr()))
+
+
+def adam_apply(w, m, v, g, scalars, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, w16=None):
+  check(_lib.load().cdml_adam_apply(_ctx(w), ptr(w), ptr(m), ptr(v), ptr(g), w.numel(), ptr(scalars), float(beta1),
+                                    float(beta2), float(eps), float(grad_scale), ptr(w16),
+                                    dtype16_of(w16) if w16 is not None else F16, stream_ptr()))
+
+
+def cast16(x, out16):
+  check(_lib.load().cdml_cast16(_ctx(x), ptr(x), x.numel(), ptr(out16), dtype16_of(out16), stream_ptr()))
+  return out16
+
+
+def mean_pair_dist(V, pairs):
+  out = torch.empty((1,), dtype=torch.float32, device=V.device)
+  pairs = pairs.to(torch.int64).contiguous()
+  check(_lib.load().cdml_mean_pair_dist(_ctx(V), ptr(V), V.stride(0), V.shape[1], ptr(pairs), pairs.shape[0], ptr(out),
+                                        stream_ptr()))
+  return out
+
+
+def mine_semihard(E16, E32, guid, B, margin, want_dist=True):
+  D = E32.shape[1]
+  neg_row = torch.empty((B,), dtype=torch.int32, device=E32.device)
+  d_an = torch.empty((B,), dtype=torch.float32, device=E32.device) if want_dist else None
+  guid = guid.to(torch.int64).contiguous()
+  check(_lib.load().cdml_mine_semihard(_ctx(E32), ptr(E16), E16.stride(0), dtype16_of(E16), ptr(E32), E32.stride(0),
+                                       ptr(guid), B, D, float(margin), ptr(neg_row), ptr(d_an), stream_ptr()))
+  return neg_row, d_an

@@ -1,0 +1,134 @@
+/* libcdml.so -- C ABI of the B200-native CDML hot path.
+ *
+ * The reference (geekieo/collaborative-deep-metric-learning) has no FFI of its own: its hot path is
+ * Python calling TensorFlow 1.13 and faiss 1.5 ops.  Each entry point below replaces the library op(s)
+ * the reference reaches at the cited call site (file:line relative to the reference tree) and is what a
+ * ctypes binding in the reference's own modules would bind.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; cdml_last_error() gives the thread-local message;
+ *   - no exceptions, no ownership transfer: all tensors are caller-owned DEVICE pointers unless a
+ *     parameter is documented as host; row-major, explicit leading dimensions in ELEMENTS;
+ *   - every compute call takes a cudaStream_t (as void*) and is asynchronous w.r.t. the host;
+ *   - dtype16: 0 = fp16, 1 = bf16 (operand type of the tensor-core GEMMs; accumulation is fp32);
+ *   - 16-bit / fp32 matrices handed to GEMMs need 16-byte aligned bases and row pitches.
+ */
+#ifndef CDML_H_
+#define CDML_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cdml_ctx cdml_ctx;
+
+#define CDML_F16 0
+#define CDML_BF16 1
+
+/* ---- context / errors ------------------------------------------------------------------------ */
+int cdml_ctx_create(int device, cdml_ctx** out);
+int cdml_ctx_destroy(cdml_ctx* ctx);
+const char* cdml_last_error(void);
+int cdml_version(void);
+/* Device-side error word (bad gather index ...): copies it to *flags (host) and clears it. Synchronises stream. */
+int cdml_ctx_poll_errors(cdml_ctx* ctx, void* stream, int32_t* flags);
+
+/* ---- K1: triplet row gather -- replaces numpy FEATURES[np.asarray(guid_triplets)] (inputs.py:158) + reshape
+ *      (train.py:313).  Bit-exact byte copy of n_idx rows of row_bytes each.  idx_is_64: int64 vs int32 indices;
+ *      negative indices wrap like numpy; out-of-range sets error flag bit 0 and writes zeros. */
+int cdml_gather_rows(cdml_ctx* ctx, const void* table, int64_t num_rows, int64_t row_bytes, int64_t table_pitch_bytes,
+                     const void* idx, int idx_is_64, int64_t n_idx, void* out, int64_t out_pitch_bytes, void* stream);
+
+/* ---- K2: row L2-normalise + cast -- replaces tf.nn.l2_normalize(model_input) (models.py:58) and the
+ *      numpy row normalisation of calc_knn (faiss_knn.py:99-104).  in fp32 [n,F] -> out16 [n,ld_out] (columns
+ *      F..ld_out-1 zeroed).  normalize: 0 = cast only, 1 = x*rsqrt(max(sum x^2,eps)) (TF), 2 = x/sqrt(sum x^2) (numpy).
+ *      out32 (nullable) receives the fp32 normalised rows [n,ld_out32]; sumsq (nullable) the row sum of squares
+ *      of the OUTPUT16 rows (after rounding) as fp32 [n]. */
+int cdml_rows_normalize_cast(cdml_ctx* ctx, const float* in, int64_t n, int64_t F, int64_t ld_in, int normalize,
+                             float eps, void* out16, int64_t ld_out, int dtype16, float* out32, int64_t ld_out32,
+                             float* sumsq, void* stream);
+
+/* ---- K3/K4/K6: tensor-core GEMM family (tcgen05 + TMA).  Replaces slim.fully_connected's MatMul/BiasAdd/
+ *      LeakyRelu (models.py:26-30), tf.nn.l2_normalize(layer_2) (models.py:61) and the autodiff MatMuls of
+ *      optimizer.compute_gradients (train.py:141-142).
+ *      A is [M,K] (a_mn_major=0) or [K,M] (a_mn_major=1); B is [N,K] (b_mn_major=0) or [K,N] (b_mn_major=1).
+ *      epilogue:
+ *        0 STORE_F32  out fp32 [M,ld_out] = leaky(acc + bias)         (bias nullable; alpha=1 -> identity);
+ *                     num_splits > 1 writes split-K partials at out + s*split_stride (reduce with cdml_sum_partials)
+ *        1 STORE_16   out 16-bit [M,ld_out] = leaky(acc + bias)
+ *        2 L2NORM     y = leaky(acc+bias); out fp32 = y*rsqrt(max(sum y^2,1e-12)); aux0 = rinv fp32 [M] (nullable);
+ *                     aux1 = 16-bit copy [M,ld_aux1] (nullable).  Requires N <= 256.
+ *        3 MASK_LEAKY out 16-bit = acc * (aux1[m,n] > 0 ? 1 : alpha)   (aux1 = 16-bit mask, ld_aux1)
+ *      num_splits: <=0 lets the library choose (STORE_F32 only); *splits_used (nullable, host) reports it. */
+int cdml_gemm16(cdml_ctx* ctx, const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
+                int64_t M, int64_t N, int64_t K, int dtype16, int epilogue, void* out, int64_t ld_out,
+                const float* bias, float alpha, void* aux0, void* aux1, int64_t ld_aux1, int num_splits,
+                int64_t split_stride, int* splits_used, void* stream);
+/* Split count the library would pick for (M,N,K) so callers can size the partial buffer. */
+int cdml_gemm16_auto_splits(cdml_ctx* ctx, int64_t M, int64_t N, int64_t K);
+
+/* out[i] = scale * sum_s parts[s*stride + i], fixed order (deterministic split-K / bias-grad reduction). */
+int cdml_sum_partials(cdml_ctx* ctx, const float* parts, int num_parts, int64_t stride, int64_t n, float scale,
+                      float* out, void* stream);
+
+/* Column sums of a 16-bit matrix: out fp32 [N] = sum_rows X[r,:] (bias gradient of the autodiff, train.py:141).
+ * workspace: fp32 [cdml_colsum_workspace_floats(R,N)]. */
+int64_t cdml_colsum_workspace_floats(int64_t R, int64_t N);
+int cdml_colsum16(cdml_ctx* ctx, const void* X, int64_t R, int64_t N, int64_t ld, int dtype16, float* workspace,
+                  float* out, void* stream);
+
+/* ---- K5: HingeLoss.calculate_loss (losses.py:21-49) forward + backward through the output L2-norm and the last
+ *      leaky-ReLU.  E fp32 [3B,ld_e] rows a0,p0,n0,a1,...  neg_row (nullable int32 [B]) overrides the negative's row
+ *      (in-batch mining); then gradients are scatter-added.  Outputs (all nullable except stats):
+ *        pos_dist,neg_dist,hinge_dist fp32 [B]; stats fp32 [4] = {mean hinge (the loss), mean pos, mean neg, #active};
+ *        dE fp32 [3B,ld_e] = d(sum_i hinge_i)/dE * grad_scale   (NOT divided by B unless grad_scale = 1/B);
+ *        dz16 16-bit [3B,ld_dz] = (dE - e(e.dE)) * rinv * leaky'(e)  -- gradient w.r.t. the last layer's
+ *        pre-activation, ready to be the A/B operand of the backward GEMMs.  rinv fp32 [3B] from the L2NORM epilogue.
+ *      workspace: fp32 [3B*D] when dE is NULL but dz16 is requested. */
+int cdml_triplet_hinge(cdml_ctx* ctx, const float* E, int64_t B, int D, int64_t ld_e, const int32_t* neg_row,
+                       float margin, float grad_scale, const float* rinv, float leaky_alpha, float* pos_dist,
+                       float* neg_dist, float* hinge_dist, float* stats, float* dE, void* dz16, int64_t ld_dz,
+                       int dtype16, float* workspace, void* stream);
+
+/* ---- K8: TF1 AdamOptimizer.apply_gradients (train.py:82,146) with exponential_decay (train.py:108-113).
+ *      cdml_adam_prepare reads/increments the device step counter and writes lr_t (bias-corrected, decayed) to
+ *      scalars[0] (device float[4]); cdml_adam_apply then updates one tensor and (optionally) its 16-bit shadow. */
+int cdml_adam_prepare(cdml_ctx* ctx, int64_t* step_counter, float base_lr, float decay_steps, float decay_rate,
+                      int staircase, float beta1, float beta2, float* scalars, void* stream);
+int cdml_adam_apply(cdml_ctx* ctx, float* w, float* m, float* v, const float* g, int64_t n, const float* scalars,
+                    float beta1, float beta2, float eps, float grad_scale, void* w16, int dtype16, void* stream);
+/* fp32 -> 16-bit cast of a flat buffer (initial shadow weights). */
+int cdml_cast16(cdml_ctx* ctx, const float* in, int64_t n, void* out16, int dtype16, void* stream);
+
+/* ---- row M: in-batch semi-hard negative mining (build-defined).  E16 16-bit [3B,ld] embeddings,
+ *      E32 fp32 [3B,ld32] (for |a-p|^2), guid int64 [B,3].  neg_row int32 [B] out, d_an fp32 [B] out (nullable). */
+int cdml_mine_semihard(cdml_ctx* ctx, const void* E16, int64_t ld16, int dtype16, const float* E32, int64_t ld32,
+                       const int64_t* guid, int64_t B, int D, float margin, int32_t* neg_row, float* d_an,
+                       void* stream);
+
+/* ---- K11-K13: exact flat KNN -- replaces faiss index.add + index.search (faiss_knn.py:116-128) with
+ *      IndexFlatL2 / IndexFlatIP semantics.  X fp32 [N,d] (ldx), Q fp32 [nq,d] (ldq); metric 0 = L2 (squared,
+ *      ascending), 1 = IP (descending).  D fp32 [nq,k], I int64 [nq,k] (+id_offset; -1/inf padding when N < k).
+ *      Workspace is internal to the index object.  The tensor-core pass only nominates candidates; the reported
+ *      distances/order come from an exact fp32 re-rank (||q||^2+||x||^2-2q.x, clamped at 0 like faiss). */
+typedef struct cdml_index cdml_index;
+int cdml_knn_index_build(cdml_ctx* ctx, const float* X, int64_t N, int d, int64_t ldx, int metric, void* stream,
+                         cdml_index** out);
+int cdml_knn_index_destroy(cdml_index* index);
+int cdml_knn_search(cdml_ctx* ctx, cdml_index* index, const float* Q, int64_t nq, int64_t ldq, int k, float* D,
+                    int64_t* I, int64_t id_offset, void* stream);
+/* Counters of the last search: stats[0] = candidates nominated, [1] = queries that overflowed to the exact fallback. */
+int cdml_knn_last_stats(cdml_index* index, int64_t* stats);
+/* Merge G per-shard results [G,nq,k] into the global top-k (ties -> lower id). */
+int cdml_knn_merge(cdml_ctx* ctx, const float* Dg, const int64_t* Ig, int G, int64_t nq, int k, int metric, float* D,
+                   int64_t* I, void* stream);
+
+/* ---- evaluate.Evaluation.mean_dist (evaluate.py:57-73): mean_p sum_d (V[p0]-V[p1])^2, pairs int64 [P,2]. */
+int cdml_mean_pair_dist(cdml_ctx* ctx, const float* V, int64_t ld, int D, const int64_t* pairs, int64_t P,
+                        float* out_mean, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDML_H_ */

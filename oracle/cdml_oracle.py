@@ -1,0 +1,394 @@
+"""CPU oracle for the CDML hot path -- TEST INFRASTRUCTURE ONLY.
+
+This module restates, in plain numpy, the arithmetic of the reference
+(geekieo/collaborative-deep-metric-learning) hot path so that the CUDA kernels
+can be checked against it.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The
+product package never does; it fails loudly when ``libcdml.so`` is missing.
+
+Pinning status (see DESIGN.md "Oracle"):
+  * gather / negative sampler / eval mean_dist / knn_result line format /
+    feature-text reader: pinned against outputs of the reference's own Python
+    run in the build container (tests/golden/make_golden.py, fixtures committed).
+  * hinge loss: pinned against the known answers derived from the reference's
+    fixture tests/test_losses.py:13-18 (the reference asserts nothing itself).
+  * tower forward/backward, TF1 Adam, flat KNN: **parity unpinned** -- the
+    arithmetic lives in tensorflow-gpu==1.13.1 and faiss-gpu==1.5.x
+    (README.md:19-22), neither vendored nor installable here.  The oracle
+    restates their published semantics and is cross-checked by torch autograd,
+    finite differences and a second, independent exact-KNN statement
+    (show_knn.py:63-68).
+
+Every function cites the reference file:line it follows.  Default dtype is
+float64 ("what the maths says"); pass ``dtype=np.float32`` for the bit-level
+checks (gather, ids).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+L2_EPS = 1e-12          # tf.nn.l2_normalize default epsilon (models.py:58,61)
+LEAKY_ALPHA = 0.2       # tf.nn.leaky_relu default alpha (models.py:21)
+
+
+# --------------------------------------------------------------------------- #
+# reader / gather                                                             #
+# --------------------------------------------------------------------------- #
+def gather_rows(features: np.ndarray, guid_triplets) -> np.ndarray:
+  """inputs.py:158 -- ``FEATURES[np.asarray(guid_triplets)]`` -> [B,3,F]."""
+  return features[np.asarray(guid_triplets)]
+
+
+def flatten_triplets(batch: np.ndarray) -> np.ndarray:
+  """train.py:313 -- [B,3,F] -> [3B,F], row order a0,p0,n0,a1,..."""
+  return np.reshape(batch, (-1, batch.shape[-1]))
+
+
+def sample_negatives(pairs: np.ndarray, num_guid: int, rng: np.random.RandomState) -> np.ndarray:
+  """inputs.py:123-129 + parse_data.py:292-298 -- for each (a,p) draw
+  ``randint(0,num_guid)`` until it is not in {a,p}; returns [B,3] int64.
+  Draw order is one scalar ``randint`` call per attempt, exactly as the
+  reference's generator does, so a seeded RandomState reproduces its stream."""
+  out = np.empty((len(pairs), 3), dtype=np.int64)
+  for i, (a, p) in enumerate(np.asarray(pairs)):
+    n = rng.randint(0, num_guid)
+    while n == a or n == p:
+      n = rng.randint(0, num_guid)
+    out[i] = (a, p, n)
+  return out
+
+
+# --------------------------------------------------------------------------- #
+# tower (models.py:19-30, 41-62)                                              #
+# --------------------------------------------------------------------------- #
+def l2_normalize(x: np.ndarray, eps: float = L2_EPS) -> np.ndarray:
+  """tf.nn.l2_normalize(x, axis=-1): x * rsqrt(max(sum(x^2), eps))."""
+  ss = np.sum(np.square(x), axis=-1, keepdims=True)
+  return x / np.sqrt(np.maximum(ss, eps))
+
+
+def leaky_relu(z: np.ndarray, alpha: float = LEAKY_ALPHA) -> np.ndarray:
+  return np.where(z > 0, z, alpha * z)
+
+
+def fully_connected(x, W, b, alpha: float = LEAKY_ALPHA):
+  """models.py:19-30 -- slim.fully_connected: leaky_relu(x @ W + b); W is [in,out]."""
+  return leaky_relu(x @ W + b, alpha)
+
+
+def xavier_uniform(rng: np.random.RandomState, fan_in: int, fan_out: int, dtype=np.float32):
+  """slim default weights_initializer: U(-sqrt(6/(in+out)), +sqrt(6/(in+out)))."""
+  lim = np.sqrt(6.0 / (fan_in + fan_out))
+  return rng.uniform(-lim, lim, size=(fan_in, fan_out)).astype(dtype)
+
+
+def init_tower(dims, seed: int = 2, bias_init: float = 0.0, dtype=np.float32):
+  """dims = [F, H1, ..., D].  VNet (models.py:59-60): [1500, 5000, 256], bias 0."""
+  rng = np.random.RandomState(seed)
+  params = []
+  for fi, fo in zip(dims[:-1], dims[1:]):
+    params.append((xavier_uniform(rng, fi, fo, dtype), np.full((fo,), bias_init, dtype)))
+  return params
+
+
+def tower_forward(x, params, alpha: float = LEAKY_ALPHA, dtype=np.float64):
+  """models.py:46-62 (VNet) generalised to a stack of fully_connected layers.
+
+  Returns dict with ``xhat`` (normalised input), ``layers`` (post-activation
+  output of every FC layer; layers[-1] is "layer_2" for VNet), ``rinv``
+  (rsqrt(max(sum y^2,eps)) of the last layer) and ``l2_norm`` (the embedding).
+  """
+  x = np.asarray(x, dtype)
+  xhat = l2_normalize(x)
+  acts = []
+  h = xhat
+  for W, b in params:
+    h = fully_connected(h, np.asarray(W, dtype), np.asarray(b, dtype), alpha)
+    acts.append(h)
+  ss = np.sum(np.square(h), axis=-1, keepdims=True)
+  rinv = 1.0 / np.sqrt(np.maximum(ss, L2_EPS))
+  return {"xhat": xhat, "layers": acts, "rinv": rinv[:, 0], "l2_norm": h * rinv}
+
+
+# --------------------------------------------------------------------------- #
+# loss (losses.py:21-49)                                                      #
+# --------------------------------------------------------------------------- #
+def hinge_loss(triplets, margin: float = 0.1, dtype=np.float64):
+  """losses.py:33-38.  triplets [B,3,D] -> the 7-key dict of losses.py:43-49."""
+  t = np.asarray(triplets, dtype)
+  a, p, n = t[:, 0:1, :], t[:, 1:2, :], t[:, 2:3, :]
+  pos = np.sum(np.square(a - p), axis=-1)
+  neg = np.sum(np.square(a - n), axis=-1)
+  hinge = np.maximum(pos - neg + margin, 0)
+  return {"hinge_loss": np.mean(hinge), "anchors": a, "positives": p, "negatives": n,
+          "pos_dist": pos, "neg_dist": neg, "hinge_dist": hinge}
+
+
+def hinge_loss_grad(triplets, margin: float = 0.1, dtype=np.float64):
+  """d(mean hinge)/d(triplets): 2(n-p)/B, 2(p-a)/B, 2(a-n)/B on active rows."""
+  t = np.asarray(triplets, dtype)
+  B = t.shape[0]
+  a, p, n = t[:, 0], t[:, 1], t[:, 2]
+  r = hinge_loss(t, margin, dtype)
+  act = (r["hinge_dist"][:, 0] > 0)[:, None]
+  g = np.zeros_like(t)
+  g[:, 0] = np.where(act, 2 * (n - p) / B, 0)
+  g[:, 1] = np.where(act, 2 * (p - a) / B, 0)
+  g[:, 2] = np.where(act, 2 * (a - n) / B, 0)
+  return g
+
+
+def calc_var(triplets):
+  """train.py:67-71 -- mean((E - mean_{B,3}(E))^2)."""
+  mean = np.mean(triplets, axis=(0, 1))
+  return np.mean((triplets - mean) ** 2)
+
+
+# --------------------------------------------------------------------------- #
+# backward (autodiff of train.py:141-142 written out)                          #
+# --------------------------------------------------------------------------- #
+def tower_backward(fwd, params, dE, alpha: float = LEAKY_ALPHA, dtype=np.float64):
+  """Given forward cache and dL/d(l2_norm) [R,D] returns [(dW,db)] per layer.
+
+  l2norm:  dy = (g - e*(e.g)) * rinv   (rows with sum y^2 >= eps)
+  leaky :  dz = dy * (z>0 ? 1 : alpha)   (sign(z) == sign(leaky(z)))
+  dense :  dW = in^T dz ; db = sum_rows dz ; d_in = dz W^T
+  No gradient flows into xhat (placeholder input, train.py:265).
+  """
+  e = fwd["l2_norm"]
+  g = np.asarray(dE, dtype)
+  dy = (g - e * np.sum(e * g, axis=-1, keepdims=True)) * fwd["rinv"][:, None]
+  grads = [None] * len(params)
+  inputs = [fwd["xhat"]] + fwd["layers"][:-1]
+  d_out = dy
+  for li in range(len(params) - 1, -1, -1):
+    y = fwd["layers"][li]
+    dz = d_out * np.where(y > 0, 1.0, alpha)
+    W = np.asarray(params[li][0], dtype)
+    grads[li] = (inputs[li].T @ dz, np.sum(dz, axis=0))
+    if li > 0:
+      d_out = dz @ W.T
+  return grads
+
+
+# --------------------------------------------------------------------------- #
+# optimizer (train.py:82,108-113,146) -- TF1 AdamOptimizer                      #
+# --------------------------------------------------------------------------- #
+def exponential_decay(base_lr, global_step, decay_steps, decay_rate, staircase=True):
+  """tf.train.exponential_decay (train.py:108-113)."""
+  p = global_step / decay_steps
+  if staircase:
+    p = np.floor(p)
+  return base_lr * decay_rate ** p
+
+
+def adam_step_tf1(w, m, v, g, lr, t, beta1=0.9, beta2=0.999, eps=1e-8):
+  """TF1 ApplyAdam; ``t`` is the 1-based step count.
+  lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v EMA; w -= lr_t*m/(sqrt(v)+eps)."""
+  lr_t = lr * np.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+  m = beta1 * m + (1.0 - beta1) * g
+  v = beta2 * v + (1.0 - beta2) * g * g
+  w = w - lr_t * m / (np.sqrt(v) + eps)
+  return w, m, v
+
+
+class OracleTrainer:
+  """train.build_graph + Trainer._build_model constants (train.py:74-146, 210-222)
+  for Adam: clip off, reg penalty 0, lr decay 0.96 per 1e6 steps (staircase)."""
+
+  def __init__(self, params, lr=1e-3, margin=0.8, decay_steps=1000000, decay=0.96, dtype=np.float64):
+    self.dtype = dtype
+    self.params = [(np.asarray(W, dtype).copy(), np.asarray(b, dtype).copy()) for W, b in params]
+    self.m = [(np.zeros_like(W), np.zeros_like(b)) for W, b in self.params]
+    self.v = [(np.zeros_like(W), np.zeros_like(b)) for W, b in self.params]
+    self.lr, self.margin, self.decay_steps, self.decay = lr, margin, decay_steps, decay
+    self.global_step = 0
+
+  def loss_and_grads(self, x_rows):
+    fwd = tower_forward(x_rows, self.params, dtype=self.dtype)
+    E = fwd["l2_norm"].reshape(-1, 3, fwd["l2_norm"].shape[-1])
+    loss = hinge_loss(E, self.margin, self.dtype)
+    dE = hinge_loss_grad(E, self.margin, self.dtype).reshape(-1, E.shape[-1])
+    return fwd, loss, tower_backward(fwd, self.params, dE, dtype=self.dtype)
+
+  def step(self, x_rows):
+    fwd, loss, grads = self.loss_and_grads(x_rows)
+    lr = exponential_decay(self.lr, self.global_step, self.decay_steps, self.decay)
+    t = self.global_step + 1
+    for li, ((W, b), (gW, gb)) in enumerate(zip(self.params, grads)):
+      W2, mW, vW = adam_step_tf1(W, self.m[li][0], self.v[li][0], gW, lr, t)
+      b2, mb, vb = adam_step_tf1(b, self.m[li][1], self.v[li][1], gb, lr, t)
+      self.params[li], self.m[li], self.v[li] = (W2, b2), (mW, mb), (vW, vb)
+    self.global_step = t
+    return float(loss["hinge_loss"]), fwd, loss
+
+
+# --------------------------------------------------------------------------- #
+# in-batch semi-hard negative mining (SURVEY.md 8a row M -- build-defined)      #
+# --------------------------------------------------------------------------- #
+def mine_semihard(E, guid_triplets, margin, dtype=np.float64):
+  """E [3B,D] embeddings (rows a0,p0,n0,...), guid_triplets [B,3].
+
+  Candidates for triplet i: the positive and negative rows of every triplet
+  (row index r = 3j+1, 3j+2) whose guid is not a_i or p_i.  With
+  dp = |a_i-p_i|^2 and d_r = |a_i-E_r|^2 choose
+    (1) argmin d_r with dp < d_r < dp+margin (semi-hard), else
+    (2) argmin d_r with d_r >= dp+margin (easiest-to-violate beyond), else
+    (3) keep the reader's own negative row 3i+2.
+  Ties -> lowest row index.  Returns (neg_row [B] int32, d_an [B])."""
+  E = np.asarray(E, dtype)
+  g = np.asarray(guid_triplets)
+  B = g.shape[0]
+  cand_rows = np.stack([3 * np.arange(B) + 1, 3 * np.arange(B) + 2], 1).reshape(-1)
+  cand_guid = g[:, 1:3].reshape(-1)
+  C = E[cand_rows]
+  A = E[0::3]
+  P = E[1::3]
+  dp = np.sum((A - P) ** 2, -1)
+  neg_row = np.empty(B, np.int32)
+  d_an = np.empty(B, dtype)
+  cn = np.sum(C * C, -1)
+  for i in range(B):
+    d = np.sum(A[i] * A[i]) + cn - 2.0 * (C @ A[i])
+    ok = (cand_guid != g[i, 0]) & (cand_guid != g[i, 1])
+    semi = ok & (d > dp[i]) & (d < dp[i] + margin)
+    beyond = ok & (d >= dp[i] + margin)
+    if semi.any():
+      j = np.flatnonzero(semi)[np.argmin(d[semi])]
+    elif beyond.any():
+      j = np.flatnonzero(beyond)[np.argmin(d[beyond])]
+    else:
+      neg_row[i] = 3 * i + 2
+      d_an[i] = np.sum((A[i] - E[3 * i + 2]) ** 2)
+      continue
+    neg_row[i] = cand_rows[j]
+    d_an[i] = d[j]
+  return neg_row, d_an
+
+
+# --------------------------------------------------------------------------- #
+# exact flat KNN (faiss_knn.py:98-131 with IndexFlatL2 / IndexFlatIP semantics) #
+# --------------------------------------------------------------------------- #
+def knn_normalize(x: np.ndarray) -> np.ndarray:
+  """faiss_knn.py:99-104 -- rows /= ||row||_2 in float32 (no epsilon)."""
+  x = x.astype(np.float32)
+  return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+
+def flat_knn(xb, xq=None, k=51, l2_norm=True, metric="L2", block=4096, dtype=np.float32):
+  """calc_knn with an exact flat index.  D [nq,k] squared L2 ascending (or inner
+  product descending for metric="IP"), I [nq,k] int64.  Distances follow faiss's
+  BLAS path ||q||^2 + ||x||^2 - 2 q.x clamped at 0; ties -> lower id first.
+  Fewer than k database rows pads with +inf / -1 like faiss."""
+  xb = np.asarray(xb, np.float32)
+  if l2_norm:
+    xb = knn_normalize(xb)
+    xq = xb if xq is None else knn_normalize(np.asarray(xq, np.float32))
+  elif xq is None:
+    xq = xb
+  xb = xb.astype(dtype)
+  xq = np.asarray(xq, dtype)
+  nq, N = xq.shape[0], xb.shape[0]
+  kk = min(k, N)
+  D = np.full((nq, k), np.inf if metric == "L2" else -np.inf, np.float32)
+  I = np.full((nq, k), -1, np.int64)
+  bn = np.sum(xb * xb, 1)
+  for s in range(0, nq, block):
+    q = xq[s:s + block]
+    ip = q @ xb.T
+    if metric == "L2":
+      d = np.maximum(np.sum(q * q, 1)[:, None] + bn[None, :] - 2.0 * ip, 0)
+      key = d
+    else:
+      d = ip
+      key = -ip
+    # stable: sort by (key, id)
+    part = np.argpartition(key, kk - 1, axis=1)[:, :kk] if kk < N else np.tile(np.arange(N), (len(q), 1))
+    pk = np.take_along_axis(key, part, 1)
+    order = np.lexsort((part, pk), axis=1)
+    idx = np.take_along_axis(part, order, 1)
+    D[s:s + block, :kk] = np.take_along_axis(d, idx, 1)
+    I[s:s + block, :kk] = idx
+  return D, I
+
+
+def exact_ip_nn(embeddings, query_row, k):
+  """show_knn.py:63-68 -- independent statement: argsort(-(E @ e_q))[:k]."""
+  sims = embeddings @ embeddings[query_row]
+  return np.argsort(-sims, kind="stable")[:k]
+
+
+def knn_merge(D_parts, I_parts, k, metric="L2"):
+  """Sharded-index merge: parts [G,nq,k] -> global top-k,
+  ties -> lower id.  Ids already carry their shard offset."""
+  D = np.concatenate(list(D_parts), axis=1)
+  I = np.concatenate(list(I_parts), axis=1)
+  key = D if metric == "L2" else -D
+  key = np.where(I < 0, np.inf, key)
+  order = np.lexsort((I, key), axis=1)[:, :k]
+  return np.take_along_axis(D, order, 1), np.take_along_axis(I, order, 1)
+
+
+# --------------------------------------------------------------------------- #
+# result writer (faiss_knn.py:267-283) and eval (evaluate.py:57-73)            #
+# --------------------------------------------------------------------------- #
+def format_knn_rows(begin_index, D, I, decode_map):
+  """write_process: '<query_guid>,<nbr_guid>#<dist><...\\n'; skips column 0 and
+  keeps a neighbour only if idx > 0 and 0.0 < dist < 1.4; dist via str(np.float32)."""
+  lines = []
+  for i in range(I.shape[0]):
+    topks = "".join(
+      decode_map[int(j)] + "#" + str(np.float32(d)) + "<"
+      if (j > 0 and d > 0.0 and d < 1.4) else ""
+      for j, d in zip(I[i][1:], D[i][1:]))
+    lines.append(decode_map[begin_index + i] + "," + topks + "\n")
+  return lines
+
+
+def split_ranges(total, split_num):
+  """write_knn patching (faiss_knn.py:288-301): split_num contiguous patches,
+  the last takes the remainder."""
+  patch = total // split_num
+  return [(i * patch, (i + 1) * patch if i < split_num - 1 else total) for i in range(split_num)]
+
+
+def mean_dist(vectors, cowatches):
+  """evaluate.py:57-73 -- mean squared L2 over cowatch pairs."""
+  co = np.asarray(vectors)[np.asarray(cowatches)]
+  return np.mean(np.sum((co[:, 0, :] - co[:, 1, :]) ** 2, axis=-1))
+
+
+def rencode_eval(features, cowatches):
+  """evaluate.py:34-55 -- compact eval guids to 0..U-1 in sorted order."""
+  uniq = np.unique(np.asarray(cowatches).reshape(-1))
+  remap = {int(o): i for i, o in enumerate(uniq)}
+  return features[uniq], [[remap[int(a)], remap[int(b)]] for a, b in cowatches]
+
+
+# --------------------------------------------------------------------------- #
+# seeded synthetic inputs (imitation_data.py:41-53 but seeded)     #
+# --------------------------------------------------------------------------- #
+def synth_features(num_guid, feature_size, seed=0, decimals=8):
+  """imitation_data.gen_features: around(U[0,1), 8) -- here with RandomState(seed), float32."""
+  return np.around(np.random.RandomState(seed).random_sample((num_guid, feature_size)), decimals).astype(np.float32)
+
+
+def synth_pairs(num_pairs, num_guid, seed=1):
+  """cowatch pairs a != p, uniform over guids."""
+  rng = np.random.RandomState(seed)
+  a = rng.randint(0, num_guid, size=num_pairs)
+  p = (a + 1 + rng.randint(0, num_guid - 1, size=num_pairs)) % num_guid
+  return np.stack([a, p], 1).astype(np.int64)
+
+
+def synth_triplets(num, num_guid, seed=1):
+  """[num,3] int64 with n not in {a,p} (vectorised equivalent of inputs.py:123-129
+  in distribution; use sample_negatives for stream-exact draws)."""
+  rng = np.random.RandomState(seed)
+  ap = synth_pairs(num, num_guid, seed)
+  n = rng.randint(0, num_guid, size=num)
+  bad = (n == ap[:, 0]) | (n == ap[:, 1])
+  while bad.any():
+    n[bad] = rng.randint(0, num_guid, size=int(bad.sum()))
+    bad = (n == ap[:, 0]) | (n == ap[:, 1])
+  return np.concatenate([ap, n[:, None]], 1).astype(np.int64)
