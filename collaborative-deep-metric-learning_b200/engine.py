@@ -1,0 +1,239 @@
+"""Tower engine: the reference's `build_graph` (train.py:74-175) + `Prediction.predict` (predict.py:67-69) executed by
+libcdml kernels.  Owns the fp32 master weights / Adam state (one flat buffer each, so the data-parallel gradient
+exchange is a single all-reduce), the 16-bit shadow weights the tensor cores read, and the per-batch activation
+buffers.  Every arithmetic step is a C-ABI call; torch only allocates memory and (for N>1 ranks) runs the NCCL
+all-reduce of the flat gradient buffer.
+
+Forward (models.py:46-62 and `fully_connected` models.py:19-30), per row of the [3B,F] batch:
+  xhat = l2norm(x) -> h_l = leaky(h_{l-1} W_l + b_l) for every layer (also the last) -> e = l2norm(h_L)
+Backward = the written-out autodiff of train.py:141-142 (see oracle/cdml_oracle.py::tower_backward).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import BF16, EPI_L2NORM, EPI_MASK_LEAKY, EPI_STORE_16, EPI_STORE_F32, F16
+
+LEAKY_ALPHA = 0.2
+
+
+def _pad8(n):
+  return (n + 7) // 8 * 8
+
+
+class TowerEngine:
+  """Stack of `fully_connected` layers with input/output L2-normalisation (VNet: dims=[1500,5000,256])."""
+
+  def __init__(self, dims, device=None, dtype16=F16, seed=2, bias_init=0.0, base_lr=1e-3, margin=0.8,
+               lr_decay_steps=1000000, lr_decay=0.96, beta1=0.9, beta2=0.999, eps=1e-8, alpha=LEAKY_ALPHA,
+               process_group=None, init_params=None):
+    if not torch.cuda.is_available():
+      raise RuntimeError("TowerEngine needs a CUDA device (sm_100a); there is no CPU path")
+    self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+    self.dims = [int(d) for d in dims]
+    if self.dims[-1] > 256:
+      raise ValueError("output_size must be <= 256 (the L2-norm epilogue holds the whole row in one tile)")
+    for d in self.dims[1:]:
+      if d % 8:
+        raise ValueError("layer widths must be multiples of 8 (16-byte row pitch for TMA); got %d" % d)
+    self.L = len(self.dims) - 1
+    self.dtype16 = dtype16
+    self.t16 = ops.TORCH16[dtype16]
+    self.alpha = float(alpha)
+    self.margin = float(margin)
+    self.base_lr, self.lr_decay_steps, self.lr_decay = float(base_lr), float(lr_decay_steps), float(lr_decay)
+    self.beta1, self.beta2, self.eps = beta1, beta2, eps
+    self.pg = process_group
+    self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+    self.F = self.dims[0]
+    self.F_pad = _pad8(self.F)
+
+    # ---- flat fp32 parameter / gradient / Adam buffers; per-tensor views ----
+    sizes = []
+    for fi, fo in zip(self.dims[:-1], self.dims[1:]):
+      sizes += [fi * fo, fo]
+    self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    # keep every tensor 16-byte aligned inside the flat buffer
+    self.offsets = np.concatenate([[0], np.cumsum([_pad8(s) for s in sizes])]).astype(np.int64)
+    total = int(self.offsets[-1])
+    dev = self.device
+    self.w = torch.zeros(total, dtype=torch.float32, device=dev)
+    self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+    self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+    self.g = torch.zeros(total, dtype=torch.float32, device=dev)
+    self.sizes = sizes
+    self.W = [self._view(self.w, 2 * l).view(self.dims[l], self.dims[l + 1]) for l in range(self.L)]
+    self.b = [self._view(self.w, 2 * l + 1) for l in range(self.L)]
+    self.gW = [self._view(self.g, 2 * l).view(self.dims[l], self.dims[l + 1]) for l in range(self.L)]
+    self.gb = [self._view(self.g, 2 * l + 1) for l in range(self.L)]
+    self.W16 = [torch.zeros((self.dims[l], self.dims[l + 1]), dtype=self.t16, device=dev) for l in range(self.L)]
+    self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)
+    self._bufs = {}
+    self._ws = {}
+
+    if init_params is None:
+      rng = np.random.RandomState(seed)
+      init_params = []
+      for fi, fo in zip(self.dims[:-1], self.dims[1:]):
+        lim = math.sqrt(6.0 / (fi + fo))  # slim xavier_initializer (uniform)
+        init_params.append((rng.uniform(-lim, lim, size=(fi, fo)).astype(np.float32),
+                            np.full((fo,), bias_init, np.float32)))
+    self.load_params(init_params)
+
+  # ------------------------------------------------------------------ parameters
+  def _view(self, flat, i):
+    o = int(self.offsets[i])
+    return flat[o:o + self.sizes[i]]
+
+  def load_params(self, params):
+    """params: [(W [in,out], b [out])] numpy / torch, e.g. from a checkpoint or the oracle's init."""
+    for l, (W, b) in enumerate(params):
+      self.W[l].copy_(torch.as_tensor(np.asarray(W), dtype=torch.float32))
+      self.b[l].copy_(torch.as_tensor(np.asarray(b), dtype=torch.float32))
+    self.refresh_shadows()
+
+  def refresh_shadows(self):
+    for l in range(self.L):
+      ops.cast16(self.W[l], self.W16[l])
+
+  def get_params(self):
+    return [(self.W[l].detach().cpu().numpy().copy(), self.b[l].detach().cpu().numpy().copy()) for l in range(self.L)]
+
+  def state_dict(self):
+    return {"dims": self.dims, "w": self.w.cpu().numpy(), "m": self.m.cpu().numpy(), "v": self.v.cpu().numpy(),
+            "step": int(self.step_counter.item())}
+
+  def load_state_dict(self, sd):
+    self.w.copy_(torch.as_tensor(sd["w"]))
+    self.m.copy_(torch.as_tensor(sd["m"]))
+    self.v.copy_(torch.as_tensor(sd["v"]))
+    self.step_counter.fill_(int(sd["step"]))
+    self.refresh_shadows()
+
+  @property
+  def global_step(self):
+    return int(self.step_counter.item())
+
+  # ------------------------------------------------------------------ buffers
+  def _buffers(self, R, train):
+    key = (R, train)
+    buf = self._bufs.get(key)
+    if buf is not None:
+      return buf
+    dev, t16 = self.device, self.t16
+    D = self.dims[-1]
+    buf = {"acts": [torch.empty((R, self.dims[l + 1]), dtype=t16, device=dev) for l in range(self.L - 1)],
+           "e": torch.empty((R, D), dtype=torch.float32, device=dev),
+           "rinv": torch.empty((R,), dtype=torch.float32, device=dev)}
+    if train:
+      B = R // 3
+      buf["dz"] = [torch.empty((R, self.dims[l + 1]), dtype=t16, device=dev) for l in range(self.L)]
+      buf["G"] = torch.empty((R, D), dtype=torch.float32, device=dev)
+      buf["loss"] = {k: torch.empty((B,), dtype=torch.float32, device=dev) for k in ("pos_dist", "neg_dist", "hinge_dist")}
+      buf["loss"]["stats"] = torch.empty((4,), dtype=torch.float32, device=dev)
+      buf["splits"] = [ops.auto_splits(self.w, self.dims[l], self.dims[l + 1], R) for l in range(self.L)]
+      part = max(s * self.dims[l] * self.dims[l + 1] if s > 1 else 0 for l, s in enumerate(buf["splits"]))
+      buf["partials"] = torch.empty((max(part, 1),), dtype=torch.float32, device=dev)
+      buf["colsum_ws"] = torch.empty((max(ops.colsum_workspace_floats(R, d) for d in self.dims[1:]),),
+                                     dtype=torch.float32, device=dev)
+    if len(self._bufs) > 4:
+      self._bufs.clear()
+    self._bufs[key] = buf
+    return buf
+
+  # ------------------------------------------------------------------ forward
+  def forward_rows(self, x16, R, train=False, want_e16=None):
+    """x16: 16-bit [R, >=F] already-normalised input rows.  Returns the buffer dict (e, rinv, acts)."""
+    buf = self._buffers(R, train)
+    h = x16
+    for l in range(self.L):
+      K, N = self.dims[l], self.dims[l + 1]
+      if l < self.L - 1:
+        ops.gemm16(h, self.W16[l], R, N, K, 0, 1, EPI_STORE_16, buf["acts"][l], bias=self.b[l], alpha=self.alpha)
+        h = buf["acts"][l]
+      else:
+        ops.gemm16(h, self.W16[l], R, N, K, 0, 1, EPI_L2NORM, buf["e"], bias=self.b[l], alpha=self.alpha,
+                   aux0=buf["rinv"], aux1=want_e16)
+    return buf
+
+  def embed(self, x, batch_rows=None):
+    """Prediction.predict (predict.py:67-69): fp32 [n,F] raw features -> fp32 [n,D] embeddings (device tensor)."""
+    n = x.shape[0]
+    x16, _, _ = ops.rows_normalize_cast(x, self.dtype16, 1, 1e-12, ld_out=self.F_pad)
+    buf = self.forward_rows(x16, n, train=False)
+    return buf["e"]
+
+  # ------------------------------------------------------------------ training
+  def prepare_table(self, features):
+    """K2 folded into a one-off table transform: fp32 [G,F] -> L2-normalised 16-bit [G,F_pad] resident in HBM."""
+    x16, _, _ = ops.rows_normalize_cast(features, self.dtype16, 1, 1e-12, ld_out=self.F_pad)
+    return x16
+
+  def train_step_indices(self, table16, idx, mine=False, guid=None):
+    """One optimisation step from guid index triplets [B,3] (device int32/int64): gather -> fwd -> loss -> bwd -> Adam."""
+    B = idx.shape[0]
+    x16 = self._ws.get(("x16", B))
+    if x16 is None:
+      x16 = self._ws[("x16", B)] = torch.empty((3 * B, self.F_pad), dtype=self.t16, device=self.device)
+    ops.gather_rows(table16, idx, out=x16)
+    return self.train_step_rows(x16, B, mine=mine, guid=idx if guid is None else guid)
+
+  def train_step_rows(self, x16, B, mine=False, guid=None):
+    R = 3 * B
+    D = self.dims[-1]
+    e16 = None
+    if mine:
+      e16 = self._ws.get(("e16", R))
+      if e16 is None:
+        e16 = self._ws[("e16", R)] = torch.empty((R, D), dtype=self.t16, device=self.device)
+    buf = self.forward_rows(x16, R, train=True, want_e16=e16)
+    neg_row = None
+    if mine:
+      neg_row, _ = ops.mine_semihard(e16, buf["e"], guid, B, self.margin, want_dist=False)
+    dz = buf["dz"]
+    # loss + backward through the output L2-norm and last leaky (gradients of the SUM of hinges; 1/B goes into Adam)
+    ops.triplet_hinge(buf["e"], B, self.margin, neg_row=neg_row, grad_scale=1.0, rinv=buf["rinv"],
+                      leaky_alpha=self.alpha, dz16=dz[self.L - 1], workspace=buf["G"], out=buf["loss"])
+    self.backward_rows(x16, R, buf)
+    self.apply_gradients(B)
+    return buf["loss"]["stats"]
+
+  def backward_rows(self, x16, R, buf):
+    dz = buf["dz"]
+    for l in range(self.L - 1, -1, -1):
+      K_in, N_out = self.dims[l], self.dims[l + 1]
+      inp = x16 if l == 0 else buf["acts"][l - 1]
+      s = buf["splits"][l]
+      # weight gradient: dW[in,out] = inp^T[in,R] . dz[R,out]   (both operands MN-major, K = R)
+      if s > 1:
+        used = ops.gemm16(inp, dz[l], K_in, N_out, R, 1, 1, EPI_STORE_F32, buf["partials"], num_splits=s,
+                          split_stride=K_in * N_out)
+        ops.sum_partials(buf["partials"], used, K_in * N_out, K_in * N_out, self.gW[l])
+      else:
+        ops.gemm16(inp, dz[l], K_in, N_out, R, 1, 1, EPI_STORE_F32, self.gW[l])
+      ops.colsum16(dz[l], R, N_out, self.gb[l], buf["colsum_ws"])
+      if l > 0:
+        # data gradient + leaky' of the previous layer: dz[l-1] = (dz[l] . W_l^T) * leaky'(h_{l-1})
+        ops.gemm16(dz[l], self.W16[l], R, K_in, N_out, 0, 0, EPI_MASK_LEAKY, dz[l - 1], alpha=self.alpha,
+                   aux1=buf["acts"][l - 1])
+
+  def apply_gradients(self, B_local):
+    if self.world > 1:
+      torch.distributed.all_reduce(self.g, group=self.pg)  # NCCL sum over ranks, one flat buffer
+    ops.adam_prepare(self.step_counter, self.scalars, self.base_lr, self.lr_decay_steps, self.lr_decay, True,
+                     self.beta1, self.beta2)
+    scale = 1.0 / (B_local * self.world)
+    for l in range(self.L):
+      ops.adam_apply(self.W[l], self._view(self.m, 2 * l), self._view(self.v, 2 * l), self.gW[l], self.scalars,
+                     self.beta1, self.beta2, self.eps, scale, w16=self.W16[l])
+      ops.adam_apply(self.b[l], self._view(self.m, 2 * l + 1), self._view(self.v, 2 * l + 1), self.gb[l], self.scalars,
+                     self.beta1, self.beta2, self.eps, scale)
+
+  # loss only (no update) -- used by tests and by the summaries of train.py
+  def loss_rows(self, x16, B):
+    buf = self.forward_rows(x16, 3 * B, train=True)
+    ops.triplet_hinge(buf["e"], B, self.margin, out=buf["loss"])
+    return buf

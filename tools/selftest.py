@@ -36,10 +36,11 @@ def mk(shape, dt, scale=1.0):
 
 
 def gemm_case(M, N, K, amn, bmn, dt=torch.float16, splits=1, tag=""):
-  A = mk((K, M) if amn else (M, K), dt)
-  B = mk((K, N) if bmn else (N, K), dt)
-  Af = A.float().t() if amn else A.float()
-  Bf = B.float() if bmn else B.float().t()
+  p8 = lambda n: (n + 7) // 8 * 8
+  A = mk((K, p8(M)) if amn else (M, p8(K)), dt)
+  B = mk((K, p8(N)) if bmn else (N, p8(K)), dt)
+  Af = A.float()[:, :M].t() if amn else A.float()[:, :K]
+  Bf = B.float()[:, :N] if bmn else B.float()[:, :K].t()
   ref = Af @ Bf
   if splits == 1:
     out = torch.full((M, N), float("nan"), device=dev)
