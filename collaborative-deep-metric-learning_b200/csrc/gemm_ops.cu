@@ -1,68 +1,7 @@
 // Host launchers + C ABI for the tcgen05 GEMM family (cdml_gemm16).
-#include "../../include/cdml.h"
-#include "ctx.cuh"
-#include "gemm_sm100.cuh"
+#include "gemm_launch.cuh"
 
 namespace cdml {
-
-constexpr int kBN = 256;
-constexpr int kStages = 4;
-
-static int pick_splits(int num_sms, int tiles, int num_kb) {
-  // Few output tiles but a long K (weight gradients): split K so that tiles*S fills whole waves of SMs.
-  if (tiles >= 2 * num_sms || num_kb < 16) return 1;
-  const int smax = max(1, min(64, num_kb / 8));
-  int best = 1;
-  double best_eff = -1.0;
-  for (int s = 1; s <= smax; ++s) {
-    const int per = (num_kb + s - 1) / s;
-    const int seff = (num_kb + per - 1) / per;
-    if (seff != s) continue;
-    const long units = static_cast<long>(tiles) * s;
-    const long waves = (units + num_sms - 1) / num_sms;
-    double eff = static_cast<double>(units) / static_cast<double>(waves * num_sms);
-    if (units < num_sms) eff *= 0.5;          // leaves SMs idle
-    eff -= 0.002 * s;                          // partial-buffer traffic: prefer fewer splits on ties
-    if (eff > best_eff) best_eff = eff, best = s;
-  }
-  return best;
-}
-
-template <int AMN, int BMN, class Epi>
-static int launch_gemm(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
-                       int64_t K, int dtype16, int num_splits, const Epi& epi, cudaStream_t stream) {
-  using L = GemmSmem<kBN, kStages>;
-  CUtensorMap ta, tb;
-  int rc;
-  if (AMN == 0) rc = make_tmap_2d(ctx, &ta, A, dtype16, K, M, lda, kBK, kBM);
-  else rc = make_tmap_2d(ctx, &ta, A, dtype16, M, K, lda, 64, kBK);
-  if (rc) return rc;
-  if (BMN == 0) rc = make_tmap_2d(ctx, &tb, B, dtype16, K, N, ldb, kBK, kBN);
-  else rc = make_tmap_2d(ctx, &tb, B, dtype16, N, K, ldb, 64, kBK);
-  if (rc) return rc;
-
-  GemmShape s;
-  s.M = static_cast<int>(M), s.N = static_cast<int>(N), s.K = static_cast<int>(K);
-  s.m_tiles = (s.M + kBM - 1) / kBM;
-  s.n_tiles = (s.N + kBN - 1) / kBN;
-  s.num_kb = (s.K + kBK - 1) / kBK;
-  num_splits = max(1, min(num_splits, s.num_kb));
-  s.kb_per_split = (s.num_kb + num_splits - 1) / num_splits;
-  s.num_splits = (s.num_kb + s.kb_per_split - 1) / s.kb_per_split;
-  s.idesc = make_idesc_f16(dtype16 == CDML_BF16 ? 1 : 0, AMN, BMN, kBM, kBN);
-
-  auto kern = gemm_tcgen05_kernel<AMN, BMN, kBN, kStages, Epi>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    CDML_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    attr_set = true;
-  }
-  const long units = static_cast<long>(s.m_tiles) * s.n_tiles * s.num_splits;
-  const int grid = static_cast<int>(units < ctx->num_sms ? units : ctx->num_sms);
-  kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, s, epi);
-  CDML_CHECK_CUDA(cudaGetLastError());
-  return s.num_splits;
-}
 
 template <int AMN, int BMN>
 static int dispatch_epilogue(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,

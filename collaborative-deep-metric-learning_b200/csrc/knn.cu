@@ -1,11 +1,630 @@
-// placeholder until the KNN kernels land (same commit series)
-#include "../../include/cdml.h"
-#include "ctx.cuh"
-extern "C" {
-int cdml_mine_semihard(cdml_ctx*, const void*, int64_t, int, const float*, int64_t, const int64_t*, int64_t, int, float, int32_t*, float*, void*) { cdml::set_error("cdml_mine_semihard: not built yet"); return -3; }
-int cdml_knn_index_build(cdml_ctx*, const float*, int64_t, int, int64_t, int, void*, cdml_index**) { cdml::set_error("knn: not built yet"); return -3; }
-int cdml_knn_index_destroy(cdml_index*) { return 0; }
-int cdml_knn_search(cdml_ctx*, cdml_index*, const float*, int64_t, int64_t, int, float*, int64_t*, int64_t, void*) { cdml::set_error("knn: not built yet"); return -3; }
-int cdml_knn_last_stats(cdml_index*, int64_t*) { return -3; }
-int cdml_knn_merge(cdml_ctx*, const float*, const int64_t*, int, int64_t, int, int, float*, int64_t*, void*) { cdml::set_error("knn: not built yet"); return -3; }
+// Exact flat KNN (IndexFlatL2 / IndexFlatIP semantics, faiss_knn.py:116-128) on the tcgen05 GEMM core.
+//
+// The nq x N score matrix never reaches HBM.  Per query chunk:
+//   pass A  (sample)   S = Q16 . Xs16^T  over ~N/8 evenly spaced index rows; the epilogue keeps, per query, the best
+//                      score of every 32-row group.  The k-th best group score is a LOWER bound of the k-th best score
+//                      over the whole index (k distinct rows reach it).
+//   pass B  (collect)  S = X16 . Q16^T   over the whole index; the epilogue appends (row, score) to the query's
+//                      candidate list when score > bound - 2*eps, eps = a rigorous bound of the fp16 rounding error,
+//                      so every true top-k row is nominated.  Warp-uniform ballot per column: no divergence.
+//   refine             per query: prune by approximate score (again with the 2*eps guard), recompute the survivors in
+//                      exact fp32 (||q||^2 + ||x||^2 - 2 q.x, clamped at 0 like faiss), sort by (distance, id), emit k.
+// Queries whose list overflows (mass duplicates) take an exact fp32 brute-force path.
+// score s = q.x - ||x||^2/2 (L2; ranking by s descending == distance ascending) or q.x (IP).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include <vector>
+
+#include "gemm_launch.cuh"
+
+namespace cdml {
+
+constexpr int kCandCap = 2048;   // candidate list capacity per query
+constexpr int kKeepCap = 1024;   // survivors of the approximate prune that get an exact re-rank
+constexpr int kMaxGroups = 4096; // sample groups per query (sample <= 131072 rows)
+constexpr int kRefineThreads = 256;
+
+__device__ __forceinline__ uint32_t f2key(float f) {  // order-preserving float -> uint32
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+__device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
+__device__ __forceinline__ float pos_inf() { return __int_as_float(0x7f800000); }
+
+// ---- pass A epilogue: thread <-> query row; best score of each 32-column (index-row) group ----
+template <int BN>
+struct EpiKnnGroupMax {
+  const float* h;  // [Ns] ||x||^2/2 of the sampled rows (zeros for IP)
+  float* gmax;     // [nq, ldg]
+  int64_t ldg;
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
+    float g[BN / 32];
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nb = n0 + c * 32;
+      float best = neg_inf();
+      if (nb < s.N) {  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = nb + j;
+          const float sc = col < s.N ? __uint_as_float(v[j]) - __ldg(h + col) : neg_inf();
+          best = fmaxf(best, sc);
+        }
+      }
+      g[c] = best;
+    }
+    if (row < s.M) {
+      float4* p = reinterpret_cast<float4*>(gmax + static_cast<int64_t>(row) * ldg + n0 / 32);
+#pragma unroll
+      for (int c = 0; c < BN / 128; ++c) p[c] = make_float4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
+    }
+  }
+};
+
+// ---- pass B epilogue: thread <-> index row, column <-> query; ballot + append ----
+template <int BN>
+struct EpiKnnCollect {
+  const float* h;    // [N] ||x||^2/2 (zeros for IP)
+  const float* thr;  // [nq] score bound per query
+  int32_t* cand_idx; // [nq, cap]
+  float* cand_val;   // [nq, cap]
+  int32_t* cnt;      // [nq]
+  int cap;
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
+    const int lane = threadIdx.x & 31;
+    const bool row_ok = row < s.M;
+    const float hr = row_ok ? __ldg(h + row) : 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nb = n0 + c * 32;
+      if (nb >= s.N) break;
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      const float t_lane = nb + lane < s.N ? __ldg(thr + nb + lane) : pos_inf();
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float sc = row_ok ? __uint_as_float(v[j]) - hr : neg_inf();
+        const float tj = __shfl_sync(0xffffffffu, t_lane, j);
+        const bool pass = sc > tj;
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m != 0u) {  // warp-uniform, rare
+          const int q = nb + j;
+          const int leader = __ffs(m) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(cnt + q, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (pass) {
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            if (pos < cap) {
+              cand_idx[static_cast<int64_t>(q) * cap + pos] = row;
+              cand_val[static_cast<int64_t>(q) * cap + pos] = sc;
+            }
+          }
+        }
+      }
+    }
+  }
+};
+
+// ---- small helpers -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+row_sumsq32_kernel(const float* __restrict__ X, int64_t n, int d, int64_t ld, float* __restrict__ ss, float half_scale,
+                   float* __restrict__ half_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + warp; r < n; r += static_cast<int64_t>(gridDim.x) * 8) {
+    const float* x = X + r * ld;
+    float a = 0.f;
+    for (int j = lane; j < d; j += 32) a = fmaf(x[j], x[j], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      ss[r] = a;
+      if (half_out != nullptr) half_out[r] = a * half_scale;
+    }
+  }
+}
+
+__global__ void max_reduce_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float m = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, x[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) *out = m;
+  }
+}
+
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    p[i] = v;
+}
+
+// block-wide sum of an int (all threads get the result)
+__device__ __forceinline__ int block_sum(int v, int* sh) {
+  v = __reduce_add_sync(0xffffffffu, v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = 0;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) t += sh[w];
+  return t;
+}
+
+// k-th best sampled group score per query -> collection bound  thr = kth - slack(q)
+__global__ void __launch_bounds__(kRefineThreads)
+knn_kth_kernel(const float* __restrict__ gmax, int64_t ldg, int G, int k, const float* __restrict__ qss,
+               float slack_scale, float slack_abs, float* __restrict__ thr) {
+  __shared__ int sh[kRefineThreads / 32];
+  const int q = blockIdx.x;
+  const float* g = gmax + static_cast<int64_t>(q) * ldg;
+  constexpr int kPer = kMaxGroups / kRefineThreads;
+  uint32_t keys[kPer];
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int j = threadIdx.x + i * kRefineThreads;
+    keys[i] = j < G ? f2key(g[j]) : 0u;
+  }
+  uint32_t T = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) c += keys[i] >= cand ? 1 : 0;
+    if (block_sum(c, sh) >= k) T = cand;
+  }
+  if (threadIdx.x == 0) {
+    const float kth = key2f(T);
+    const bool finite = T > f2key(neg_inf());
+    thr[q] = finite ? kth - (slack_scale * sqrtf(qss[q]) + slack_abs) : neg_inf();
+  }
+}
+
+// Per query: approximate prune -> exact fp32 re-rank -> (distance,id) sort -> top-k.
+__global__ void __launch_bounds__(kRefineThreads)
+knn_refine_kernel(const float* __restrict__ Q, int64_t ldq, int d, const float* __restrict__ qss,
+                  const float* __restrict__ X, int64_t ldx, const float* __restrict__ xss,
+                  const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_val,
+                  const int32_t* __restrict__ cnt, int cap, int k, int metric, float slack_scale, float slack_abs,
+                  int64_t id_offset, float* __restrict__ D, int64_t* __restrict__ I, int64_t out_ld,
+                  int32_t* __restrict__ overflow) {
+  __shared__ uint32_t skey[kCandCap];
+  __shared__ int32_t sidx[kCandCap];
+  __shared__ unsigned long long kept[kKeepCap];
+  __shared__ int sh[kRefineThreads / 32];
+  __shared__ int n_keep;
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int n = cnt[q];
+  if (n > cap) {  // too many nominees (mass ties): exact fallback handles this query
+    if (tid == 0) overflow[q] = 1;
+    return;
+  }
+  for (int i = tid; i < n; i += kRefineThreads) {
+    skey[i] = f2key(cand_val[static_cast<int64_t>(q) * cap + i]);
+    sidx[i] = cand_idx[static_cast<int64_t>(q) * cap + i];
+  }
+  if (tid == 0) n_keep = 0;
+  __syncthreads();
+  // k-th best approximate score among the nominees
+  uint32_t T = 0;
+  if (n > k) {
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = T | (1u << bit);
+      int c = 0;
+      for (int i = tid; i < n; i += kRefineThreads) c += skey[i] >= cand ? 1 : 0;
+      if (block_sum(c, sh) >= k) T = cand;
+    }
+  }
+  const float slack = slack_scale * sqrtf(qss[q]) + slack_abs;
+  const uint32_t keep_key = n > k ? f2key(key2f(T) - slack) : 0u;
+  for (int i = tid; i < n; i += kRefineThreads) {
+    if (skey[i] >= keep_key) {
+      const int pos = atomicAdd(&n_keep, 1);
+      if (pos < kKeepCap) kept[pos] = static_cast<unsigned long long>(static_cast<uint32_t>(sidx[i]));
+    }
+  }
+  __syncthreads();
+  const int nk = n_keep;
+  if (nk > kKeepCap) {
+    if (tid == 0) overflow[q] = 1;
+    return;
+  }
+  // exact fp32 scores of the survivors: one warp per candidate
+  const int warp = tid >> 5, lane = tid & 31;
+  const float* qv = Q + static_cast<int64_t>(q) * ldq;
+  const float qn = qss[q];
+  for (int i = warp; i < nk; i += kRefineThreads / 32) {
+    const uint32_t id = static_cast<uint32_t>(kept[i]);
+    const float* xv = X + static_cast<int64_t>(id) * ldx;
+    float dot = 0.f;
+    for (int j = lane; j < d; j += 32) dot = fmaf(qv[j], xv[j], dot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) {
+      const float key = metric == 0 ? fmaxf(qn + xss[id] - 2.f * dot, 0.f) : -dot;
+      kept[i] = (static_cast<unsigned long long>(f2key(key)) << 32) | id;
+    }
+  }
+  int P = 1;
+  while (P < nk) P <<= 1;
+  if (P < 2) P = 2;
+  for (int i = nk + tid; i < P; i += kRefineThreads) kept[i] = ~0ull;
+  __syncthreads();
+  // bitonic sort ascending on (distance key, id)
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (P >> 1); t += kRefineThreads) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long a = kept[lo], b = kept[hi];
+        if ((a > b) == up) kept[lo] = b, kept[hi] = a;
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < k; i += kRefineThreads) {
+    float dist;
+    int64_t id;
+    if (i < nk) {
+      const float key = key2f(static_cast<uint32_t>(kept[i] >> 32));
+      dist = metric == 0 ? key : -key;
+      id = static_cast<int64_t>(static_cast<uint32_t>(kept[i])) + id_offset;
+    } else {  // fewer than k database rows: faiss pads with inf / -1
+      dist = metric == 0 ? pos_inf() : neg_inf();
+      id = -1;
+    }
+    D[static_cast<int64_t>(q) * out_ld + i] = dist;
+    I[static_cast<int64_t>(q) * out_ld + i] = id;
+  }
+}
+
+// ---- exact fallback (rare): one query against every row in fp32 ----
+__global__ void __launch_bounds__(256)
+knn_exact_keys_kernel(const float* __restrict__ qv, int d, float qn, const float* __restrict__ X, int64_t N, int64_t ldx,
+                      const float* __restrict__ xss, int metric, unsigned long long* __restrict__ keys) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + warp; r < N; r += static_cast<int64_t>(gridDim.x) * 8) {
+    const float* xv = X + r * ldx;
+    float dot = 0.f;
+    for (int j = lane; j < d; j += 32) dot = fmaf(qv[j], xv[j], dot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) {
+      const float key = metric == 0 ? fmaxf(qn + xss[r] - 2.f * dot, 0.f) : -dot;
+      keys[r] = (static_cast<unsigned long long>(f2key(key)) << 32) | static_cast<uint32_t>(r);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+knn_exact_select_kernel(const unsigned long long* __restrict__ keys, int64_t N, int k, int metric, int64_t id_offset,
+                        float* __restrict__ D, int64_t* __restrict__ I) {
+  __shared__ int sh[32];
+  __shared__ unsigned long long best[1024];
+  __shared__ int nb;
+  const int tid = threadIdx.x;
+  const int kk = static_cast<int>(N < k ? N : k);
+  // T = kk-th smallest key: largest T with fewer than kk keys strictly below it
+  unsigned long long T = 0;
+  for (int bit = 63; bit >= 0; --bit) {
+    const unsigned long long cand = T | (1ull << bit);
+    int c = 0;
+    for (int64_t i = tid; i < N; i += 1024) c += keys[i] < cand ? 1 : 0;
+    if (block_sum(c, sh) < kk) T = cand;
+  }
+  if (tid == 0) nb = 0;
+  __syncthreads();
+  for (int64_t i = tid; i < N; i += 1024)
+    if (keys[i] <= T) {
+      const int pos = atomicAdd(&nb, 1);
+      if (pos < 1024) best[pos] = keys[i];
+    }
+  __syncthreads();
+  for (int i = nb + tid; i < 1024; i += 1024) best[i] = ~0ull;
+  __syncthreads();
+  for (int size = 2; size <= 1024; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (tid < 512) {
+        const int lo = ((tid / stride) * (stride << 1)) + (tid % stride);
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long a = best[lo], b = best[hi];
+        if ((a > b) == up) best[lo] = b, best[hi] = a;
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < k; i += 1024) {
+    if (i < kk) {
+      const float key = key2f(static_cast<uint32_t>(best[i] >> 32));
+      D[i] = metric == 0 ? key : -key;
+      I[i] = static_cast<int64_t>(static_cast<uint32_t>(best[i])) + id_offset;
+    } else {
+      D[i] = metric == 0 ? pos_inf() : neg_inf();
+      I[i] = -1;
+    }
+  }
+}
+
+// ---- sharded merge: [G, nq, k] -> top-k by (distance, id) ----
+__global__ void __launch_bounds__(256)
+knn_merge_kernel(const float* __restrict__ Dg, const int64_t* __restrict__ Ig, int G, int64_t nq, int k, int metric,
+                 float* __restrict__ D, int64_t* __restrict__ I) {
+  extern __shared__ unsigned long long mk[];  // P composite keys + P payload slots
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int n = G * k;
+  int P = 2;
+  while (P < n) P <<= 1;
+  unsigned long long* key = mk;
+  int* src = reinterpret_cast<int*>(mk + P);
+  for (int i = tid; i < P; i += 256) {
+    if (i < n) {
+      const int g = i / k, j = i % k;
+      const int64_t off = (static_cast<int64_t>(g) * nq + q) * k + j;
+      const int64_t id = Ig[off];
+      const float dv = Dg[off];
+      // rank by (distance, id); ids fit 32 bits per shard set of < 2^32 rows
+      key[i] = id < 0 ? ~0ull : ((static_cast<unsigned long long>(f2key(metric == 0 ? dv : -dv)) << 32) |
+                                 static_cast<uint32_t>(id));
+    } else {
+      key[i] = ~0ull;
+    }
+    src[i] = i;
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (P >> 1); t += 256) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long a = key[lo], b = key[hi];
+        if ((a > b) == up) {
+          key[lo] = b, key[hi] = a;
+          const int s = src[lo];
+          src[lo] = src[hi], src[hi] = s;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < k; i += 256) {
+    const int s = src[i];
+    if (key[i] != ~0ull && s < n) {
+      const int g = s / k, j = s % k;
+      const int64_t off = (static_cast<int64_t>(g) * nq + q) * k + j;
+      D[q * k + i] = Dg[off];
+      I[q * k + i] = Ig[off];
+    } else {
+      D[q * k + i] = metric == 0 ? pos_inf() : neg_inf();
+      I[q * k + i] = -1;
+    }
+  }
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t n) {
+  CDML_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  return 0;
+}
+
+}  // namespace cdml
+
+using namespace cdml;
+
+struct cdml_index {
+  cdml_ctx* ctx;
+  int64_t N;
+  int d, dpad, metric;
+  float* x32;      // [N, d] copy of the database
+  float* xss;      // [N] exact ||x||^2
+  float* h;        // [N] ||x||^2/2 (L2) or 0 (IP)
+  uint16_t* x16;   // [N, dpad] fp16 operand
+  int64_t Ns;      // sampled rows (0 = collect everything)
+  uint16_t* xs16;  // [Ns, dpad]
+  float* hs;       // [Ns]
+  float xmaxnorm;
+  // per-chunk workspace
+  int64_t qc;
+  uint16_t* q16;
+  float *qss, *gmax, *thr, *cand_val;
+  int32_t *cand_idx, *cnt, *overflow;
+  unsigned long long* fb_keys;
+  int64_t ldg;
+  int64_t stats[2];
+};
+
+static void index_free(cdml_index* ix) {
+  if (ix == nullptr) return;
+  cudaFree(ix->x32), cudaFree(ix->xss), cudaFree(ix->h), cudaFree(ix->x16), cudaFree(ix->xs16), cudaFree(ix->hs);
+  cudaFree(ix->q16), cudaFree(ix->qss), cudaFree(ix->gmax), cudaFree(ix->thr), cudaFree(ix->cand_val);
+  cudaFree(ix->cand_idx), cudaFree(ix->cnt), cudaFree(ix->overflow), cudaFree(ix->fb_keys);
+  delete ix;
+}
+
+extern "C" {
+
+int cdml_knn_index_build(cdml_ctx* ctx, const float* X, int64_t N, int d, int64_t ldx, int metric, void* stream,
+                         cdml_index** out) {
+  CDML_REQUIRE(ctx && X && out, "cdml_knn_index_build: NULL argument");
+  CDML_REQUIRE(N > 0 && N < (1ll << 31) && d > 0 && ldx >= d && (metric == 0 || metric == 1),
+               "cdml_knn_index_build: bad geometry N=%lld d=%d", (long long)N, d);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cdml_index* ix = new cdml_index();
+  memset(ix, 0, sizeof(*ix));
+  ix->ctx = ctx, ix->N = N, ix->d = d, ix->dpad = (d + 7) / 8 * 8, ix->metric = metric;
+  *out = nullptr;
+  int rc = 0;
+  rc |= dev_alloc(&ix->x32, static_cast<size_t>(N) * d);
+  rc |= dev_alloc(&ix->xss, N + 1);
+  rc |= dev_alloc(&ix->h, N);
+  rc |= dev_alloc(&ix->x16, static_cast<size_t>(N) * ix->dpad);
+  if (rc) { index_free(ix); return -2; }
+  cudaError_t e = cudaMemcpy2DAsync(ix->x32, sizeof(float) * d, X, sizeof(float) * ldx, sizeof(float) * d, N,
+                                    cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) { index_free(ix); set_error("index build copy failed: %s", cudaGetErrorString(e)); return -2; }
+  const int grid = static_cast<int>(std::min<int64_t>((N + 7) / 8, ctx->num_sms * 8));
+  row_sumsq32_kernel<<<grid, 256, 0, st>>>(ix->x32, N, d, d, ix->xss, metric == 0 ? 0.5f : 0.f, ix->h);
+  max_reduce_kernel<<<1, 1024, 0, st>>>(ix->xss, N, ix->xss + N);
+  rc = cdml_rows_normalize_cast(ctx, ix->x32, N, d, d, 0, 0.f, ix->x16, ix->dpad, CDML_F16, nullptr, 0, nullptr, stream);
+  if (rc) { index_free(ix); return rc; }
+  float maxss = 0.f;
+  e = cudaMemcpyAsync(&maxss, ix->xss + N, sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { index_free(ix); set_error("index build failed: %s", cudaGetErrorString(e)); return -2; }
+  ix->xmaxnorm = sqrtf(maxss);
+  // evenly spaced row sample for the bound pass (robust to any ordering of the database)
+  if (N > kCandCap) {
+    int64_t ns = std::max<int64_t>(N / 8, 4096);
+    ns = std::min<int64_t>(std::min<int64_t>(ns, N), static_cast<int64_t>(kMaxGroups) * 32);
+    ns = ns / 32 * 32;
+    ix->Ns = ns;
+    std::vector<int32_t> rows(ns);
+    for (int64_t i = 0; i < ns; ++i) rows[i] = static_cast<int32_t>(i * N / ns);
+    int32_t* drows = nullptr;
+    rc |= dev_alloc(&drows, ns);
+    rc |= dev_alloc(&ix->xs16, static_cast<size_t>(ns) * ix->dpad);
+    rc |= dev_alloc(&ix->hs, ns);
+    if (rc) { cudaFree(drows); index_free(ix); return -2; }
+    cudaMemcpyAsync(drows, rows.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, st);
+    rc = cdml_gather_rows(ctx, ix->x16, N, ix->dpad * 2, ix->dpad * 2, drows, 0, ns, ix->xs16, ix->dpad * 2, stream);
+    if (!rc) rc = cdml_gather_rows(ctx, ix->h, N, 4, 4, drows, 0, ns, ix->hs, 4, stream);
+    cudaStreamSynchronize(st);
+    cudaFree(drows);
+    if (rc) { index_free(ix); return rc; }
+  }
+  *out = ix;
+  return 0;
+}
+
+int cdml_knn_index_destroy(cdml_index* index) {
+  index_free(index);
+  return 0;
+}
+
+int cdml_knn_last_stats(cdml_index* index, int64_t* stats) {
+  CDML_REQUIRE(index && stats, "cdml_knn_last_stats: NULL argument");
+  stats[0] = index->stats[0], stats[1] = index->stats[1];
+  return 0;
+}
+
+static int ensure_workspace(cdml_index* ix, int64_t qc) {
+  if (ix->qc >= qc) return 0;
+  cudaFree(ix->q16), cudaFree(ix->qss), cudaFree(ix->gmax), cudaFree(ix->thr), cudaFree(ix->cand_val);
+  cudaFree(ix->cand_idx), cudaFree(ix->cnt), cudaFree(ix->overflow);
+  ix->q16 = nullptr, ix->qss = ix->gmax = ix->thr = ix->cand_val = nullptr, ix->cand_idx = ix->cnt = ix->overflow = nullptr;
+  ix->qc = 0;
+  ix->ldg = ix->Ns > 0 ? ((ix->Ns / 32 + 7) / 8 * 8) : 8;
+  int rc = 0;
+  rc |= dev_alloc(&ix->q16, static_cast<size_t>(qc) * ix->dpad);
+  rc |= dev_alloc(&ix->qss, qc);
+  rc |= dev_alloc(&ix->gmax, static_cast<size_t>(qc) * ix->ldg);
+  rc |= dev_alloc(&ix->thr, qc);
+  rc |= dev_alloc(&ix->cand_val, static_cast<size_t>(qc) * kCandCap);
+  rc |= dev_alloc(&ix->cand_idx, static_cast<size_t>(qc) * kCandCap);
+  rc |= dev_alloc(&ix->cnt, qc);
+  rc |= dev_alloc(&ix->overflow, qc);
+  if (rc) return -2;
+  ix->qc = qc;
+  return 0;
+}
+
+int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k, float* D,
+                    int64_t* I, int64_t id_offset, void* stream) {
+  CDML_REQUIRE(ctx && ix && Q && D && I, "cdml_knn_search: NULL argument");
+  CDML_REQUIRE(nq >= 0 && ldq >= ix->d && k >= 1 && k <= 1024, "cdml_knn_search: bad arguments (k=%d, supported 1..1024)", k);
+  CDML_REQUIRE(k <= kKeepCap / 2, "cdml_knn_search: k=%d exceeds the re-rank capacity %d", k, kKeepCap / 2);
+  if (nq == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t chunk = std::min<int64_t>(nq, 32768);
+  int rc = ensure_workspace(ix, chunk);
+  if (rc) { set_error("cdml_knn_search: workspace allocation failed"); return rc; }
+  ix->stats[0] = ix->stats[1] = 0;
+  const int d = ix->d;
+  // rigorous bound of |fp16 tensor-core score - exact score| <= (2u+u^2)|q||x| + accumulation; u = 2^-11
+  const float rel = 1.5f * 0.0009765625f + 1.2e-7f * d;            // operand rounding + fp32 accumulation
+  const float slack_scale = 2.f * rel * ix->xmaxnorm;               // times |q|
+  const float slack_abs = 2.f * 1e-6f * (1.f + ix->xmaxnorm);       // fp16 subnormal floor
+  std::vector<int32_t> host_cnt, host_ovf;
+  for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+    const int64_t qc = std::min<int64_t>(chunk, nq - q0);
+    const float* Qc = Q + q0 * ldq;
+    rc = cdml_rows_normalize_cast(ctx, Qc, qc, d, ldq, 0, 0.f, ix->q16, ix->dpad, CDML_F16, nullptr, 0, nullptr, stream);
+    if (rc) return rc;
+    const int grid = static_cast<int>(std::min<int64_t>((qc + 7) / 8, ctx->num_sms * 8));
+    row_sumsq32_kernel<<<grid, 256, 0, st>>>(Qc, qc, d, ldq, ix->qss, 0.f, nullptr);
+    CDML_CHECK_CUDA(cudaMemsetAsync(ix->cnt, 0, sizeof(int32_t) * qc, st));
+    CDML_CHECK_CUDA(cudaMemsetAsync(ix->overflow, 0, sizeof(int32_t) * qc, st));
+    if (ix->Ns > 0 && ix->Ns / 32 >= k) {
+      EpiKnnGroupMax<kBN> ea{ix->hs, ix->gmax, ix->ldg};
+      rc = launch_gemm<0, 0>(ctx, ix->q16, ix->dpad, ix->xs16, ix->dpad, qc, ix->Ns, ix->dpad, CDML_F16, 1, ea, st);
+      if (rc < 0) return rc;
+      knn_kth_kernel<<<static_cast<int>(qc), kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, static_cast<int>(ix->Ns / 32), k,
+                                                                    ix->qss, slack_scale, slack_abs, ix->thr);
+    } else {
+      fill_f32_kernel<<<64, 256, 0, st>>>(ix->thr, qc, -INFINITY);
+    }
+    EpiKnnCollect<kBN> eb{ix->h, ix->thr, ix->cand_idx, ix->cand_val, ix->cnt, kCandCap};
+    rc = launch_gemm<0, 0>(ctx, ix->x16, ix->dpad, ix->q16, ix->dpad, ix->N, qc, ix->dpad, CDML_F16, 1, eb, st);
+    if (rc < 0) return rc;
+    knn_refine_kernel<<<static_cast<int>(qc), kRefineThreads, 0, st>>>(
+        Qc, ldq, d, ix->qss, ix->x32, d, ix->xss, ix->cand_idx, ix->cand_val, ix->cnt, kCandCap, k, ix->metric,
+        slack_scale, slack_abs, id_offset, D + q0 * k, I + q0 * k, k, ix->overflow);
+    CDML_CHECK_CUDA(cudaGetLastError());
+    host_cnt.resize(qc), host_ovf.resize(qc);
+    CDML_CHECK_CUDA(cudaMemcpyAsync(host_cnt.data(), ix->cnt, sizeof(int32_t) * qc, cudaMemcpyDeviceToHost, st));
+    CDML_CHECK_CUDA(cudaMemcpyAsync(host_ovf.data(), ix->overflow, sizeof(int32_t) * qc, cudaMemcpyDeviceToHost, st));
+    CDML_CHECK_CUDA(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < qc; ++i) {
+      ix->stats[0] += host_cnt[i];
+      if (!host_ovf[i]) continue;
+      ix->stats[1] += 1;
+      if (ix->fb_keys == nullptr && dev_alloc(&ix->fb_keys, ix->N)) return -2;
+      float qn = 0.f;
+      CDML_CHECK_CUDA(cudaMemcpyAsync(&qn, ix->qss + i, sizeof(float), cudaMemcpyDeviceToHost, st));
+      CDML_CHECK_CUDA(cudaStreamSynchronize(st));
+      const int g2 = static_cast<int>(std::min<int64_t>((ix->N + 7) / 8, ctx->num_sms * 8));
+      knn_exact_keys_kernel<<<g2, 256, 0, st>>>(Qc + i * ldq, d, qn, ix->x32, ix->N, d, ix->xss, ix->metric, ix->fb_keys);
+      knn_exact_select_kernel<<<1, 1024, 0, st>>>(ix->fb_keys, ix->N, k, ix->metric, id_offset, D + (q0 + i) * k,
+                                                  I + (q0 + i) * k);
+      CDML_CHECK_CUDA(cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+int cdml_knn_merge(cdml_ctx* ctx, const float* Dg, const int64_t* Ig, int G, int64_t nq, int k, int metric, float* D,
+                   int64_t* I, void* stream) {
+  CDML_REQUIRE(ctx && Dg && Ig && D && I && G >= 1 && k >= 1 && nq >= 0, "cdml_knn_merge: bad argument");
+  if (nq == 0) return 0;
+  int P = 2;
+  while (P < G * k) P <<= 1;
+  const size_t smem = static_cast<size_t>(P) * (sizeof(unsigned long long) + sizeof(int));
+  CDML_REQUIRE(smem <= 200 * 1024, "cdml_knn_merge: G*k=%d too large for one block", G * k);
+  if (smem > 48 * 1024)
+    CDML_CHECK_CUDA(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  knn_merge_kernel<<<static_cast<unsigned>(nq), 256, smem, static_cast<cudaStream_t>(stream)>>>(Dg, Ig, G, nq, k, metric, D, I);
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

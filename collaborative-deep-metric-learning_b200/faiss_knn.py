@@ -1,0 +1,163 @@
+"""KNN retrieval + result files -- host-side mirror of the reference's faiss_knn.py: `calc_knn` (faiss_knn.py:82-131),
+`write_process` / `write_knn` (:267-305), loaders (:52-66) and `main` (:359-402), same names / arguments / flags /
+file formats.  `faiss.Index*.add/search` is replaced by libcdml's exact flat index (tensor-core candidate pass +
+fp32 re-rank); with WORLD_SIZE>1 the index is row-sharded over the ranks and the per-shard top-k are all-gathered
+and merged on the GPU.  The de-similarity post-filter and cross_knn are SURVEY 8(f) rank 2 (next)."""
+import json
+import multiprocessing as mp
+import os
+import shutil
+import time
+import traceback
+
+import numpy as np
+import torch
+from absl import app, flags
+
+from . import ops
+
+FLAGS = flags.FLAGS
+if "embedding_file" not in FLAGS:
+  flags.DEFINE_string("embedding_file", "serving_dir/predict_result/output.npy", "embeddings to index / query")
+  flags.DEFINE_string("decode_map_file", "serving_dir/predict_result/decode_map.json", "row index -> guid")
+  flags.DEFINE_string("pred_feature_file", "serving_dir/predict_result/features.npy", "raw feature vectors")
+  flags.DEFINE_string("pred_feature_info", "serving_dir/dataset/feature.info", "feature info file")
+  flags.DEFINE_integer("nearest_num", 81, "neighbours per embedding (incl. the query itself)")
+  flags.DEFINE_integer("desim_nearest_num", 26, "neighbours per raw feature vector (de-similarity)")
+  flags.DEFINE_string("knn_result", "serving_dir/knn_result/newresult", "where knn results are written")
+
+DECODE_MAP = {}
+
+
+def load_decode_map(filename):
+  """json {"0": guid, ...} -> ({int: guid}, {guid: int}) (faiss_knn.py:52-61)."""
+  with open(filename, "r") as f:
+    index2guid_str = json.load(f)
+  decode_map = {int(k): v for k, v in index2guid_str.items()}
+  encode_map = {v: int(k) for k, v in index2guid_str.items()}
+  return decode_map, encode_map
+
+
+def load_embedding(filename):
+  return np.load(filename)
+
+
+def _device():
+  if not torch.cuda.is_available():
+    raise RuntimeError("calc_knn runs on the CUDA device only (libcdml has no CPU path)")
+  return torch.device("cuda:%d" % torch.cuda.current_device())
+
+
+def calc_knn(embeddings, q_embeddings=None, nearest_num=51, l2_norm=True, M=80, efConstruction=64, efSearch=32,
+             metric="L2", process_group=None):
+  """Exact KNN of q_embeddings (default: the embeddings themselves) in embeddings.
+  Returns D [nq,k] float32 squared-L2 ascending, I [nq,k] int64.  The HNSW arguments of the reference signature are
+  accepted and ignored: the flat index is exact (docstring faiss_knn.py:86-89).  As in the reference, rows are
+  L2-normalised first when l2_norm (queries in place, faiss_knn.py:99-104)."""
+  begin = time.time()
+  dev = _device()
+  embeddings = embeddings.astype(np.float32)
+  if l2_norm:
+    embeddings /= np.linalg.norm(embeddings, axis=1, keepdims=True)
+    if q_embeddings is not None:
+      q_embeddings /= np.linalg.norm(q_embeddings, axis=1, keepdims=True)
+    else:
+      q_embeddings = embeddings
+  elif q_embeddings is None:
+    q_embeddings = embeddings
+  xq = torch.as_tensor(np.ascontiguousarray(q_embeddings, np.float32)).to(dev)
+  world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+  rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
+  N = embeddings.shape[0]
+  lo, hi = rank * N // world, (rank + 1) * N // world          # row shard of this rank
+  xb = torch.as_tensor(np.ascontiguousarray(embeddings[lo:hi])).to(dev)
+  index = ops.FlatIndex(xb, metric)
+  print('create index time cost:', time.time() - begin)
+  end = time.time()
+  D, I = index.search(xq, nearest_num, id_offset=lo)
+  if world > 1:
+    Dg = torch.empty((world,) + tuple(D.shape), dtype=D.dtype, device=dev)
+    Ig = torch.empty((world,) + tuple(I.shape), dtype=I.dtype, device=dev)
+    torch.distributed.all_gather_into_tensor(Dg, D, group=process_group)
+    torch.distributed.all_gather_into_tensor(Ig, I, group=process_group)
+    D, I = ops.knn_merge(Dg, Ig, metric)
+  D, I = D.cpu().numpy(), I.cpu().numpy()
+  index.close()
+  print('whole set query time cost:', time.time() - end)
+  return D, I
+
+
+# ============================ write result ============================
+def format_rows(begin_index, D, I, decode_map):
+  """Lines '<query_guid>,<nbr_guid>#<dist><...' ; column 0 skipped; a neighbour is kept iff idx > 0 and
+  0.0 < dist < 1.4; dist printed as str(np.float32) (faiss_knn.py:272-280)."""
+  lines = []
+  for i in range(I.shape[0]):
+    parts = [decode_map[begin_index + i], ","]
+    for idx, dist in zip(I[i][1:], D[i][1:]):
+      if idx > 0 and dist > 0.0 and dist < 1.4:
+        parts += [decode_map[idx], "#", str(dist), "<"]
+    parts.append("\n")
+    lines.append("".join(parts))
+  return lines
+
+
+def write_process(path, index, begin_index, D, I, prefix='knn_split', decode_map=None):
+  """One shard file `<path>/<prefix><index>` (faiss_knn.py:267-283)."""
+  decode_map = DECODE_MAP if decode_map is None else decode_map
+  try:
+    with open(os.path.join(path, prefix + str(index)), 'w') as fp:
+      fp.writelines(format_rows(begin_index, D, I, decode_map))
+  except Exception:
+    print(traceback.format_exc())
+    raise
+
+
+def write_knn(knn_result, split_num=10, D=None, I=None, prefix='knn_result', decode_map=None):
+  """split_num contiguous patches, the last takes the remainder, one process each (faiss_knn.py:285-305)."""
+  os.makedirs(knn_result, exist_ok=True)
+  decode_map = DECODE_MAP if decode_map is None else decode_map
+  total_num = D.shape[0]
+  patch_num = total_num // split_num
+  begin = time.time()
+  jobs = []
+  for i in range(split_num):
+    lo = i * patch_num
+    hi = (i + 1) * patch_num if i < split_num - 1 else total_num
+    jobs.append((knn_result, i, lo, D[lo:hi], I[lo:hi], prefix, decode_map))
+  if total_num >= 200000:
+    with mp.get_context("fork").Pool(processes=split_num) as pool:
+      pool.starmap(write_process, jobs)
+  else:
+    for job in jobs:
+      write_process(*job)
+  print('write_knn cost: %fs' % (time.time() - begin))
+
+
+def main(args):
+  global DECODE_MAP
+  try:
+    global_begin = time.time()
+    DECODE_MAP, _ = load_decode_map(FLAGS.decode_map_file)
+    os.makedirs(FLAGS.knn_result, exist_ok=True)
+    pg = None
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+      torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+      torch.distributed.init_process_group("nccl")
+      pg = torch.distributed.group.WORLD
+    embeddings = load_embedding(FLAGS.embedding_file)
+    print("faiss_knn embedding_file shape", embeddings.shape)
+    D, I = calc_knn(embeddings, nearest_num=FLAGS.nearest_num, process_group=pg)
+    if pg is None or torch.distributed.get_rank() == 0:
+      np.save(FLAGS.knn_result + '/strictD.npy', D)
+      np.save(FLAGS.knn_result + '/strictI.npy', I)
+      write_knn(FLAGS.knn_result, split_num=10, D=D, I=I, prefix='knn_split')   # cdml_run.sh:147 uploads knn_split*
+      shutil.copyfile(FLAGS.decode_map_file, FLAGS.knn_result + '/decode_map.json')
+    print("faiss_knn cost: %fs" % (time.time() - global_begin))
+  except Exception:
+    print(traceback.format_exc())
+    raise
+
+
+if __name__ == '__main__':
+  app.run(main)

@@ -157,3 +157,54 @@ def mine_semihard(E16, E32, guid, B, margin, want_dist=True):
   check(_lib.load().cdml_mine_semihard(_ctx(E32), ptr(E16), E16.stride(0), dtype16_of(E16), ptr(E32), E32.stride(0),
                                        ptr(guid), B, D, float(margin), ptr(neg_row), ptr(d_an), stream_ptr()))
   return neg_row, d_an
+
+
+class FlatIndex(object):
+  """Exact flat index resident on one GPU (IndexFlatL2 / IndexFlatIP semantics; faiss_knn.py:116-128)."""
+
+  def __init__(self, xb, metric="L2"):
+    if xb.dtype != torch.float32 or xb.dim() != 2 or not xb.is_cuda:
+      raise TypeError("FlatIndex needs a CUDA float32 [N,d] tensor")
+    self.metric = {"L2": _lib.METRIC_L2, "IP": _lib.METRIC_IP}[metric]
+    self.n, self.d = xb.shape
+    self._ref = xb
+    self._h = ctypes.c_void_p()
+    check(_lib.load().cdml_knn_index_build(_ctx(xb), ptr(xb), self.n, self.d, _row_major_2d(xb, "xb"), self.metric,
+                                           stream_ptr(), ctypes.byref(self._h)))
+
+  def search(self, xq, k, id_offset=0):
+    if xq.dtype != torch.float32 or xq.dim() != 2 or xq.shape[1] != self.d:
+      raise TypeError("queries must be float32 [nq,%d]" % self.d)
+    nq = xq.shape[0]
+    D = torch.empty((nq, k), dtype=torch.float32, device=xq.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=xq.device)
+    check(_lib.load().cdml_knn_search(_ctx(xq), self._h, ptr(xq), nq, _row_major_2d(xq, "xq"), k, ptr(D), ptr(I),
+                                      int(id_offset), stream_ptr()))
+    return D, I
+
+  def last_stats(self):
+    s = (ctypes.c_int64 * 2)()
+    check(_lib.load().cdml_knn_last_stats(self._h, s))
+    return {"candidates": int(s[0]), "fallback_queries": int(s[1])}
+
+  def close(self):
+    if self._h:
+      _lib.load().cdml_knn_index_destroy(self._h)
+      self._h = ctypes.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+
+def knn_merge(Dg, Ig, metric="L2"):
+  """[G,nq,k] per-shard results -> global top-k (ties -> lower id)."""
+  G, nq, k = Dg.shape
+  Dg, Ig = Dg.contiguous(), Ig.contiguous()
+  D = torch.empty((nq, k), dtype=torch.float32, device=Dg.device)
+  I = torch.empty((nq, k), dtype=torch.int64, device=Dg.device)
+  check(_lib.load().cdml_knn_merge(_ctx(Dg), ptr(Dg), ptr(Ig), G, nq, k, {"L2": 0, "IP": 1}[metric], ptr(D), ptr(I),
+                                   stream_ptr()))
+  return D, I

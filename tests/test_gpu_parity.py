@@ -1,0 +1,335 @@
+"""GPU parity tests: every kernel family called through the C ABI (ctypes) and compared with the CPU oracle on the
+same seeded inputs.  Tolerances (north_star): gather / ids bit-exact (ids: except exact or sub-ulp distance ties);
+embeddings and loss <= 1e-3 relative with fp16 operands + fp32 accumulation."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import cdml_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cd():
+  import __graft_entry__ as graft
+  graft.build()
+  import cdml_b200  # noqa: F401
+  from cdml_b200 import engine, faiss_knn, inputs, losses, models, ops, predict, train
+  torch.cuda.set_device(0)
+
+  class NS:
+    pass
+  ns = NS()
+  ns.engine, ns.faiss_knn, ns.inputs, ns.losses, ns.models, ns.ops, ns.predict, ns.train = \
+      engine, faiss_knn, inputs, losses, models, ops, predict, train
+  ns.dev = torch.device("cuda:0")
+  return ns
+
+
+def dev_t(cd, a):
+  return torch.as_tensor(np.ascontiguousarray(a)).to(cd.dev)
+
+
+def rel_rows(got, ref):
+  return np.linalg.norm(got - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), 1e-30)
+
+
+# ---------------------------------------------------------------- K1 gather
+def test_gather_bit_exact_golden_and_random(cd, golden):
+  out = cd.ops.gather_rows(dev_t(cd, golden["gather_features"]), dev_t(cd, golden["sampler_seed99_triplets"]))
+  assert np.array_equal(out.cpu().numpy().reshape(8, 3, 12), golden["gather_out"])
+  feats = O.synth_features(3000, 1500, 0)
+  trip = O.synth_triplets(1024, 3000, 1)
+  want = O.flatten_triplets(O.gather_rows(feats, trip))
+  for idx in (trip, trip.astype(np.int32)):
+    got = cd.ops.gather_rows(dev_t(cd, feats), dev_t(cd, idx))
+    assert got.dtype == torch.float32 and np.array_equal(got.cpu().numpy(), want)
+  # ragged widths, empty index, numpy-style negative wrap, out-of-range flag
+  odd = O.synth_features(100, 7, 3)
+  ii = np.array([-1, 0, 99, 5], np.int64)
+  assert np.array_equal(cd.ops.gather_rows(dev_t(cd, odd), dev_t(cd, ii)).cpu().numpy(), odd[ii])
+  assert cd.ops.gather_rows(dev_t(cd, odd), dev_t(cd, np.zeros((0,), np.int64))).shape == (0, 7)
+  assert cd.ops.poll_errors(dev_t(cd, odd)) == 0
+  cd.ops.gather_rows(dev_t(cd, odd), dev_t(cd, np.array([100], np.int64)))
+  assert cd.ops.poll_errors(dev_t(cd, odd)) == 1
+
+
+def test_mptripletpipe_get_batch_matches_numpy(cd, tmp_path):
+  feats = O.synth_features(400, 1500, 0)
+  np.save(tmp_path / "features.npy", feats)
+  pairs = O.synth_pairs(300, 400, seed=9)
+  with open(tmp_path / "a.train", "w") as f:
+    f.writelines("%d,%d\n" % (a, p) for a, p in pairs)
+  pipe = cd.inputs.MPTripletPipe(str(tmp_path / "*.train"), str(tmp_path / "features.npy"), seed=1)
+  pipe.create_pipe(1, 128)
+  ref = cd.inputs.MPTripletPipe(str(tmp_path / "*.train"), str(tmp_path / "features.npy"), seed=1)
+  ref.create_pipe(1, 128)
+  n = 0
+  while True:
+    batch = pipe.get_batch()
+    idx = ref.get_batch_indices()
+    if batch is None:
+      assert idx is None
+      break
+    assert batch.shape == (128, 3, 1500) and batch.dtype == np.float32
+    assert np.array_equal(batch, feats[idx])                       # FEATURES[np.asarray(guid_triplets)]
+    n += 1
+  assert n == 2
+
+
+# ---------------------------------------------------------------- K5 loss
+def test_hinge_loss_fixture_and_random(cd):
+  fx = json.load(open(os.path.join(GOLDEN, "loss_fixture.json")))
+  r = cd.losses.HingeLoss().calculate_loss(np.asarray(fx["triplets"], np.float32), margin=0.1)
+  assert r["pos_dist"].shape == (5, 1) and r["anchors"].shape == (5, 1, 2)
+  assert np.allclose(r["pos_dist"][:, 0], fx["pos_dist"]) and np.allclose(r["hinge_dist"][:, 0], fx["hinge_dist@0.1"])
+  assert abs(float(r["hinge_loss"]) - 18.06) < 1e-5
+  assert abs(float(cd.losses.HingeLoss().calculate_loss(np.asarray(fx["triplets"], np.float32), margin=0.8)["hinge_loss"]) - 18.48) < 1e-5
+  E = O.l2_normalize(np.random.RandomState(0).standard_normal((4096, 3, 256))).astype(np.float32)
+  want = O.hinge_loss(E, 0.8)
+  got = cd.losses.HingeLoss().calculate_loss(dev_t(cd, E), margin=0.8)
+  assert abs(float(got["hinge_loss"]) / want["hinge_loss"] - 1) < 1e-5
+  assert np.allclose(got["hinge_dist"].cpu().numpy(), want["hinge_dist"], atol=1e-5)
+  # gradient of the fused kernel == oracle gradient (mean reduction -> grad_scale 1/B)
+  r = cd.ops.triplet_hinge(dev_t(cd, E.reshape(-1, 256)), 4096, 0.8, grad_scale=1.0 / 4096, want_dE=True)
+  assert np.allclose(r["dE"].cpu().numpy(), O.hinge_loss_grad(E, 0.8).reshape(-1, 256), atol=1e-9)
+
+
+# ---------------------------------------------------------------- K2-K4 forward
+@pytest.mark.parametrize("dims,rows", [([1500, 5000, 256], 3 * 171), ([64, 128, 256], 3 * 50), ([2048, 2048, 2048, 2048, 256], 3 * 64)])
+def test_tower_forward_embeddings_within_1e3(cd, dims, rows):
+  feats = O.synth_features(rows, dims[0], 7)
+  params = O.init_tower(dims, seed=2)
+  eng = cd.engine.TowerEngine(dims, device=cd.dev, init_params=params)
+  e = eng.embed(dev_t(cd, feats)).cpu().numpy()
+  want = O.tower_forward(feats, params)["l2_norm"]
+  assert e.shape == (rows, dims[-1])
+  assert np.allclose(np.linalg.norm(e, axis=1), 1.0, atol=1e-5)
+  assert rel_rows(e, want).max() < 1e-3                          # fp16 operands, fp32 accumulate: stated tolerance 1e-3
+
+
+def test_prediction_run_features_batches_and_tail(cd, tmp_path):
+  dims = [1500, 5000, 256]
+  params = O.init_tower(dims, seed=2)
+  eng = cd.engine.TowerEngine(dims, device=cd.dev, init_params=params)
+  feats = O.synth_features(250, 1500, 8)
+  pred = cd.predict.Prediction(sess=eng)
+  out = pred.run_features(feats, batch_size=100, output_dir=str(tmp_path), suffix="_x")
+  assert out.dtype == np.float32 and out.shape == (250, 256)
+  assert np.array_equal(np.load(tmp_path / "output_x.npy"), out)
+  want = O.tower_forward(feats, params)["l2_norm"]
+  assert rel_rows(out, want).max() < 1e-3
+  assert np.allclose(pred.predict(feats[:7]), out[:7], atol=1e-6)
+
+
+# ---------------------------------------------------------------- K5-K8 training step
+def _grad_rel(got, want):
+  return np.linalg.norm(got - want) / np.linalg.norm(want)
+
+
+def test_training_step_gradients_loss_and_adam(cd):
+  G, F, B = 2000, 1500, 512
+  dims = [F, 5000, 256]
+  feats = O.synth_features(G, F, 0)
+  trip = O.synth_triplets(B, G, 1)
+  params = O.init_tower(dims, seed=2)
+  eng = cd.engine.TowerEngine(dims, device=cd.dev, base_lr=1e-3, margin=0.8, init_params=params)
+  table16 = eng.prepare_table(dev_t(cd, feats))
+  x = O.flatten_triplets(O.gather_rows(feats, trip))
+  tr = O.OracleTrainer(params, lr=1e-3, margin=0.8)
+  _, loss0, grads = tr.loss_and_grads(x)
+  stats = eng.train_step_indices(table16, dev_t(cd, trip))
+  torch.cuda.synchronize()
+  s = stats.cpu().numpy()
+  assert abs(s[0] / loss0["hinge_loss"] - 1) < 1e-3
+  assert abs(s[1] / loss0["pos_dist"].mean() - 1) < 1e-3 and abs(s[2] / loss0["neg_dist"].mean() - 1) < 1e-3
+  # gradient buffers hold SUM-gradients; the oracle's are means over B
+  for l in range(2):
+    assert _grad_rel(eng.gW[l].cpu().numpy() / B, grads[l][0]) < 3e-3, l
+    assert _grad_rel(eng.gb[l].cpu().numpy() / B, grads[l][1]) < 3e-3, l
+  # 10 optimisation steps on fresh batches: loss curve within 1e-3, weights drift << one lr step
+  tr.step(x)
+  losses_g, losses_c = [], []
+  for t in range(2, 11):
+    trip_t = O.synth_triplets(B, G, t)
+    losses_g.append(float(eng.train_step_indices(table16, dev_t(cd, trip_t))[0].item()))
+    losses_c.append(tr.step(O.flatten_triplets(O.gather_rows(feats, trip_t)))[0])
+  assert eng.global_step == 10 and tr.global_step == 10
+  assert np.max(np.abs(np.array(losses_g) / np.array(losses_c) - 1)) < 1e-3
+  for l, (W, b) in enumerate(eng.get_params()):
+    # Adam moves a weight by at most ~lr per step; require agreement to a small fraction of the 10-step travel
+    assert np.abs(W - tr.params[l][0]).max() < 2e-3 and _grad_rel(W - params[l][0], tr.params[l][0] - params[l][0]) < 0.05
+    assert np.abs(b - tr.params[l][1]).max() < 2e-3
+
+
+def test_trainer_end_to_end_small(cd, tmp_path):
+  G, F = 600, 1500
+  feats = O.synth_features(G, F, 0)
+  np.save(tmp_path / "features.npy", feats)
+  for i in range(2):
+    with open(tmp_path / ("c%d.train" % i), "w") as f:
+      f.writelines("%d,%d\n" % (a, p) for a, p in O.synth_pairs(1024, G, seed=20 + i))
+  for name, seed in (("cowatches.eval", 30), ("cowatches.test", 31)):
+    with open(tmp_path / name, "w") as f:
+      f.writelines("%d,%d\n" % (a, p) for a, p in O.synth_pairs(64, G, seed=seed))
+  from cdml_b200.online_data import load_cowatches
+  pipe = cd.inputs.MPTripletPipe(str(tmp_path / "*.train"), str(tmp_path / "features.npy"), seed=1)
+  trainer = cd.train.Trainer(pipe=pipe, num_epochs=2, batch_size=256, model=cd.models.VNet(), loss_fn=cd.losses.HingeLoss(),
+                             learning_rate=1e-3, margin=0.8, checkpoint_dir=str(tmp_path / "ckpt"),
+                             optimizer_class=cd.train.AdamOptimizer, config=None,
+                             eval_cowatches=load_cowatches(str(tmp_path / "cowatches.eval")),
+                             test_cowatches=load_cowatches(str(tmp_path / "cowatches.test")),
+                             check_stop_epoch=0, best_eval_dist=10.0, eval_per_epoch=2, require_improve_num=100)
+  eng = trainer.run()
+  assert eng.global_step == 16                                   # 2 files x (2048 lines / 256) batches
+  assert trainer.total_eval_num >= 3 and np.isfinite(trainer.eval_dist) and trainer.best_eval_dist < 10.0
+  ckpt = cd.predict.latest_checkpoint(str(tmp_path / "ckpt"))
+  assert ckpt is not None and os.path.exists(ckpt + ".npz")
+  z = np.load(ckpt + ".npz")
+  assert z["fully_connected/weights"].shape == (1500, 5000) and z["fully_connected_1/biases"].shape == (256,)
+  pred = cd.predict.Prediction(ckpt=ckpt)
+  e = pred.run_features(feats[:50], batch_size=32)
+  assert e.shape == (50, 256) and np.allclose(np.linalg.norm(e, axis=1), 1, atol=1e-5)
+
+
+# ---------------------------------------------------------------- K11-K13 KNN
+def assert_knn_matches(D, I, Dw, Iw, metric="L2", tol=2e-6):
+  """ids identical except where the oracle's own distances tie within fp32 summation noise."""
+  assert D.shape == Dw.shape and I.shape == Iw.shape
+  finite = np.isfinite(Dw)
+  assert np.allclose(D[finite], Dw[finite], atol=2e-5, rtol=1e-5)
+  assert np.array_equal(np.isfinite(D), finite) and np.array_equal(I < 0, Iw < 0)
+  diff = I != Iw
+  if diff.any():
+    rows = np.unique(np.nonzero(diff)[0])
+    for r in rows:
+      cols = np.nonzero(diff[r])[0]
+      # every disagreeing position sits inside a run of (near-)equal distances and the id SETS agree over that run
+      for c in cols:
+        run = np.abs(Dw[r] - Dw[r, c]) <= tol
+        assert run.sum() >= 2 or c == Dw.shape[1] - 1, (r, c, Dw[r, max(0, c - 2):c + 3], I[r, c], Iw[r, c])
+        if c < Dw.shape[1] - 1 and run[-1] == False:   # run fully inside the list -> same id set
+          assert set(I[r, run]) == set(Iw[r, run]), (r, c)
+  return diff.mean()
+
+
+@pytest.mark.parametrize("N,nq,k,metric", [(20000, 1000, 100, "L2"), (5000, 300, 10, "IP"), (1500, 200, 51, "L2"),
+                                           (60, 60, 100, "L2"), (33000, 257, 81, "L2")])
+def test_flat_knn_ids_match_oracle(cd, N, nq, k, metric):
+  rng = np.random.RandomState(4)
+  X = O.knn_normalize(rng.standard_normal((N, 256)).astype(np.float32))
+  if metric == "IP":
+    X = (X * rng.uniform(0.5, 2.0, size=(N, 1))).astype(np.float32)
+  Q = X[:nq] if nq <= N else X
+  index = cd.ops.FlatIndex(dev_t(cd, X), metric)
+  D, I = index.search(dev_t(cd, Q), k)
+  Dw, Iw = O.flat_knn(X, Q, k=k, l2_norm=False, metric=metric)
+  assert_knn_matches(D.cpu().numpy(), I.cpu().numpy(), Dw, Iw, metric)
+  st = index.last_stats()
+  assert st["fallback_queries"] == 0 and st["candidates"] >= min(k, N) * Q.shape[0]
+  if metric == "L2" and N >= k:
+    assert (I[:, 0].cpu().numpy() == np.arange(Q.shape[0])).all()         # self query first, distance ~0
+
+
+def test_flat_knn_clustered_duplicates_and_separate_queries(cd):
+  rng = np.random.RandomState(5)
+  centres = rng.standard_normal((50, 256)).astype(np.float32)
+  X = centres[rng.randint(0, 50, 12000)] + 0.05 * rng.standard_normal((12000, 256)).astype(np.float32)
+  X[rng.randint(0, 12000, 120)] = X[rng.randint(0, 12000, 120)]             # ~1% exact duplicate rows -> exact ties
+  X = O.knn_normalize(X)
+  Q = O.knn_normalize(centres + 0.05 * rng.standard_normal((50, 256)).astype(np.float32))
+  index = cd.ops.FlatIndex(dev_t(cd, X), "L2")
+  D, I = index.search(dev_t(cd, Q), 100)
+  Dw, Iw = O.flat_knn(X, Q, k=100, l2_norm=False)
+  assert_knn_matches(D.cpu().numpy(), I.cpu().numpy(), Dw, Iw)
+  D2, I2 = index.search(dev_t(cd, X[:500]), 100)
+  assert_knn_matches(D2.cpu().numpy(), I2.cpu().numpy(), *O.flat_knn(X, X[:500], k=100, l2_norm=False))
+  # a database made of ONE repeated row overflows every candidate list -> exact fallback, ties -> lowest ids
+  Xd = np.tile(X[:1], (5000, 1))
+  idx2 = cd.ops.FlatIndex(dev_t(cd, Xd), "L2")
+  D3, I3 = idx2.search(dev_t(cd, X[:3]), 7)
+  assert np.array_equal(I3.cpu().numpy(), np.tile(np.arange(7), (3, 1)))
+  assert idx2.last_stats()["fallback_queries"] == 3
+
+
+def test_calc_knn_api_and_sharded_merge(cd, tmp_path):
+  rng = np.random.RandomState(6)
+  emb = rng.standard_normal((3000, 256)).astype(np.float32)
+  D, I = cd.faiss_knn.calc_knn(emb, nearest_num=51)
+  Dw, Iw = O.flat_knn(emb, k=51)
+  assert D.dtype == np.float32 and I.dtype == np.int64
+  assert_knn_matches(D, I, Dw, Iw)
+  assert np.abs(np.linalg.norm(emb, axis=1) - 1).max() > 0.1          # caller's index array is not mutated (astype copy)
+  q = emb[:40].copy()
+  cd.faiss_knn.calc_knn(emb, q, nearest_num=5)
+  assert np.allclose(np.linalg.norm(q, axis=1), 1, atol=1e-6)         # queries ARE normalised in place (faiss_knn.py:103-104)
+  # row-sharded search on one GPU (4 shards) + merge kernel == unsharded
+  Xn = O.knn_normalize(emb)
+  parts = []
+  for s in range(4):
+    lo, hi = s * 3000 // 4, (s + 1) * 3000 // 4
+    ix = cd.ops.FlatIndex(dev_t(cd, Xn[lo:hi]), "L2")
+    parts.append(ix.search(dev_t(cd, Xn), 51, id_offset=lo))
+  Dm, Im = cd.ops.knn_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), "L2")
+  assert_knn_matches(Dm.cpu().numpy(), Im.cpu().numpy(), Dw, Iw)
+  # merge kernel alone against the oracle merge (bit-exact: same inputs, (distance,id) order)
+  Dg = np.stack([p[0].cpu().numpy() for p in parts]); Ig = np.stack([p[1].cpu().numpy() for p in parts])
+  Do, Io = O.knn_merge(list(Dg), list(Ig), 51)
+  assert np.array_equal(Im.cpu().numpy(), Io) and np.array_equal(Dm.cpu().numpy(), Do)
+  # result files
+  dm = {i: "g%04d" % i for i in range(3000)}
+  cd.faiss_knn.write_knn(str(tmp_path / "res"), split_num=10, D=D, I=I, prefix="knn_split", decode_map=dm)
+  txt = "".join(open(tmp_path / "res" / ("knn_split%d" % j)).read() for j in range(10))
+  assert txt == "".join(O.format_knn_rows(0, D, I, dm))
+
+
+def test_mean_dist_matches_oracle(cd, golden):
+  from cdml_b200.evaluate import Evaluation
+  ev = Evaluation(golden["gather_features"], golden["eval_cowatches"].tolist())
+  assert np.array_equal(ev.features, golden["eval_rencoded_features"])
+  assert np.array_equal(np.asarray(ev.cowatches), golden["eval_rencoded_cowatches"])
+  got = ev.mean_dist(golden["eval_vectors"], golden["eval_cowatches"].tolist())
+  assert abs(got - float(golden["eval_mean_dist"])) < 1e-6
+
+
+# ---------------------------------------------------------------- row M: in-batch semi-hard mining
+def test_semihard_mining_matches_oracle_up_to_fp16_selection_noise(cd):
+  rng = np.random.RandomState(11)
+  B, D, G = 700, 256, 400                       # few guids -> plenty of excluded (same-guid) candidates
+  trip = O.synth_triplets(B, G, seed=3)
+  base = O.l2_normalize(rng.standard_normal((G, D)))
+  E = O.l2_normalize(base[trip.reshape(-1)] + 0.15 * rng.standard_normal((3 * B, D))).astype(np.float32)
+  E32 = dev_t(cd, E)
+  E16 = E32.half()
+  margin = 0.8
+  neg_row, d_an = cd.ops.mine_semihard(E16, E32, dev_t(cd, trip), B, margin)
+  neg_row, d_an = neg_row.cpu().numpy(), d_an.cpu().numpy()
+  want_row, want_d = O.mine_semihard(E, trip, margin)
+  A, P = E[0::3].astype(np.float64), E[1::3].astype(np.float64)
+  dp = ((A - P) ** 2).sum(-1)
+  exact = ((A - E[neg_row].astype(np.float64)) ** 2).sum(-1)
+  assert np.allclose(d_an, exact, atol=1e-5)                     # reported distance is the exact fp32 one
+  same = neg_row == want_row
+  assert same.mean() > 0.97
+  tol = 4e-3                                                     # fp16 operand rounding of the selection distances
+  for i in np.nonzero(~same)[0]:
+    r = neg_row[i]
+    g = trip[r // 3, r % 3]
+    assert r == 3 * i + 2 or (r % 3 != 0 and g != trip[i, 0] and g != trip[i, 1])
+    # a different pick is only acceptable as a near-tie of the oracle's pick or at a category boundary
+    near_tie = abs(exact[i] - want_d[i]) < tol
+    at_boundary = min(abs(exact[i] - dp[i]), abs(exact[i] - dp[i] - margin), abs(want_d[i] - dp[i]),
+                      abs(want_d[i] - dp[i] - margin)) < tol
+    assert near_tie or at_boundary, (i, r, want_row[i], exact[i], want_d[i], dp[i])
+  # mined training step runs and lowers/keeps a finite loss
+  dims = [64, 128, 256]
+  eng = cd.engine.TowerEngine(dims, device=cd.dev, init_params=O.init_tower(dims, seed=2))
+  feats = O.synth_features(G, 64, 0)
+  t16 = eng.prepare_table(dev_t(cd, feats))
+  s = eng.train_step_indices(t16, dev_t(cd, trip), mine=True).cpu().numpy()
+  assert np.isfinite(s).all() and s[3] <= B

@@ -1,0 +1,223 @@
+"""CPU: host-side logic of the package -- C-ABI exports, reader semantics, tower plug-in interface, result writer,
+checkpoint index, and the N>1 protocol (reader sharding, gradient all-reduce, sharded-KNN merge) over gloo."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as graft
+from conftest import GOLDEN, ROOT
+from oracle import cdml_oracle as O
+
+
+@pytest.fixture(scope="session")
+def lib():
+  graft.build()
+  import cdml_b200  # noqa: F401
+  from cdml_b200 import _lib
+  return _lib
+
+
+def test_library_exports_every_symbol_of_the_header(lib):
+  header = open(os.path.join(ROOT, "include", "cdml.h")).read()
+  declared = sorted(set(re.findall(r"\b(cdml_[a-z0-9_]+)\s*\(", header)))
+  assert len(declared) >= 20
+  handle = lib.load()
+  for name in declared:
+    assert hasattr(handle, name), "libcdml.so does not export %s" % name
+  assert sorted(lib.exported_symbols()) == declared          # the ctypes prototypes cover the header exactly
+  assert handle.cdml_version() >= 100
+
+
+def test_no_cpu_fallback_context_creation_fails_loudly(lib):
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip("GPU present")
+  with pytest.raises(lib.CdmlError):
+    lib.context(0)
+  from cdml_b200 import engine
+  with pytest.raises(RuntimeError):
+    engine.TowerEngine([8, 16, 8])
+
+
+def test_product_never_imports_the_oracle():
+  pkg = os.path.join(ROOT, "collaborative-deep-metric-learning_b200")
+  for root, _, files in os.walk(pkg):
+    for f in files:
+      if f.endswith(".py"):
+        src = open(os.path.join(root, f)).read()
+        assert not re.search(r"^\s*(from|import)\s+\.*oracle|cdml_oracle\s*(import|as)|import_module\(.*oracle", src, re.M), \
+            "%s imports the oracle" % f
+
+
+def test_model_plugin_interface(lib):
+  from cdml_b200 import models, utils
+  cls = utils.find_class_by_name("VNet", [models])
+  out = cls().create_model(models.placeholder(1500), output_size=256)
+  assert set(out) >= {"layer_1", "layer_2", "l2_norm"} and out["l2_norm"].name == "model_output"
+  spec = models.compile_chain(out["l2_norm"])
+  assert spec["dims"] == [1500, 5000, 256] and spec["bias_init"] == [0.0, 0.0] and spec["alpha"] == 0.2
+  wide = models.compile_chain(models.WideNet().create_model(models.placeholder(2048))["l2_norm"])
+  assert wide["dims"] == [2048, 2048, 2048, 2048, 256]
+  with pytest.raises(StopIteration):
+    utils.find_class_by_name("VedeNet", [models])            # the reference's broken default
+  with pytest.raises(NotImplementedError):
+    models.ResNet().create_model(models.placeholder(1628))
+  with pytest.raises(NotImplementedError):                   # topology outside the hot path
+    models.compile_chain(models.fully_connected(models.placeholder(8), 4))
+
+
+def _write_dataset(tmp_path, G=50, F=12, n_lines=(23, 10)):
+  feats = O.synth_features(G, F, seed=0)
+  np.save(tmp_path / "features.npy", feats)
+  rng = np.random.RandomState(3)
+  for i, n in enumerate(n_lines):
+    pairs = O.synth_pairs(n, G, seed=10 + i)
+    with open(tmp_path / ("cowatches_%d.train" % i), "w") as f:
+      for a, p in pairs:
+        f.write("%d,%d\n" % (a, p))
+  return feats
+
+
+def test_reader_semantics_and_rank_sharding(lib, tmp_path):
+  from cdml_b200 import inputs
+  feats = _write_dataset(tmp_path)
+  pipe = inputs.MPTripletPipe(str(tmp_path / "*.train"), str(tmp_path / "features.npy"), seed=5)
+  assert pipe.cowatch_num == 33 and len(pipe.cowatch_files) == 2
+  assert np.array_equal(inputs.FEATURES, feats)
+  pipe.create_pipe(num_epochs=2, batch_size=8)
+  batches = []
+  while True:
+    b = pipe.get_batch_indices()
+    if b is None:
+      break
+    batches.append(b)
+  # file 0: 46 lines over 2 epochs -> 5 full batches; file 1: 20 lines -> 2 full batches (partial tail dropped)
+  assert len(batches) == 7 and all(b.shape == (8, 3) and b.dtype == np.int64 for b in batches)
+  for b in batches:
+    assert ((b[:, 2] != b[:, 0]) & (b[:, 2] != b[:, 1])).all() and (b >= 0).all() and (b < 50).all()
+  pairs0 = np.loadtxt(tmp_path / "cowatches_0.train", delimiter=",", dtype=np.int64)
+  first_file_batches = [b for b in batches if np.array_equal(b[0, :2], pairs0[0]) or True]
+  assert np.array_equal(batches[0][:, :2], pairs0[:8])
+  # epoch wrap inside a batch: rows 16..23 of file 0's stream are lines 16..22 then line 0 again
+  stream0 = np.concatenate([pairs0, pairs0])
+  got0 = np.concatenate([b[:, :2] for b in (batches[0], batches[2], batches[4], batches[5], batches[6])])
+  assert np.array_equal(got0, stream0[:40])
+  # two ranks see disjoint halves of the same deterministic order
+  shards = []
+  for r in range(2):
+    p = inputs.MPTripletPipe(str(tmp_path / "*.train"), str(tmp_path / "features.npy"), seed=5, rank=r, world=2)
+    p.create_pipe(2, 8)
+    s = []
+    while (b := p.get_batch_indices()) is not None:
+      s.append(b)
+    shards.append(s)
+  assert len(shards[0]) == 4 and len(shards[1]) == 3
+  assert all(np.array_equal(shards[0][i], batches[2 * i]) for i in range(4))
+  assert all(np.array_equal(shards[1][i], batches[2 * i + 1]) for i in range(3))
+
+
+def test_feature_text_reader_and_cowatch_loader_match_reference(lib, golden):
+  from cdml_b200 import online_data
+  fe, enc, dec = online_data.read_features_txt(os.path.join(GOLDEN, "features_small.txt"), 12)
+  assert np.array_equal(fe, golden["read_features_txt"])
+  maps = json.load(open(os.path.join(GOLDEN, "features_small_maps.json")))
+  assert enc == maps["encode"] and {str(k): v for k, v in dec.items()} == maps["decode"]
+  cw = online_data.load_cowatches(os.path.join(GOLDEN, "cowatches_small.eval"))
+  assert np.array_equal(np.asarray(cw), golden["load_cowatches"])
+
+
+def test_knn_result_writer_matches_reference_bytes(lib, golden, tmp_path):
+  from cdml_b200 import faiss_knn
+  dm, enc = faiss_knn.load_decode_map(os.path.join(GOLDEN, "knn_decode_map.json"))
+  assert dm[3] == "guid03" and enc["guid03"] == 3
+  faiss_knn.write_process(str(tmp_path), 0, 0, golden["knn_D"], golden["knn_I"], "knn_split", decode_map=dm)
+  want = open(os.path.join(GOLDEN, "knn_split0.txt")).read()
+  assert open(tmp_path / "knn_split0").read() == want
+  # write_knn: split_num patches, last takes the remainder, query ids continue across patches
+  D = np.tile(golden["knn_D"], (4, 1))[:11]
+  I = np.tile(golden["knn_I"], (4, 1))[:11]
+  dm2 = {i: "g%d" % i for i in range(11)}
+  faiss_knn.write_knn(str(tmp_path / "out"), split_num=3, D=D, I=I, prefix="knn_result", decode_map=dm2)
+  sizes = [len(open(tmp_path / "out" / ("knn_result%d" % j)).readlines()) for j in range(3)]
+  assert sizes == [3, 3, 5]
+  assert open(tmp_path / "out" / "knn_result2").readline().startswith("g6,")
+  assert "".join(open(tmp_path / "out" / ("knn_result%d" % j)).read() for j in range(3)) == \
+      "".join(O.format_knn_rows(0, D, I, dm2))
+
+
+def test_checkpoint_index_and_deploy_fallback(lib, tmp_path):
+  from cdml_b200 import predict, utils
+  d1, d2 = tmp_path / "2019071001", tmp_path / "2019071002"
+  for d, step in ((d1, 10), (d2, 20)):
+    d.mkdir()
+    (d / "checkpoint").write_text('model_checkpoint_path: "model.ckpt-%d"\n' % step)
+    np.savez(d / ("model.ckpt-%d.npz" % step), dims=np.array([4, 8, 4]))
+  (d1 / "transend.signal").write_text("")
+  os.utime(d1, (1, 1))
+  assert predict.latest_checkpoint(str(d2)).endswith("model.ckpt-20")
+  assert utils.get_latest_folder(str(tmp_path), 1) == str(d2)
+  # newest folder lacks transend.signal -> fall back to the second newest (predict.py:119-132)
+  assert predict._deployed_checkpoint(str(tmp_path)).endswith(os.path.join("2019071001", "model.ckpt-10"))
+  (d1 / "transend.signal").unlink()
+  os.utime(d1, (1, 1))
+  with pytest.raises(IOError):
+    predict._deployed_checkpoint(str(tmp_path))
+
+
+def test_imitation_data_matches_reference_stream(lib, golden):
+  from cdml_b200 import imitation_data
+  np.random.seed(1234)
+  assert np.array_equal(imitation_data.gen_features(64, 12), golden["gen_features_seed1234"])
+  np.random.seed(7)
+  assert np.array_equal(imitation_data.gen_triplets(5, 4), golden["gen_triplets_seed7"])
+  assert imitation_data.gen_triplets(100, 256).shape == (100, 3, 256)       # tests/test_imitation_data.py:39-41
+
+
+_GLOO_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from oracle import cdml_oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, world = dist.get_rank(), 2
+# --- data-parallel step: local sum-gradients, all-reduce(sum), scale 1/(B_local*world) == full-batch mean gradient
+feats = O.synth_features(200, 24, 0); trip = O.synth_triplets(16, 200, 1)
+params = O.init_tower([24, 32, 16], seed=2, dtype=np.float64)
+x = O.flatten_triplets(O.gather_rows(feats, trip)).astype(np.float64)
+full = O.OracleTrainer(params).loss_and_grads(x)[2]
+Bl = 8
+xl = x[rank * 3 * Bl:(rank + 1) * 3 * Bl]
+local = O.OracleTrainer(params).loss_and_grads(xl)[2]          # mean over B_local
+flat = torch.tensor(np.concatenate([np.concatenate([gW.ravel(), gb]) for gW, gb in local]) * Bl)   # SUM gradients
+dist.all_reduce(flat)
+flat = flat.numpy() / (Bl * world)
+want = np.concatenate([np.concatenate([gW.ravel(), gb]) for gW, gb in full])
+assert np.allclose(flat, want, atol=1e-12), np.abs(flat - want).max()
+# --- row-sharded KNN: local top-k with id offset, all-gather, merge == global top-k
+X = O.knn_normalize(np.random.RandomState(4).standard_normal((301, 16)).astype(np.float32))
+lo, hi = rank * 301 // world, (rank + 1) * 301 // world
+D, I = O.flat_knn(X[lo:hi], X, k=7, l2_norm=False)
+Dg = [torch.zeros(301, 7) for _ in range(world)]; Ig = [torch.zeros(301, 7, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(Dg, torch.tensor(D)); dist.all_gather(Ig, torch.tensor(I + lo))
+Dm, Im = O.knn_merge([d.numpy() for d in Dg], [i.numpy() for i in Ig], 7)
+Dw, Iw = O.flat_knn(X, k=7, l2_norm=False)
+assert np.array_equal(Im, Iw) and np.allclose(Dm, Dw, atol=1e-6)
+dist.barrier(); dist.destroy_process_group()
+print("rank %d ok" % rank)
+'''
+
+
+def test_two_rank_protocol_over_gloo(tmp_path):
+  script = tmp_path / "gloo_worker.py"
+  script.write_text(_GLOO_WORKER)
+  port = str(29500 + os.getpid() % 2000)
+  procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                            stderr=subprocess.STDOUT, text=True) for r in range(2)]
+  outs = [p.communicate(timeout=240)[0] for p in procs]
+  for r, (p, o) in enumerate(zip(procs, outs)):
+    assert p.returncode == 0 and ("rank %d ok" % r) in o, o

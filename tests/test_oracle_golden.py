@@ -1,0 +1,161 @@
+"""CPU: the oracle against the golden vectors produced by the reference's own Python (tests/golden/make_golden.py),
+against the known answers of the reference's loss fixture, and against independent restatements (torch autograd,
+finite differences, show_knn-style brute force)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cdml_oracle as O
+from conftest import GOLDEN
+
+
+def test_gather_matches_reference_numpy_fancy_index(golden):
+  out = O.gather_rows(golden["gather_features"], golden["sampler_seed99_triplets"])
+  assert out.dtype == np.float32 and out.shape == (8, 3, 12)
+  assert np.array_equal(out, golden["gather_out"])
+  assert np.array_equal(O.flatten_triplets(out)[4], golden["gather_out"][1, 1])
+
+
+def test_negative_sampler_replays_reference_stream(golden):
+  trip = O.sample_negatives(golden["sampler_seed99_pairs"], 64, np.random.RandomState(99))
+  assert np.array_equal(trip, golden["sampler_seed99_triplets"])
+  assert ((trip[:, 2] != trip[:, 0]) & (trip[:, 2] != trip[:, 1])).all()
+
+
+def test_synthetic_features_match_imitation_data(golden):
+  ref = golden["gen_features_seed1234"]
+  assert np.array_equal(O.synth_features(64, 12, seed=1234), ref.astype(np.float32))
+  assert golden["gen_triplets_seed7"].shape == (5, 3, 4)
+
+
+def test_hinge_loss_known_answers_from_reference_fixture():
+  with open(os.path.join(GOLDEN, "loss_fixture.json")) as f:
+    fx = json.load(f)
+  t = np.asarray(fx["triplets"], np.float32)
+  r = O.hinge_loss(t, margin=0.1)
+  assert r["pos_dist"].shape == (5, 1) and r["anchors"].shape == (5, 1, 2)
+  assert np.allclose(r["pos_dist"][:, 0], fx["pos_dist"]) and np.allclose(r["neg_dist"][:, 0], fx["neg_dist"])
+  assert np.allclose(r["hinge_dist"][:, 0], fx["hinge_dist@0.1"])
+  assert abs(r["hinge_loss"] - fx["hinge_loss@0.1"]) < 1e-9
+  assert abs(O.hinge_loss(t, margin=0.8)["hinge_loss"] - fx["hinge_loss@0.8"]) < 1e-9
+
+
+def test_eval_mean_dist_and_rencode(golden):
+  feats, cow = O.rencode_eval(golden["gather_features"], golden["eval_cowatches"])
+  assert np.array_equal(feats, golden["eval_rencoded_features"])
+  assert np.array_equal(np.asarray(cow), golden["eval_rencoded_cowatches"])
+  assert abs(O.mean_dist(golden["eval_vectors"], golden["eval_cowatches"]) - float(golden["eval_mean_dist"])) < 1e-6
+
+
+def test_knn_result_line_format(golden):
+  with open(os.path.join(GOLDEN, "knn_decode_map.json")) as f:
+    dm = {int(k): v for k, v in json.load(f).items()}
+  with open(os.path.join(GOLDEN, "knn_split0.txt")) as f:
+    want = f.read()
+  assert "".join(O.format_knn_rows(0, golden["knn_D"], golden["knn_I"], dm)) == want
+  assert O.split_ranges(103, 10)[-1] == (90, 103) and O.split_ranges(103, 10)[0] == (0, 10)
+
+
+def _torch_tower(x, params, margin):
+  x = torch.tensor(x, dtype=torch.float64)
+  ps = [(torch.tensor(W, dtype=torch.float64, requires_grad=True), torch.tensor(b, dtype=torch.float64, requires_grad=True))
+        for W, b in params]
+  h = x * torch.rsqrt(torch.clamp((x * x).sum(-1, keepdim=True), min=1e-12))
+  for W, b in ps:
+    h = torch.nn.functional.leaky_relu(h @ W + b, 0.2)
+  e = h * torch.rsqrt(torch.clamp((h * h).sum(-1, keepdim=True), min=1e-12))
+  E = e.view(-1, 3, e.shape[-1])
+  pos = ((E[:, 0] - E[:, 1]) ** 2).sum(-1)
+  neg = ((E[:, 0] - E[:, 2]) ** 2).sum(-1)
+  loss = torch.clamp(pos - neg + margin, min=0).mean()
+  loss.backward()
+  return e.detach().numpy(), loss.item(), [(W.grad.numpy(), b.grad.numpy()) for W, b in ps]
+
+
+def test_tower_forward_backward_against_torch_autograd():
+  rng = np.random.RandomState(0)
+  x = rng.random_sample((12, 40))
+  params = O.init_tower([40, 64, 24, 16], seed=3, bias_init=0.05, dtype=np.float64)
+  tr = O.OracleTrainer(params, margin=0.8)
+  fwd, loss, grads = tr.loss_and_grads(x)
+  e_t, loss_t, grads_t = _torch_tower(x, params, 0.8)
+  assert np.allclose(fwd["l2_norm"], e_t, atol=1e-12)
+  assert abs(loss["hinge_loss"] - loss_t) < 1e-12
+  for (gW, gb), (tW, tb) in zip(grads, grads_t):
+    assert np.allclose(gW, tW, atol=1e-12) and np.allclose(gb, tb, atol=1e-12)
+  assert np.allclose(np.linalg.norm(fwd["l2_norm"], axis=1), 1.0)
+
+
+def test_backward_against_finite_differences():
+  rng = np.random.RandomState(1)
+  x = rng.random_sample((6, 10))
+  params = O.init_tower([10, 12, 8], seed=4, bias_init=0.1, dtype=np.float64)
+  tr = O.OracleTrainer(params, margin=0.8)
+  _, _, grads = tr.loss_and_grads(x)
+  W0 = tr.params[0][0]
+  for (i, j) in [(0, 0), (3, 5), (9, 11)]:
+    eps = 1e-6
+    W0[i, j] += eps
+    lp = tr.loss_and_grads(x)[1]["hinge_loss"]
+    W0[i, j] -= 2 * eps
+    lm = tr.loss_and_grads(x)[1]["hinge_loss"]
+    W0[i, j] += eps
+    assert abs((lp - lm) / (2 * eps) - grads[0][0][i, j]) < 1e-6
+
+
+def test_tf1_adam_first_step_closed_form_and_schedule():
+  w, g = np.array([1.0, -2.0, 0.5]), np.array([0.3, -0.7, 1e-3])
+  w1, m1, v1 = O.adam_step_tf1(w, np.zeros(3), np.zeros(3), g, lr=1e-3, t=1)
+  # t=1: m=(1-b1)g, v=(1-b2)g^2, lr_t=lr*sqrt(1-b2)/(1-b1)  =>  w -= lr * g/(|g| + eps/sqrt(1-b2))
+  assert np.allclose(w1, w - 1e-3 * g / (np.abs(g) + 1e-8 / np.sqrt(1 - 0.999)), rtol=1e-12)
+  assert O.exponential_decay(0.01, 999999, 1000000, 0.96) == 0.01
+  assert abs(O.exponential_decay(0.01, 2500000, 1000000, 0.96) - 0.01 * 0.96 ** 2) < 1e-15
+
+
+def test_flat_knn_against_independent_brute_force_and_merge():
+  rng = np.random.RandomState(4)
+  X = rng.standard_normal((600, 32)).astype(np.float32)
+  D, I = O.flat_knn(X, k=10)
+  Xn = O.knn_normalize(X)
+  for q in (0, 17, 599):
+    assert list(I[q]) == list(O.exact_ip_nn(Xn, q, 10))          # show_knn.py:63-68 statement
+  assert (I[:, 0] == np.arange(600)).all() and np.allclose(D[:, 0], 0, atol=1e-6)
+  assert (np.diff(D, axis=1) >= 0).all() and (D >= 0).all() and (D <= 4 + 1e-5).all()
+  # sharded: 3 row shards with id offsets, merged == global
+  parts = [O.flat_knn(Xn[s:e], Xn, k=10, l2_norm=False) for s, e in ((0, 200), (200, 400), (400, 600))]
+  Dg = [p[0] for p in parts]
+  Ig = [p[1] + off for p, off in zip(parts, (0, 200, 400))]
+  Dm, Im = O.knn_merge(Dg, Ig, 10)
+  assert np.array_equal(Im, I) and np.allclose(Dm, D, atol=1e-6)
+  # fewer rows than k pads like faiss
+  Ds, Is = O.flat_knn(X[:4], k=6)
+  assert (Is[:, 4:] == -1).all() and np.isinf(Ds[:, 4:]).all()
+  # inner product
+  Dip, Iip = O.flat_knn(X, k=5, l2_norm=False, metric="IP")
+  assert (np.diff(Dip, axis=1) <= 0).all() and Iip[3, 0] == np.argmax(X @ X[3])
+
+
+def test_semihard_mining_definition():
+  rng = np.random.RandomState(5)
+  B, D = 40, 16
+  E = O.l2_normalize(rng.standard_normal((3 * B, D)))
+  g = O.synth_triplets(B, 30, seed=2)
+  neg_row, d_an = O.mine_semihard(E, g, margin=0.8)
+  A, P = E[0::3], E[1::3]
+  dp = ((A - P) ** 2).sum(-1)
+  for i in range(B):
+    r = neg_row[i]
+    assert r % 3 != 0 or r == 3 * i + 2
+    if r != 3 * i + 2 or True:
+      guid_r = g[r // 3, r % 3]
+      if r != 3 * i + 2:
+        assert guid_r != g[i, 0] and guid_r != g[i, 1]
+    assert abs(d_an[i] - ((A[i] - E[r]) ** 2).sum()) < 1e-9
+    if dp[i] < d_an[i] < dp[i] + 0.8:
+      # semi-hard: no candidate is closer while still beyond the positive
+      cand = [3 * j + c for j in range(B) for c in (1, 2) if g[j, c] not in (g[i, 0], g[i, 1])]
+      dc = ((A[i] - E[cand]) ** 2).sum(-1)
+      assert d_an[i] <= dc[(dc > dp[i]) & (dc < dp[i] + 0.8)].min() + 1e-12
