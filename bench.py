@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the CDML hot path on B200 (one JSON line on stdout).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--no-mine] [--no-knn]
+
+Metric (BASELINE.json): train triplets/sec.  Workload at N=1: configs[1] -- the default models.py tower
+(VNet 1500->5000->256) at batch 65536 with in-batch semi-hard negative mining, feature table of 1M guids resident in
+HBM.  A step = gather -> tower fwd -> mining -> hinge loss -> bwd -> Adam (+ NCCL all-reduce of the flat gradient
+buffer when N>1; weak scaling: every rank keeps batch 65536).  `value` is timed with CUDA events with the index
+triplets already on the device; `e2e` times the same step through the public API from pinned HOST index buffers with
+the H2D copy and the D2H read of the loss inside the timed region.  The second BASELINE metric (KNN top-100
+queries/sec on a 1M-item index) is reported in the `knn` object of the same line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIMS = [1500, 5000, 256]
+FLOP_PER_TRIPLET = 3 * (4 * DIMS[0] * DIMS[1] + 6 * DIMS[1] * DIMS[2])      # 113.04 MFLOP fwd+bwd
+
+
+def peaks():
+  p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(path):
+    with open(path) as f:
+      m = json.load(f)
+    p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+    p["source"] = "measured"
+  return p
+
+
+class ClockSampler(object):
+  """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+  Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index):
+    self.index, self.proc, self.lines = index, None, []
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+      self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    time.sleep(0.25)
+    self.proc.terminate()
+    self.thread.join(timeout=2)
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ln in self.lines:
+      parts = [p.strip() for p in ln.split(",")]
+      if len(parts) < 6:
+        continue
+      try:
+        sm.append(float(parts[0])), mx.append(float(parts[1]))
+      except ValueError:
+        continue
+      for n, v in zip(names, parts[2:6]):
+        if v.lower().startswith("active"):
+          reasons.add(n)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference path on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_train_baseline(budget_s=12.0, batch=1024, G=10000):
+  from oracle import cdml_oracle as O
+  feats = O.synth_features(G, DIMS[0], 0)
+  params = O.init_tower(DIMS, seed=2)
+  tr = O.OracleTrainer(params, lr=1e-3, margin=0.8, dtype=np.float32)
+  trip = O.synth_triplets(batch, G, 1)
+  tr.step(O.flatten_triplets(O.gather_rows(feats, trip)))                 # warm-up (BLAS threads, page faults)
+  n, t0 = 0, time.time()
+  while time.time() - t0 < budget_s or n < 2:
+    trip = O.synth_triplets(batch, G, 2 + n)
+    tr.step(O.flatten_triplets(O.gather_rows(feats, trip)))               # numpy gather exactly as inputs.py:158
+    n += 1
+  dt = time.time() - t0
+  return {"value": n * batch / dt, "unit": "triplets/s", "cores": os.cpu_count(), "kind": "port",
+          "sample": "%d steps of batch %d (VNet 1500-5000-256, fp32 numpy/BLAS oracle, G=%d) in %.1f s" % (n, batch, G, dt)}
+
+
+def cpu_knn_baseline(budget_s=10.0, N=1000000, d=256, k=100, nq_block=1024):
+  from oracle import cdml_oracle as O
+  X = O.knn_normalize(np.random.RandomState(4).standard_normal((N, d)).astype(np.float32))
+  n, t0 = 0, time.time()
+  while time.time() - t0 < budget_s or n < 1:
+    O.flat_knn(X, X[n * nq_block:(n + 1) * nq_block], k=k, l2_norm=False, block=nq_block)
+    n += 1
+  dt = time.time() - t0
+  return {"value": n * nq_block / dt, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+          "sample": "%d queries against N=%d d=%d k=%d (blocked sgemm + argpartition oracle) in %.1f s" % (n * nq_block, N, d, k, dt)}
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  steps = max(args.steps, 1)
+  per_step = max(2.0, min(20.0, 90.0 / (steps + args.warmup)))
+  base = cpu_train_baseline(budget_s=per_step * steps, batch=2048 if args.batch >= 2048 else args.batch)
+  line = {"impl": "reference", "metric": "train_triplets_per_sec", "value": base["value"], "unit": "triplets/s",
+          "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": workload_config(args, mine=not args.no_mine), "cpu_baseline": base,
+          "e2e": {"value": base["value"], "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "note": "TensorFlow 1.13 / faiss are not installable offline; this arm times the oracle port of the reference "
+                  "path (numpy/BLAS, all host threads) on a bounded sample of the workload; the reference has no in-batch "
+                  "mining (SURVEY Q4), so the port trains on the reader's random negatives"}
+  print(json.dumps(line))
+
+
+def workload_config(args, mine):
+  return {"workload": "configs[1]: VNet 1500-5000-256, batch %d triplets/GPU, in-batch semi-hard mining %s, "
+                      "feature table %d guids resident in HBM" % (args.batch, "on" if mine else "off", args.guids),
+          "tower": DIMS, "batch_per_gpu": args.batch, "guids": args.guids, "mining": bool(mine), "margin": 0.8,
+          "optimizer": "adam(tf1) lr=1e-3", "parallelism": "dp%d" % args.gpus,
+          "l2_policy": "inputs_exceed_l2 (table+activations per step >> 126 MB)"}
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="ours")
+  ap.add_argument("--batch", type=int, default=65536)
+  ap.add_argument("--guids", type=int, default=1000000)
+  ap.add_argument("--no-mine", action="store_true")
+  ap.add_argument("--no-knn", action="store_true")
+  ap.add_argument("--no-cpu", action="store_true")
+  ap.add_argument("--knn-n", type=int, default=1000000)
+  ap.add_argument("--knn-queries", type=int, default=65536)
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3)
+  if args.impl == "reference":
+    return run_reference(args)
+
+  import torch
+  import torch.distributed as dist
+  import __graft_entry__ as graft
+  graft.build()
+  from cdml_b200 import _lib, engine, ops
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda:%d" % local)
+  pg = None
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+    pg = dist.group.WORLD
+  mine = not args.no_mine
+  B, G, F = args.batch, args.guids, DIMS[0]
+
+  # ---- synthetic inputs (seeded; uniform [0,1) features like imitation_data.gen_features) generated on the device
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(1234)
+  eng = engine.TowerEngine(DIMS, device=dev, base_lr=1e-3, margin=0.8, seed=2, process_group=pg)
+  table16 = torch.empty((G, eng.F_pad), dtype=torch.float16, device=dev)
+  for s in range(0, G, 65536):                                            # normalise+cast in slabs (K2 folded, one-off)
+    rows = min(65536, G - s)
+    slab = torch.rand((rows, F), generator=gen, device=dev, dtype=torch.float32)
+    ops.rows_normalize_cast(slab, 0, 1, 1e-12, ld_out=eng.F_pad, out16=table16[s:s + rows])
+  del slab
+  gen.manual_seed(100 + rank)
+  nbatch = args.steps + args.warmup
+  idx_all = torch.randint(0, G, (nbatch, B, 3), generator=gen, device=dev, dtype=torch.int64)
+  idx_all[:, :, 1] = (idx_all[:, :, 0] + 1 + idx_all[:, :, 1] % (G - 1)) % G          # positive != anchor
+  idx_all[:, :, 2] = (idx_all[:, :, 1] + 1 + idx_all[:, :, 2] % (G - 2)) % G
+  clash = idx_all[:, :, 2] == idx_all[:, :, 0]
+  idx_all[:, :, 2][clash] = (idx_all[:, :, 2][clash] + 1) % G                          # negative not in {a,p}
+  idx_host = idx_all.cpu().pin_memory()
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def step(i, idx_dev):
+    return eng.train_step_indices(table16, idx_dev, mine=mine)
+
+  # ---- value: device-resident indices, CUDA events, max over ranks
+  for i in range(args.warmup):
+    step(i, idx_all[i])
+  barrier()
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  launches0 = ops.launch_count()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for i in range(args.steps):
+    stats = step(i, idx_all[args.warmup + i])
+  e1.record()
+  barrier()
+  ms = e0.elapsed_time(e1)
+  launches = ops.launch_count() - launches0
+  clocks = sampler.stop() if rank == 0 else None
+  loss_last = float(stats[0].item())
+  t = torch.tensor([ms], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms = float(t.item())
+  value = world * B * args.steps / (ms / 1e3)
+
+  # ---- e2e: pinned host indices -> H2D -> step -> D2H loss, every step
+  barrier()
+  stats_host = torch.empty(4, dtype=torch.float32).pin_memory()
+  idx_dev = torch.empty((B, 3), dtype=torch.int64, device=dev)
+  e0.record()
+  for i in range(args.steps):
+    idx_dev.copy_(idx_host[args.warmup + i], non_blocking=True)
+    st = step(i, idx_dev)
+    stats_host.copy_(st, non_blocking=True)
+    torch.cuda.current_stream().synchronize()                             # the host reads the loss every step
+  e1.record()
+  barrier()
+  t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  e2e_value = world * B * args.steps / (float(t.item()) / 1e3)
+
+  # ---- per-kernel timing of one step (CUDA events around every tensor-core GEMM launch) for the roofline entry
+  timings = {}
+  orig = ops.gemm16
+
+  def timed_gemm16(A, Bm, M, N, K, amn, bmn, epi, out, **kw):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    r = orig(A, Bm, M, N, K, amn, bmn, epi, out, **kw)
+    b.record()
+    timings.setdefault((M, N, K, amn, bmn, epi), []).append((a, b))
+    return r
+
+  ops.gemm16 = timed_gemm16
+  engine.ops.gemm16 = timed_gemm16
+  reps = min(5, args.steps)
+  for i in range(reps):
+    step(i, idx_all[i])
+  torch.cuda.synchronize()
+  ops.gemm16 = orig
+  engine.ops.gemm16 = orig
+  kern = []
+  for (M, N, K, amn, bmn, epi), evs in timings.items():
+    avg = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    kern.append({"gemm": "M=%d N=%d K=%d A%s B%s epi=%d" % (M, N, K, "mn" if amn else "k", "mn" if bmn else "k", epi),
+                 "ms": avg, "tflops": 2.0 * M * N * K / avg / 1e9})
+  kern.sort(key=lambda r: -r["ms"])
+  pk = peaks()
+  top = kern[0]
+  roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel " + top["gemm"], "achieved": top["tflops"],
+              "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": top["tflops"] / pk["bf16_tflops_sustained"],
+              "traffic": None, "peak_source": "%s bf16_tflops_sustained (kernel timed inside the step)" % pk["source"],
+              "step_tensor_frac": (FLOP_PER_TRIPLET * value / world / 1e12) / pk["bf16_tflops_sustained"],
+              "gemms": kern}
+
+  if rank != 0:
+    if world > 1:
+      dist.barrier()
+      dist.destroy_process_group()
+    return
+
+  line = {"metric": "train_triplets_per_sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "fp16 operands / fp32 accumulate (tcgen05 kind::f16), fp32 master weights",
+          "data": "synthetic", "config": workload_config(args, mine),
+          "e2e": {"value": e2e_value, "unit": "triplets/s", "h2d_bytes_per_step": B * 3 * 8, "d2h_bytes_per_step": 16},
+          "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "loss_last_step": loss_last,
+          "tflops_per_gpu": FLOP_PER_TRIPLET * value / world / 1e12}
+
+  # ---- second BASELINE metric: exact KNN top-100 queries/sec on a 1M-item index (1 GPU; sharded run: tools/bench_knn.py)
+  if not args.no_knn:
+    del table16, idx_all, eng
+    torch.cuda.empty_cache()
+    N, nq, k, d = args.knn_n, args.knn_queries, 100, 256
+    gen.manual_seed(4)
+    X = torch.nn.functional.normalize(torch.randn((N, d), generator=gen, device=dev), dim=1)
+    index = ops.FlatIndex(X, "L2")
+    index.search(X[:4096], k)
+    torch.cuda.synchronize()
+    e0.record()
+    D, I = index.search(X[:nq], k)
+    e1.record()
+    torch.cuda.synchronize()
+    kms = e0.elapsed_time(e1)
+    self_first = float((I[:, 0] == torch.arange(nq, device=dev)).float().mean().item())
+    Xh = X[:nq].cpu().pin_memory()
+    Dh, Ih = torch.empty((nq, k)).pin_memory(), torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    t0 = time.time()
+    D2, I2 = index.search(Xh.to(dev, non_blocking=True), k)
+    Dh.copy_(D2, non_blocking=True), Ih.copy_(I2, non_blocking=True)
+    torch.cuda.synchronize()
+    ke2e = nq / (time.time() - t0)
+    st = index.last_stats()
+    line["knn"] = {"metric": "knn_top100_queries_per_sec", "value": nq / (kms / 1e3), "unit": "queries/s",
+                   "config": {"workload": "configs[3]: exact flat L2 top-100, N=%d d=%d, %d queries (rows of the index)" % (N, d, nq)},
+                   "ms": kms, "tflops": 2.0 * nq * N * d / kms / 1e9, "e2e": {"value": ke2e, "unit": "queries/s",
+                   "h2d_bytes": nq * d * 4, "d2h_bytes": nq * k * 12},
+                   "candidates_per_query": st["candidates"] / nq, "fallback_queries": st["fallback_queries"],
+                   "self_is_first_neighbour": self_first,
+                   "roofline": {"bound": "tensor", "achieved": 2.0 * nq * N * d / kms / 1e9, "peak": pk["bf16_tflops_sustained"],
+                                "unit": "TFLOP/s", "frac": 2.0 * nq * N * d / kms / 1e9 / pk["bf16_tflops_sustained"]}}
+    index.close()
+  if not args.no_cpu and world == 1:
+    line["cpu_baseline"] = cpu_train_baseline()
+    if not args.no_knn:
+      line["knn"]["cpu_baseline"] = cpu_knn_baseline(N=min(args.knn_n, 1000000))
+  print(json.dumps(line))
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

@@ -11,6 +11,17 @@ from ._lib import BF16, EPI_L2NORM, EPI_MASK_LEAKY, EPI_STORE_16, EPI_STORE_F32,
 
 TORCH16 = {F16: torch.float16, BF16: torch.bfloat16}
 
+_LAUNCHES = 0   # kernels of libcdml launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n):
+  global _LAUNCHES
+  _LAUNCHES += n
+
+
+def launch_count():
+  return _LAUNCHES
+
 
 def _ctx(t):
   return _lib.context(t.device.index if t.device.index is not None else torch.cuda.current_device())
@@ -47,6 +58,7 @@ def gather_rows(table, idx, out=None):
   if out is None:
     out = torch.empty((flat.numel(), table.shape[1]), dtype=table.dtype, device=table.device)
   out_pitch = _row_major_2d(out, "out") * out.element_size()
+  _count(1)
   check(_lib.load().cdml_gather_rows(_ctx(table), ptr(table), table.shape[0], row_bytes, pitch, ptr(flat),
                                      int(flat.dtype == torch.int64), flat.numel(), ptr(out), out_pitch, stream_ptr()))
   return out
@@ -63,6 +75,7 @@ def rows_normalize_cast(x, dtype16=F16, normalize=1, eps=1e-12, ld_out=None, wan
     out16 = torch.empty((n, ld_out), dtype=TORCH16[dtype16], device=x.device)
   out32 = torch.empty((n, F), dtype=torch.float32, device=x.device) if want_fp32 else None
   sumsq = torch.empty((n,), dtype=torch.float32, device=x.device) if want_sumsq else None
+  _count(1)
   check(_lib.load().cdml_rows_normalize_cast(_ctx(x), ptr(x), n, F, ld_in, normalize, eps, ptr(out16), out16.stride(0),
                                              dtype16, ptr(out32), F, ptr(sumsq), stream_ptr()))
   return out16, out32, sumsq
@@ -73,6 +86,7 @@ def gemm16(A, B, M, N, K, a_mn_major, b_mn_major, epilogue, out, bias=None, alph
   """Raw cdml_gemm16 call.  A/B are 16-bit 2-D tensors; shapes are passed explicitly (logical M,N,K)."""
   lda, ldb = _row_major_2d(A, "A"), _row_major_2d(B, "B")
   used = ctypes.c_int(0)
+  _count(1)
   check(_lib.load().cdml_gemm16(_ctx(A), ptr(A), int(a_mn_major), lda, ptr(B), int(b_mn_major), ldb, M, N, K,
                                 dtype16_of(A), epilogue, ptr(out), out.stride(-2), ptr(bias), float(alpha), ptr(aux0),
                                 ptr(aux1), aux1.stride(0) if aux1 is not None else 0, num_splits, split_stride,
@@ -85,6 +99,7 @@ def auto_splits(ref, M, N, K):
 
 
 def sum_partials(parts, num_parts, stride, n, out, scale=1.0):
+  _count(1)
   check(_lib.load().cdml_sum_partials(_ctx(parts), ptr(parts), num_parts, stride, n, float(scale), ptr(out), stream_ptr()))
   return out
 
@@ -93,6 +108,7 @@ def colsum16(X, R, N, out, workspace=None):
   need = _lib.load().cdml_colsum_workspace_floats(R, N)
   if workspace is None or workspace.numel() < need:
     workspace = torch.empty((need,), dtype=torch.float32, device=X.device)
+  _count(2)
   check(_lib.load().cdml_colsum16(_ctx(X), ptr(X), R, N, X.stride(0), dtype16_of(X), ptr(workspace), ptr(out), stream_ptr()))
   return out
 
@@ -116,6 +132,7 @@ def triplet_hinge(E, B, margin, neg_row=None, grad_scale=1.0, rinv=None, leaky_a
     dE = out.get("dE") if "dE" in out else torch.empty_like(E)
   if dz16 is not None and dE is None and workspace is None:
     workspace = torch.empty((3 * B * E.stride(0),), dtype=torch.float32, device=dev)
+  _count(2 + (1 if dz16 is not None else 0))
   check(_lib.load().cdml_triplet_hinge(_ctx(E), ptr(E), B, D, E.stride(0), ptr(neg_row), float(margin), float(grad_scale),
                                        ptr(rinv), float(leaky_alpha), ptr(pos), ptr(neg), ptr(hin), ptr(stats), ptr(dE),
                                        ptr(dz16), dz16.stride(0) if dz16 is not None else 0,
@@ -125,18 +142,21 @@ def triplet_hinge(E, B, margin, neg_row=None, grad_scale=1.0, rinv=None, leaky_a
 
 def adam_prepare(step_counter, scalars, base_lr, decay_steps=1e6, decay_rate=0.96, staircase=True, beta1=0.9,
                  beta2=0.999):
+  _count(1)
   check(_lib.load().cdml_adam_prepare(_ctx(scalars), ptr(step_counter), float(base_lr), float(decay_steps),
                                       float(decay_rate), int(staircase), float(beta1), float(beta2), ptr(scalars),
                                       stream_ptr()))
 
 
 def adam_apply(w, m, v, g, scalars, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, w16=None):
+  _count(1)
   check(_lib.load().cdml_adam_apply(_ctx(w), ptr(w), ptr(m), ptr(v), ptr(g), w.numel(), ptr(scalars), float(beta1),
                                     float(beta2), float(eps), float(grad_scale), ptr(w16),
                                     dtype16_of(w16) if w16 is not None else F16, stream_ptr()))
 
 
 def cast16(x, out16):
+  _count(1)
   check(_lib.load().cdml_cast16(_ctx(x), ptr(x), x.numel(), ptr(out16), dtype16_of(out16), stream_ptr()))
   return out16
 
@@ -144,6 +164,7 @@ def cast16(x, out16):
 def mean_pair_dist(V, pairs):
   out = torch.empty((1,), dtype=torch.float32, device=V.device)
   pairs = pairs.to(torch.int64).contiguous()
+  _count(2)
   check(_lib.load().cdml_mean_pair_dist(_ctx(V), ptr(V), V.stride(0), V.shape[1], ptr(pairs), pairs.shape[0], ptr(out),
                                         stream_ptr()))
   return out
@@ -154,6 +175,7 @@ def mine_semihard(E16, E32, guid, B, margin, want_dist=True):
   neg_row = torch.empty((B,), dtype=torch.int32, device=E32.device)
   d_an = torch.empty((B,), dtype=torch.float32, device=E32.device) if want_dist else None
   guid = guid.to(torch.int64).contiguous()
+  _count(4)
   check(_lib.load().cdml_mine_semihard(_ctx(E32), ptr(E16), E16.stride(0), dtype16_of(E16), ptr(E32), E32.stride(0),
                                        ptr(guid), B, D, float(margin), ptr(neg_row), ptr(d_an), stream_ptr()))
   return neg_row, d_an
@@ -169,6 +191,7 @@ class FlatIndex(object):
     self.n, self.d = xb.shape
     self._ref = xb
     self._h = ctypes.c_void_p()
+    _count(5)
     check(_lib.load().cdml_knn_index_build(_ctx(xb), ptr(xb), self.n, self.d, _row_major_2d(xb, "xb"), self.metric,
                                            stream_ptr(), ctypes.byref(self._h)))
 
@@ -178,6 +201,7 @@ class FlatIndex(object):
     nq = xq.shape[0]
     D = torch.empty((nq, k), dtype=torch.float32, device=xq.device)
     I = torch.empty((nq, k), dtype=torch.int64, device=xq.device)
+    _count(6 * ((nq + 32767) // 32768))
     check(_lib.load().cdml_knn_search(_ctx(xq), self._h, ptr(xq), nq, _row_major_2d(xq, "xq"), k, ptr(D), ptr(I),
                                       int(id_offset), stream_ptr()))
     return D, I
@@ -205,6 +229,7 @@ def knn_merge(Dg, Ig, metric="L2"):
   Dg, Ig = Dg.contiguous(), Ig.contiguous()
   D = torch.empty((nq, k), dtype=torch.float32, device=Dg.device)
   I = torch.empty((nq, k), dtype=torch.int64, device=Dg.device)
+  _count(1)
   check(_lib.load().cdml_knn_merge(_ctx(Dg), ptr(Dg), ptr(Ig), G, nq, k, {"L2": 0, "IP": 1}[metric], ptr(D), ptr(I),
                                    stream_ptr()))
   return D, I
