@@ -44,10 +44,18 @@ struct GemmSmem {
 //   row   : global output row of this thread;  n0 : first global column of the tile
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float leaky(float v, float alpha) { return v > 0.f ? v : alpha * v; }
+// Bias of the 32 columns starting at nb: one coalesced load (lane j <-> column nb+j), handed to every thread's
+// column loop by shuffle.  (A per-column uniform __ldg serialises on load latency inside the unrolled loop.)
+__device__ __forceinline__ float chunk_bias(const float* bias, int nb, int N) {
+  const int col = nb + static_cast<int>(threadIdx.x & 31);
+  return (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
+}
 
 // fp32 store (optionally bias + leaky).  Split-K partials land at out + split * split_stride.
 template <int BN>
 struct EpiStoreF32 {
+  __device__ __forceinline__ void block_begin() const {}
+  __device__ __forceinline__ void block_end() const {}
   float* out;
   int64_t ld;
   int64_t split_stride;
@@ -62,14 +70,12 @@ struct EpiStoreF32 {
       if (nb >= s.N) break;
       uint32_t v[32];
       tmem_ld_32x32(taddr + c * 32, v);
+      const float b_lane = chunk_bias(bias, nb, s.N);
       tmem_ld_wait();
       float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (bias != nullptr && nb + j < s.N) x += __ldg(bias + nb + j);
-        f[j] = leaky(x, alpha);
-      }
+      for (int j = 0; j < 32; ++j)
+        f[j] = leaky(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_lane, j), alpha);
       if (row_ok) {
         if (nb + 32 <= s.N && (ld & 3) == 0) {
           float4* p = reinterpret_cast<float4*>(orow + nb);
@@ -88,6 +94,8 @@ struct EpiStoreF32 {
 // 16-bit store of leaky(acc + bias): the hidden-layer forward epilogue (models.py:19-30).
 template <int BN, int kBf16>
 struct EpiStore16 {
+  __device__ __forceinline__ void block_begin() const {}
+  __device__ __forceinline__ void block_end() const {}
   uint16_t* out;
   int64_t ld;
   const float* bias;  // nullable
@@ -101,15 +109,13 @@ struct EpiStore16 {
       if (nb >= s.N) break;
       uint32_t v[32];
       tmem_ld_32x32(taddr + c * 32, v);
+      const float b_lane = chunk_bias(bias, nb, s.N);
       tmem_ld_wait();
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
-        if (bias != nullptr) {
-          if (nb + 2 * j < s.N) x0 += __ldg(bias + nb + 2 * j);
-          if (nb + 2 * j + 1 < s.N) x1 += __ldg(bias + nb + 2 * j + 1);
-        }
+        const float x0 = __uint_as_float(v[2 * j]) + __shfl_sync(0xffffffffu, b_lane, 2 * j);
+        const float x1 = __uint_as_float(v[2 * j + 1]) + __shfl_sync(0xffffffffu, b_lane, 2 * j + 1);
         pk[j] = pack2<kBf16>(leaky(x0, alpha), leaky(x1, alpha));
       }
       if (row_ok) {
@@ -131,6 +137,8 @@ struct EpiStore16 {
 // Requires the whole row in one tile (N <= BN).  Writes e (fp32), rinv[row], optional 16-bit e.
 template <int BN, int kBf16>
 struct EpiL2Norm {
+  __device__ __forceinline__ void block_begin() const {}
+  __device__ __forceinline__ void block_end() const {}
   float* out;  // [M, ld] fp32 embedding
   int64_t ld;
   const float* bias;
@@ -147,15 +155,13 @@ struct EpiL2Norm {
       if (nb >= s.N) break;
       uint32_t v[32];
       tmem_ld_32x32(taddr + c * 32, v);
+      const float b_lane = chunk_bias(bias, nb, s.N);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (nb + j < s.N) {
-          float x = __uint_as_float(v[j]);
-          if (bias != nullptr) x += __ldg(bias + nb + j);
-          x = leaky(x, alpha);
-          ss = fmaf(x, x, ss);
-        }
+        // columns beyond N hold exact zeros (TMA zero fill) and a zero bias: they add nothing
+        const float x = leaky(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_lane, j), alpha);
+        ss = fmaf(x, x, ss);
       }
     }
     const float r = rsqrtf(fmaxf(ss, 1e-12f));
@@ -167,14 +173,12 @@ struct EpiL2Norm {
       if (nb >= s.N) break;
       uint32_t v[32];
       tmem_ld_32x32(taddr + c * 32, v);
+      const float b_lane = chunk_bias(bias, nb, s.N);
       tmem_ld_wait();
       float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (bias != nullptr && nb + j < s.N) x += __ldg(bias + nb + j);
-        f[j] = leaky(x, alpha) * r;
-      }
+      for (int j = 0; j < 32; ++j)
+        f[j] = leaky(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_lane, j), alpha) * r;
       if (row_ok) {
         if (nb + 32 <= s.N && (ld & 3) == 0) {
           float4* p = reinterpret_cast<float4*>(orow + nb);
@@ -203,6 +207,8 @@ struct EpiL2Norm {
 // forward output -- sign(leaky(z)) == sign(z), so no pre-activation stash is needed.
 template <int BN, int kBf16>
 struct EpiMaskLeaky {
+  __device__ __forceinline__ void block_begin() const {}
+  __device__ __forceinline__ void block_end() const {}
   uint16_t* out;
   int64_t ld;
   const uint16_t* mask;
@@ -309,6 +315,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  if (threadIdx.x == 96) epi.block_begin();  // warp 3: per-CTA epilogue state (e.g. the KNN candidate log cursor)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -401,6 +408,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 96) epi.block_end();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);

@@ -40,6 +40,8 @@ __device__ __forceinline__ float pos_inf() { return __int_as_float(0x7f800000); 
 // ---- pass A epilogue: thread <-> query row; best score of each 32-column (index-row) group ----
 template <int BN>
 struct EpiKnnGroupMax {
+  __device__ __forceinline__ void block_begin() const {}
+  __device__ __forceinline__ void block_end() const {}
   const float* h;  // [Ns] ||x||^2/2 of the sampled rows (zeros for IP)
   float* gmax;     // [nq, ldg]
   int64_t ldg;
@@ -71,18 +73,33 @@ struct EpiKnnGroupMax {
 };
 
 // ---- pass B epilogue: thread <-> index row, column <-> query; ballot + append ----
+// Survivors go to a CTA-private log (cursor in shared memory, one fast shared atomic per hit column, fire-and-forget
+// 16-byte stores); knn_bin_kernel later files the log entries under their queries.  Keeping the per-query global
+// atomics out of the GEMM epilogue matters: their ~1 us round trip would otherwise stall the epilogue warp per hit.
+__device__ __forceinline__ unsigned int& knn_log_cursor() {
+  __shared__ unsigned int cursor;
+  return cursor;
+}
+
 template <int BN>
 struct EpiKnnCollect {
   const float* h;    // [N] ||x||^2/2 (zeros for IP)
   const float* thr;  // [nq] score bound per query
-  int32_t* cand_idx; // [nq, cap]
-  float* cand_val;   // [nq, cap]
-  int32_t* cnt;      // [nq]
-  int cap;
+  uint4* log;        // [gridDim.x, log_cap] entries (query, row, score bits, 0)
+  int32_t* log_count;  // [gridDim.x]
+  int32_t* log_overflow;
+  unsigned int log_cap;
+  __device__ __forceinline__ void block_begin() const { knn_log_cursor() = 0u; }
+  __device__ __forceinline__ void block_end() const {
+    const unsigned int n = knn_log_cursor();
+    log_count[blockIdx.x] = static_cast<int32_t>(n < log_cap ? n : log_cap);
+    if (n > log_cap) atomicOr(log_overflow, 1);
+  }
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
     const int lane = threadIdx.x & 31;
     const bool row_ok = row < s.M;
     const float hr = row_ok ? __ldg(h + row) : 0.f;
+    uint4* my_log = log + static_cast<size_t>(blockIdx.x) * log_cap;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int nb = n0 + c * 32;
@@ -98,23 +115,36 @@ struct EpiKnnCollect {
         const bool pass = sc > tj;
         const unsigned m = __ballot_sync(0xffffffffu, pass);
         if (m != 0u) {  // warp-uniform, rare
-          const int q = nb + j;
           const int leader = __ffs(m) - 1;
-          int base = 0;
-          if (lane == leader) base = atomicAdd(cnt + q, __popc(m));
+          unsigned int base = 0;
+          if (lane == leader) base = atomicAdd(&knn_log_cursor(), static_cast<unsigned int>(__popc(m)));
           base = __shfl_sync(0xffffffffu, base, leader);
           if (pass) {
-            const int pos = base + __popc(m & ((1u << lane) - 1u));
-            if (pos < cap) {
-              cand_idx[static_cast<int64_t>(q) * cap + pos] = row;
-              cand_val[static_cast<int64_t>(q) * cap + pos] = sc;
-            }
+            const unsigned int pos = base + __popc(m & ((1u << lane) - 1u));
+            if (pos < log_cap)
+              my_log[pos] = make_uint4(static_cast<uint32_t>(nb + j), static_cast<uint32_t>(row), __float_as_uint(sc), 0u);
           }
         }
       }
     }
   }
 };
+
+// File the CTA logs under their queries: cand[q][atomicAdd(cnt[q])] = (row, score).
+__global__ void __launch_bounds__(256)
+knn_bin_kernel(const uint4* __restrict__ log, const int32_t* __restrict__ log_count, unsigned int log_cap,
+               int32_t* __restrict__ cand_idx, float* __restrict__ cand_val, int32_t* __restrict__ cnt, int cap) {
+  const int n = log_count[blockIdx.y];
+  const uint4* my = log + static_cast<size_t>(blockIdx.y) * log_cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint4 e = my[i];
+    const int pos = atomicAdd(cnt + e.x, 1);
+    if (pos < cap) {
+      cand_idx[static_cast<int64_t>(e.x) * cap + pos] = static_cast<int32_t>(e.y);
+      cand_val[static_cast<int64_t>(e.x) * cap + pos] = __uint_as_float(e.z);
+    }
+  }
+}
 
 // ---- small helpers -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -448,6 +478,9 @@ struct cdml_index {
   uint16_t* q16;
   float *qss, *gmax, *thr, *cand_val;
   int32_t *cand_idx, *cnt, *overflow;
+  uint4* log;          // [num_sms, log_cap] CTA-private candidate logs of pass B
+  int32_t* log_count;  // [num_sms] + 1 overflow word
+  unsigned int log_cap;
   unsigned long long* fb_keys;
   int64_t ldg;
   int64_t stats[2];
@@ -458,6 +491,7 @@ static void index_free(cdml_index* ix) {
   cudaFree(ix->x32), cudaFree(ix->xss), cudaFree(ix->h), cudaFree(ix->x16), cudaFree(ix->xs16), cudaFree(ix->hs);
   cudaFree(ix->q16), cudaFree(ix->qss), cudaFree(ix->gmax), cudaFree(ix->thr), cudaFree(ix->cand_val);
   cudaFree(ix->cand_idx), cudaFree(ix->cnt), cudaFree(ix->overflow), cudaFree(ix->fb_keys);
+  cudaFree(ix->log), cudaFree(ix->log_count);
   delete ix;
 }
 
@@ -530,7 +564,8 @@ int cdml_knn_last_stats(cdml_index* index, int64_t* stats) {
 static int ensure_workspace(cdml_index* ix, int64_t qc) {
   if (ix->qc >= qc) return 0;
   cudaFree(ix->q16), cudaFree(ix->qss), cudaFree(ix->gmax), cudaFree(ix->thr), cudaFree(ix->cand_val);
-  cudaFree(ix->cand_idx), cudaFree(ix->cnt), cudaFree(ix->overflow);
+  cudaFree(ix->cand_idx), cudaFree(ix->cnt), cudaFree(ix->overflow), cudaFree(ix->log), cudaFree(ix->log_count);
+  ix->log = nullptr, ix->log_count = nullptr;
   ix->q16 = nullptr, ix->qss = ix->gmax = ix->thr = ix->cand_val = nullptr, ix->cand_idx = ix->cnt = ix->overflow = nullptr;
   ix->qc = 0;
   ix->ldg = ix->Ns > 0 ? ((ix->Ns / 32 + 7) / 8 * 8) : 8;
@@ -543,6 +578,11 @@ static int ensure_workspace(cdml_index* ix, int64_t qc) {
   rc |= dev_alloc(&ix->cand_idx, static_cast<size_t>(qc) * kCandCap);
   rc |= dev_alloc(&ix->cnt, qc);
   rc |= dev_alloc(&ix->overflow, qc);
+  // log capacity: 1536 nominees per query on average, never less than 64K entries per CTA
+  const int sms = ix->ctx->num_sms;
+  ix->log_cap = static_cast<unsigned int>(std::max<int64_t>(qc * 1536 / sms, 65536));
+  rc |= dev_alloc(&ix->log, static_cast<size_t>(sms) * ix->log_cap);
+  rc |= dev_alloc(&ix->log_count, sms + 1);
   if (rc) return -2;
   ix->qc = qc;
   return 0;
@@ -583,9 +623,12 @@ int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, i
     } else {
       fill_f32_kernel<<<64, 256, 0, st>>>(ix->thr, qc, -INFINITY);
     }
-    EpiKnnCollect<kBN> eb{ix->h, ix->thr, ix->cand_idx, ix->cand_val, ix->cnt, kCandCap};
+    CDML_CHECK_CUDA(cudaMemsetAsync(ix->log_count, 0, sizeof(int32_t) * (ctx->num_sms + 1), st));
+    EpiKnnCollect<kBN> eb{ix->h, ix->thr, ix->log, ix->log_count, ix->log_count + ctx->num_sms, ix->log_cap};
     rc = launch_gemm<0, 0>(ctx, ix->x16, ix->dpad, ix->q16, ix->dpad, ix->N, qc, ix->dpad, CDML_F16, 1, eb, st);
     if (rc < 0) return rc;
+    knn_bin_kernel<<<dim3(32, ctx->num_sms), 256, 0, st>>>(ix->log, ix->log_count, ix->log_cap, ix->cand_idx, ix->cand_val,
+                                                          ix->cnt, kCandCap);
     knn_refine_kernel<<<static_cast<int>(qc), kRefineThreads, 0, st>>>(
         Qc, ldq, d, ix->qss, ix->x32, d, ix->xss, ix->cand_idx, ix->cand_val, ix->cnt, kCandCap, k, ix->metric,
         slack_scale, slack_abs, id_offset, D + q0 * k, I + q0 * k, k, ix->overflow);
@@ -593,10 +636,12 @@ int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, i
     host_cnt.resize(qc), host_ovf.resize(qc);
     CDML_CHECK_CUDA(cudaMemcpyAsync(host_cnt.data(), ix->cnt, sizeof(int32_t) * qc, cudaMemcpyDeviceToHost, st));
     CDML_CHECK_CUDA(cudaMemcpyAsync(host_ovf.data(), ix->overflow, sizeof(int32_t) * qc, cudaMemcpyDeviceToHost, st));
+    int32_t log_ovf = 0;
+    CDML_CHECK_CUDA(cudaMemcpyAsync(&log_ovf, ix->log_count + ctx->num_sms, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CDML_CHECK_CUDA(cudaStreamSynchronize(st));
     for (int64_t i = 0; i < qc; ++i) {
       ix->stats[0] += host_cnt[i];
-      if (!host_ovf[i]) continue;
+      if (!host_ovf[i] && !log_ovf) continue;   // a full CTA log may have dropped nominees of any query
       ix->stats[1] += 1;
       if (ix->fb_keys == nullptr && dev_alloc(&ix->fb_keys, ix->N)) return -2;
       float qn = 0.f;

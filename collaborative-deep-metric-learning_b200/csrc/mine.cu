@@ -16,6 +16,8 @@ constexpr unsigned long long kNoCand = ~0ull;
 
 template <int BN>
 struct EpiMine {
+  __device__ __forceinline__ void block_begin() const {}
+  __device__ __forceinline__ void block_end() const {}
   const float* dp;        // [B] exact |a-p|^2
   const int32_t* guid;    // [B,3] int32 guids
   unsigned long long* semi;    // [B] best semi-hard (float bits << 32 | row)
@@ -23,11 +25,12 @@ struct EpiMine {
   float margin;
   int cand;  // 1: columns are the positives' rows 3j+1, 2: the negatives' rows 3j+2
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
+    const int lane = threadIdx.x & 31;
     const bool row_ok = row < s.M;
     const float dpi = row_ok ? __ldg(dp + row) : 0.f;
     const float lim = dpi + margin;
-    const int ga = row_ok ? __ldg(guid + 3 * row) : -1;
-    const int gp = row_ok ? __ldg(guid + 3 * row + 1) : -1;
+    const int ga = row_ok ? __ldg(guid + 3 * row) : 0;
+    const int gp = row_ok ? __ldg(guid + 3 * row + 1) : 0;
     float sd = __int_as_float(0x7f800000), bd = __int_as_float(0x7f800000);
     int sr = -1, br = -1;
 #pragma unroll 1
@@ -36,19 +39,19 @@ struct EpiMine {
       if (nb >= s.N) break;
       uint32_t v[32];
       tmem_ld_32x32(taddr + c * 32, v);
+      // one coalesced load of the chunk's 32 candidate guids, broadcast per column by shuffle
+      const int g_lane = nb + lane < s.N ? __ldg(guid + 3 * (nb + lane) + cand) : ga;  // beyond N: never valid
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = nb + j;
-        if (col < s.N) {  // warp-uniform
-          const int gj = __ldg(guid + 3 * col + cand);
-          const float d = fmaxf(fmaf(-2.f, __uint_as_float(v[j]), 2.f), 0.f);
-          const bool valid = gj != ga && gj != gp;
-          const bool is_semi = valid && d > dpi && d < lim && d < sd;
-          const bool is_beyond = valid && d >= lim && d < bd;
-          if (is_semi) sd = d, sr = 3 * col + cand;
-          if (is_beyond) bd = d, br = 3 * col + cand;
-        }
+        const int gj = __shfl_sync(0xffffffffu, g_lane, j);
+        const float d = fmaxf(fmaf(-2.f, __uint_as_float(v[j]), 2.f), 0.f);
+        const bool valid = gj != ga && gj != gp;
+        const bool is_semi = valid && d > dpi && d < lim && d < sd;
+        const bool is_beyond = valid && d >= lim && d < bd;
+        sd = is_semi ? d : sd, sr = is_semi ? 3 * col + cand : sr;
+        bd = is_beyond ? d : bd, br = is_beyond ? 3 * col + cand : br;
       }
     }
     if (row_ok) {

@@ -57,6 +57,8 @@ def gather_rows(table, idx, out=None):
   row_bytes = table.shape[1] * table.element_size()
   if out is None:
     out = torch.empty((flat.numel(), table.shape[1]), dtype=table.dtype, device=table.device)
+  if flat.numel() == 0:
+    return out
   out_pitch = _row_major_2d(out, "out") * out.element_size()
   _count(1)
   check(_lib.load().cdml_gather_rows(_ctx(table), ptr(table), table.shape[0], row_bytes, pitch, ptr(flat),
@@ -82,13 +84,15 @@ def rows_normalize_cast(x, dtype16=F16, normalize=1, eps=1e-12, ld_out=None, wan
 
 
 def gemm16(A, B, M, N, K, a_mn_major, b_mn_major, epilogue, out, bias=None, alpha=1.0, aux0=None, aux1=None,
-           num_splits=1, split_stride=0):
+           num_splits=1, split_stride=0, ld_out=None):
   """Raw cdml_gemm16 call.  A/B are 16-bit 2-D tensors; shapes are passed explicitly (logical M,N,K)."""
   lda, ldb = _row_major_2d(A, "A"), _row_major_2d(B, "B")
   used = ctypes.c_int(0)
+  if ld_out is None:
+    ld_out = out.stride(-2) if out.dim() >= 2 else N
   _count(1)
   check(_lib.load().cdml_gemm16(_ctx(A), ptr(A), int(a_mn_major), lda, ptr(B), int(b_mn_major), ldb, M, N, K,
-                                dtype16_of(A), epilogue, ptr(out), out.stride(-2), ptr(bias), float(alpha), ptr(aux0),
+                                dtype16_of(A), epilogue, ptr(out), ld_out, ptr(bias), float(alpha), ptr(aux0),
                                 ptr(aux1), aux1.stride(0) if aux1 is not None else 0, num_splits, split_stride,
                                 ctypes.byref(used), stream_ptr()))
   return used.value

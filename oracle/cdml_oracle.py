@@ -171,6 +171,47 @@ def tower_backward(fwd, params, dE, alpha: float = LEAKY_ALPHA, dtype=np.float64
   return grads
 
 
+def round16(a, kind="fp16"):
+  """Round-to-nearest-even to the 16-bit storage type the kernels use, back to float64."""
+  a = np.asarray(a, np.float64)
+  if kind == "fp16":
+    return a.astype(np.float16).astype(np.float64)
+  u = a.astype(np.float32).view(np.uint32).astype(np.uint64)
+  u = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+  return u.astype(np.uint32).view(np.float32).astype(np.float64)
+
+
+def tower_grads_emulated16(x, params, margin, kind="fp16", alpha: float = LEAKY_ALPHA):
+  """PRECISION MODEL of the GPU step (test infrastructure): the exact arithmetic of tower_forward / hinge /
+  tower_backward in float64, but with operands rounded to 16 bits at exactly the places the kernels store them
+  (normalised input, shadow weights, hidden activations, dz of every layer).  The kernels must match this model to
+  ~1e-3; the distance between this model and the unrounded oracle is the inherent cost of 16-bit operands
+  (differences of nearly equal embeddings amplify the ~5e-4 forward error to ~1-2e-2 in the gradients)."""
+  r = lambda a: round16(a, kind)
+  xh = r(l2_normalize(np.asarray(x, np.float64)))
+  W16 = [r(W) for W, _ in params]
+  acts, h = [], xh
+  for li, (W, b) in enumerate(params):
+    z = leaky_relu(h @ W16[li] + np.asarray(b, np.float64), alpha)
+    h = z if li == len(params) - 1 else r(z)
+    acts.append(h)
+  y = acts[-1]
+  rinv = 1.0 / np.sqrt(np.maximum(np.sum(y * y, -1, keepdims=True), L2_EPS))
+  e = y * rinv
+  E = e.reshape(-1, 3, e.shape[-1])
+  B = E.shape[0]
+  loss = hinge_loss(E, margin)
+  g = hinge_loss_grad(E, margin).reshape(-1, e.shape[-1]) * B          # gradient of the SUM of hinges
+  dz = r((g - e * np.sum(e * g, -1, keepdims=True)) * rinv * np.where(e > 0, 1.0, alpha))
+  grads = [None] * len(params)
+  inputs = [xh] + acts[:-1]
+  for li in range(len(params) - 1, -1, -1):
+    grads[li] = (inputs[li].T @ dz / B, np.sum(dz, 0) / B)
+    if li > 0:
+      dz = r((dz @ W16[li].T) * np.where(acts[li - 1] > 0, 1.0, alpha))
+  return {"l2_norm": e, "loss": loss, "grads": grads}
+
+
 # --------------------------------------------------------------------------- #
 # optimizer (train.py:82,108-113,146) -- TF1 AdamOptimizer                      #
 # --------------------------------------------------------------------------- #
