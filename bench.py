@@ -298,7 +298,7 @@ def main():
     gen.manual_seed(4)
     X = torch.nn.functional.normalize(torch.randn((N, d), generator=gen, device=dev), dim=1)
     index = ops.FlatIndex(X, "L2")
-    index.search(X[:4096], k)
+    index.search(X[:nq], k)                                               # warm-up at full size (workspace, L2)
     torch.cuda.synchronize()
     e0.record()
     D, I = index.search(X[:nq], k)

@@ -65,4 +65,52 @@ static int launch_gemm(cdml_ctx* ctx, const void* A, int64_t lda, const void* B,
   return s.num_splits;
 }
 
+// Resident-B launch (K <= 256, both operands K-major).  Chooses the row-tile chunking so that units fill whole waves.
+constexpr int kResBStages = 4;
+inline bool resb_applicable(int64_t K) { return K <= 4 * kBK; }
+
+template <class Epi>
+static int launch_gemm_resb(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
+                            int64_t K, int dtype16, const Epi& epi, cudaStream_t stream) {
+  using L = ResBSmem<kBN, kResBStages>;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d(ctx, &ta, A, dtype16, K, M, lda, kBK, kBM);
+  if (rc) return rc;
+  rc = make_tmap_2d(ctx, &tb, B, dtype16, K, N, ldb, kBK, kBN);
+  if (rc) return rc;
+  ResBShape s;
+  s.M = static_cast<int>(M), s.N = static_cast<int>(N), s.K = static_cast<int>(K);
+  s.m_tiles = (s.M + kBM - 1) / kBM;
+  s.n_tiles = (s.N + kBN - 1) / kBN;
+  s.num_kb = (s.K + kBK - 1) / kBK;
+  // chunks per column block: whole waves of SMs, >= 8 row tiles per unit when possible
+  int best = 1;
+  double best_eff = -1.0;
+  const int cmax = max(1, min(s.m_tiles / 8, 4 * ctx->num_sms));
+  for (int c = 1; c <= cmax; ++c) {
+    const int tpc = (s.m_tiles + c - 1) / c;
+    const int ceff = (s.m_tiles + tpc - 1) / tpc;
+    if (ceff != c) continue;
+    const long units = static_cast<long>(s.n_tiles) * c;
+    const long waves = (units + ctx->num_sms - 1) / ctx->num_sms;
+    double eff = static_cast<double>(units) / static_cast<double>(waves * ctx->num_sms);
+    eff -= 0.15 / tpc;   // panel reload bubble per unit
+    if (eff > best_eff) best_eff = eff, best = c;
+  }
+  s.m_chunks = best;
+  s.tiles_per_chunk = (s.m_tiles + best - 1) / best;
+  s.idesc = make_idesc_f16(dtype16 == CDML_BF16 ? 1 : 0, 0, 0, kBM, kBN);
+  auto kern = gemm_resb_tcgen05_kernel<kBN, kResBStages, Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDML_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  const long units = static_cast<long>(s.n_tiles) * s.m_chunks;
+  const int grid = static_cast<int>(units < ctx->num_sms ? units : ctx->num_sms);
+  kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, s, epi);
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 1;
+}
+
 }  // namespace cdml

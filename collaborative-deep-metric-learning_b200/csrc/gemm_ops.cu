@@ -3,6 +3,17 @@
 
 namespace cdml {
 
+// K-major x K-major with K <= 256 -> resident-B kernel (3x less L2 operand traffic); everything else -> generic.
+template <int AMN, int BMN, class Epi>
+static int launch_any(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                      int dtype16, int num_splits, const Epi& epi, cudaStream_t stream) {
+  if constexpr (AMN == 0 && BMN == 0) {
+    if (num_splits <= 1 && resb_applicable(K) && M >= 8 * kBM)
+      return launch_gemm_resb(ctx, A, lda, B, ldb, M, N, K, dtype16, epi, stream);
+  }
+  return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, num_splits, epi, stream);
+}
+
 template <int AMN, int BMN>
 static int dispatch_epilogue(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
                              int64_t K, int dtype16, int epilogue, void* out, int64_t ld_out, const float* bias,
@@ -12,35 +23,35 @@ static int dispatch_epilogue(cdml_ctx* ctx, const void* A, int64_t lda, const vo
   switch (epilogue) {
     case 0: {
       EpiStoreF32<kBN> e{static_cast<float*>(out), ld_out, split_stride, bias, alpha};
-      return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, num_splits, e, stream);
+      return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, num_splits, e, stream);
     }
     case 1: {
       if (bf) {
         EpiStore16<kBN, 1> e{static_cast<uint16_t*>(out), ld_out, bias, alpha};
-        return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+        return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
       }
       EpiStore16<kBN, 0> e{static_cast<uint16_t*>(out), ld_out, bias, alpha};
-      return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+      return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
     }
     case 2: {
       CDML_REQUIRE(N <= kBN, "L2NORM epilogue needs the whole row in one tile (N=%lld > %d)", (long long)N, kBN);
       if (bf) {
         EpiL2Norm<kBN, 1> e{static_cast<float*>(out), ld_out, bias, alpha, static_cast<float*>(aux0),
                             static_cast<uint16_t*>(aux1), ld_aux1};
-        return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+        return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
       }
       EpiL2Norm<kBN, 0> e{static_cast<float*>(out), ld_out, bias, alpha, static_cast<float*>(aux0),
                           static_cast<uint16_t*>(aux1), ld_aux1};
-      return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+      return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
     }
     case 3: {
       CDML_REQUIRE(aux1 != nullptr, "MASK_LEAKY epilogue needs aux1 (the forward activation)");
       if (bf) {
         EpiMaskLeaky<kBN, 1> e{static_cast<uint16_t*>(out), ld_out, static_cast<const uint16_t*>(aux1), ld_aux1, alpha};
-        return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+        return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
       }
       EpiMaskLeaky<kBN, 0> e{static_cast<uint16_t*>(out), ld_out, static_cast<const uint16_t*>(aux1), ld_aux1, alpha};
-      return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+      return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
     }
     default:
       set_error("cdml_gemm16: unknown epilogue %d", epilogue);

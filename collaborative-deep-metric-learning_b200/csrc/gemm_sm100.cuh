@@ -415,4 +415,170 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Resident-B variant for short K (K <= 256: the data-gradient, mining and KNN scans).
+//
+// With only 4 k-blocks per tile the generic kernel re-streams 128 KB of B per 128x256 tile and is bound by L2->SM
+// bandwidth, not by the tensor pipe.  Here a CTA owns one 256-wide column block (B panel: <=4 x 32 KB, loaded once)
+// and sweeps a contiguous range of row tiles, streaming only A (16 KB per k-block): 3x less L2 traffic per tile.
+// Both operands K-major.  Work unit = (column block, chunk of row tiles).
+// ------------------------------------------------------------------------------------------------
+struct ResBShape {
+  int M, N, K;
+  int m_tiles, n_tiles, num_kb;
+  int m_chunks;         // row-tile chunks per column block
+  int tiles_per_chunk;  // ceil(m_tiles / m_chunks)
+  uint32_t idesc;
+};
+
+template <int BN, int kAStages>
+struct ResBSmem {
+  static constexpr uint32_t kABytes = kBM * kBK * 2;
+  static constexpr uint32_t kBPanel = BN * kBK * 2;
+  static constexpr uint32_t kMaxKb = 4;
+  static constexpr uint32_t kBarOff = kMaxKb * kBPanel + kAStages * kABytes;
+  static constexpr uint32_t kNumBars = 2 * kAStages + 2 + 4;
+  static constexpr uint32_t kTotal = kBarOff + kNumBars * 8 + 16 + 1024;
+};
+
+template <int BN, int kAStages, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                         const ResBShape s, const Epi epi) {
+  using L = ResBSmem<BN, kAStages>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  const uint32_t bar0 = base + L::kBarOff;
+  auto b_panel = [&](int kb) { return base + kb * L::kBPanel; };
+  auto a_smem = [&](int st) { return base + L::kMaxKb * L::kBPanel + st * L::kABytes; };
+  auto a_full = [&](int st) { return bar0 + 8u * st; };
+  auto a_empty = [&](int st) { return bar0 + 8u * (kAStages + st); };
+  const uint32_t b_full = bar0 + 8u * (2 * kAStages);
+  const uint32_t b_empty = bar0 + 8u * (2 * kAStages + 1);
+  auto tfull_bar = [&](int i) { return bar0 + 8u * (2 * kAStages + 2 + i); };
+  auto tempty_bar = [&](int i) { return bar0 + 8u * (2 * kAStages + 4 + i); };
+  const uint32_t tmem_slot = bar0 + 8u * L::kNumBars;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 512;
+  static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kAStages; ++i) {
+      mbar_init(a_full(i), 1);
+      mbar_init(a_empty(i), 1);
+    }
+    mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  if (threadIdx.x == 96) epi.block_begin();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int units = s.n_tiles * s.m_chunks;
+  // unit u -> column block u / m_chunks, row tiles [chunk*tpc, min(m_tiles, (chunk+1)*tpc))
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0, bphase = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int nblk = u / s.m_chunks, chunk = u - nblk * s.m_chunks;
+      const int t0 = chunk * s.tiles_per_chunk, t1 = min(s.m_tiles, t0 + s.tiles_per_chunk);
+      if (t0 >= t1) continue;
+      mbar_wait(b_empty, bphase ^ 1, 500);
+      mbar_arrive_expect_tx(b_full, s.num_kb * L::kBPanel);
+      for (int kb = 0; kb < s.num_kb; ++kb) tma_load_2d(b_panel(kb), &tma_b, b_full, kb * kBK, nblk * BN);
+      bphase ^= 1;
+      for (int t = t0; t < t1; ++t) {
+        for (int kb = 0; kb < s.num_kb; ++kb) {
+          mbar_wait(a_empty(stage), phase ^ 1, 100 + stage);
+          mbar_arrive_expect_tx(a_full(stage), L::kABytes);
+          tma_load_2d(a_smem(stage), &tma_a, a_full(stage), kb * kBK, t * kBM);
+          if (++stage == kAStages) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    int stage = 0, it = 0;
+    uint32_t phase = 0, bphase = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int nblk = u / s.m_chunks, chunk = u - nblk * s.m_chunks;
+      const int t0 = chunk * s.tiles_per_chunk, t1 = min(s.m_tiles, t0 + s.tiles_per_chunk);
+      if (t0 >= t1) continue;
+      mbar_wait(b_full, bphase, 600);
+      bphase ^= 1;
+      tc_fence_after();
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int as = it & 1;
+        const uint32_t ap = (it >> 1) & 1;
+        mbar_wait(tempty_bar(as), ap ^ 1, 200 + as);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < s.num_kb; ++kb) {
+          mbar_wait(a_full(stage), phase, 300 + stage);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kBK / kUK; ++k) {
+            const uint64_t ad = make_smem_desc(a_smem(stage) + k * (kUK * 2), 16, 1024);
+            const uint64_t bd = make_smem_desc(b_panel(kb) + k * (kUK * 2), 16, 1024);
+            umma_f16(tmem_d, ad, bd, s.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(a_empty(stage));
+          if (kb == s.num_kb - 1) tc_commit(tfull_bar(as));
+          if (++stage == kAStages) stage = 0, phase ^= 1;
+        }
+      }
+      tc_commit(b_empty);  // the panel may be overwritten once every MMA of this unit has retired
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    int it = 0;
+    GemmShape gs;
+    gs.M = s.M, gs.N = s.N, gs.K = s.K, gs.m_tiles = s.m_tiles, gs.n_tiles = s.n_tiles, gs.num_kb = s.num_kb;
+    gs.kb_per_split = s.num_kb, gs.num_splits = 1, gs.idesc = s.idesc;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int nblk = u / s.m_chunks, chunk = u - nblk * s.m_chunks;
+      const int t0 = chunk * s.tiles_per_chunk, t1 = min(s.m_tiles, t0 + s.tiles_per_chunk);
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int as = it & 1;
+        const uint32_t ap = (it >> 1) & 1;
+        mbar_wait(tfull_bar(as), ap, 400 + as);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+        epi.run(taddr, t * kBM + q * 32 + lane, nblk * BN, 0, gs);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 96) epi.block_end();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 }  // namespace cdml

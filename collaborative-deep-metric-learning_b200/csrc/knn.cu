@@ -37,12 +37,24 @@ __device__ __forceinline__ float key2f(uint32_t k) {
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
 __device__ __forceinline__ float pos_inf() { return __int_as_float(0x7f800000); }
 
+// Four consecutive per-column constants (thresholds / half norms) as one uniform 16-byte load; columns beyond N
+// read a sentinel so the unrolled loops need no branches.
+__device__ __forceinline__ float4 ld4_or(const float* p, int col, int N, float fill) {
+  if (col + 4 <= N) return __ldg(reinterpret_cast<const float4*>(p + col));
+  float4 r;
+  r.x = col < N ? __ldg(p + col) : fill;
+  r.y = col + 1 < N ? __ldg(p + col + 1) : fill;
+  r.z = col + 2 < N ? __ldg(p + col + 2) : fill;
+  r.w = col + 3 < N ? __ldg(p + col + 3) : fill;
+  return r;
+}
+
 // ---- pass A epilogue: thread <-> query row; best score of each 32-column (index-row) group ----
 template <int BN>
 struct EpiKnnGroupMax {
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
-  const float* h;  // [Ns] ||x||^2/2 of the sampled rows (zeros for IP)
+  const float* h;  // [Ns] ||x||^2/2 of the sampled rows (zeros for IP); 16-byte aligned
   float* gmax;     // [nq, ldg]
   int64_t ldg;
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
@@ -54,12 +66,16 @@ struct EpiKnnGroupMax {
       if (nb < s.N) {  // warp-uniform
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
+        float4 hv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hv[j] = ld4_or(h, nb + 4 * j, s.N, pos_inf());  // beyond N: score -inf
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = nb + j;
-          const float sc = col < s.N ? __uint_as_float(v[j]) - __ldg(h + col) : neg_inf();
-          best = fmaxf(best, sc);
+        for (int j = 0; j < 8; ++j) {
+          best = fmaxf(best, __uint_as_float(v[4 * j]) - hv[j].x);
+          best = fmaxf(best, __uint_as_float(v[4 * j + 1]) - hv[j].y);
+          best = fmaxf(best, __uint_as_float(v[4 * j + 2]) - hv[j].z);
+          best = fmaxf(best, __uint_as_float(v[4 * j + 3]) - hv[j].w);
         }
       }
       g[c] = best;
@@ -96,9 +112,8 @@ struct EpiKnnCollect {
     if (n > log_cap) atomicOr(log_overflow, 1);
   }
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
-    const int lane = threadIdx.x & 31;
     const bool row_ok = row < s.M;
-    const float hr = row_ok ? __ldg(h + row) : 0.f;
+    const float hr = row_ok ? __ldg(h + row) : pos_inf();  // rows beyond M: score -inf, never pass
     uint4* my_log = log + static_cast<size_t>(blockIdx.x) * log_cap;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -106,24 +121,30 @@ struct EpiKnnCollect {
       if (nb >= s.N) break;
       uint32_t v[32];
       tmem_ld_32x32(taddr + c * 32, v);
-      const float t_lane = nb + lane < s.N ? __ldg(thr + nb + lane) : pos_inf();
-      tmem_ld_wait();
+      float4 tv[8];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float sc = row_ok ? __uint_as_float(v[j]) - hr : neg_inf();
-        const float tj = __shfl_sync(0xffffffffu, t_lane, j);
-        const bool pass = sc > tj;
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m != 0u) {  // warp-uniform, rare
-          const int leader = __ffs(m) - 1;
-          unsigned int base = 0;
-          if (lane == leader) base = atomicAdd(&knn_log_cursor(), static_cast<unsigned int>(__popc(m)));
-          base = __shfl_sync(0xffffffffu, base, leader);
-          if (pass) {
-            const unsigned int pos = base + __popc(m & ((1u << lane) - 1u));
-            if (pos < log_cap)
-              my_log[pos] = make_uint4(static_cast<uint32_t>(nb + j), static_cast<uint32_t>(row), __float_as_uint(sc), 0u);
-          }
+      for (int j = 0; j < 8; ++j) tv[j] = ld4_or(thr, nb + 4 * j, s.N, pos_inf());  // beyond N: never pass
+      tmem_ld_wait();
+      // branch-free scan: one pass bit per column, for this thread's index row
+      uint32_t bits = 0u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        bits |= (__uint_as_float(v[4 * j]) - hr > tv[j].x ? 1u : 0u) << (4 * j);
+        bits |= (__uint_as_float(v[4 * j + 1]) - hr > tv[j].y ? 1u : 0u) << (4 * j + 1);
+        bits |= (__uint_as_float(v[4 * j + 2]) - hr > tv[j].z ? 1u : 0u) << (4 * j + 2);
+        bits |= (__uint_as_float(v[4 * j + 3]) - hr > tv[j].w ? 1u : 0u) << (4 * j + 3);
+      }
+      if (__any_sync(0xffffffffu, bits != 0u)) {
+        // rare path: every lane appends its own survivors (shared-memory cursor, fire-and-forget 16-byte stores)
+        while (bits != 0u) {
+          const int j = __ffs(bits) - 1;
+          bits &= bits - 1u;
+          const unsigned int pos = atomicAdd(&knn_log_cursor(), 1u);
+          float sc = 0.f;
+#pragma unroll
+          for (int t = 0; t < 32; ++t) sc = t == j ? __uint_as_float(v[t]) - hr : sc;   // keeps v[] in registers
+          if (pos < log_cap)
+            my_log[pos] = make_uint4(static_cast<uint32_t>(nb + j), static_cast<uint32_t>(row), __float_as_uint(sc), 0u);
         }
       }
     }
@@ -616,7 +637,10 @@ int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, i
     CDML_CHECK_CUDA(cudaMemsetAsync(ix->overflow, 0, sizeof(int32_t) * qc, st));
     if (ix->Ns > 0 && ix->Ns / 32 >= k) {
       EpiKnnGroupMax<kBN> ea{ix->hs, ix->gmax, ix->ldg};
-      rc = launch_gemm<0, 0>(ctx, ix->q16, ix->dpad, ix->xs16, ix->dpad, qc, ix->Ns, ix->dpad, CDML_F16, 1, ea, st);
+      if (resb_applicable(ix->dpad) && qc >= 8 * kBM)
+        rc = launch_gemm_resb(ctx, ix->q16, ix->dpad, ix->xs16, ix->dpad, qc, ix->Ns, ix->dpad, CDML_F16, ea, st);
+      else
+        rc = launch_gemm<0, 0>(ctx, ix->q16, ix->dpad, ix->xs16, ix->dpad, qc, ix->Ns, ix->dpad, CDML_F16, 1, ea, st);
       if (rc < 0) return rc;
       knn_kth_kernel<<<static_cast<int>(qc), kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, static_cast<int>(ix->Ns / 32), k,
                                                                     ix->qss, slack_scale, slack_abs, ix->thr);
@@ -625,7 +649,10 @@ int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, i
     }
     CDML_CHECK_CUDA(cudaMemsetAsync(ix->log_count, 0, sizeof(int32_t) * (ctx->num_sms + 1), st));
     EpiKnnCollect<kBN> eb{ix->h, ix->thr, ix->log, ix->log_count, ix->log_count + ctx->num_sms, ix->log_cap};
-    rc = launch_gemm<0, 0>(ctx, ix->x16, ix->dpad, ix->q16, ix->dpad, ix->N, qc, ix->dpad, CDML_F16, 1, eb, st);
+    if (resb_applicable(ix->dpad) && ix->N >= 8 * kBM)
+      rc = launch_gemm_resb(ctx, ix->x16, ix->dpad, ix->q16, ix->dpad, ix->N, qc, ix->dpad, CDML_F16, eb, st);
+    else
+      rc = launch_gemm<0, 0>(ctx, ix->x16, ix->dpad, ix->q16, ix->dpad, ix->N, qc, ix->dpad, CDML_F16, 1, eb, st);
     if (rc < 0) return rc;
     knn_bin_kernel<<<dim3(32, ctx->num_sms), 256, 0, st>>>(ix->log, ix->log_count, ix->log_cap, ix->cand_idx, ix->cand_val,
                                                           ix->cnt, kCandCap);

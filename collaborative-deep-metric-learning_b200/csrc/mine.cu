@@ -133,7 +133,10 @@ extern "C" int cdml_mine_semihard(cdml_ctx* ctx, const void* E16, int64_t ld16, 
   for (int cand = 1; cand <= 2 && rc >= 0; ++cand) {
     EpiMine<kBN> epi{dp, guid32, semi, beyond, margin, cand};
     // A: anchors = rows 0,3,6,.. (pitch 3*ld16); B: candidates = rows cand, cand+3, .. ; both K-major, K = D
-    rc = launch_gemm<0, 0>(ctx, e16, 3 * ld16, e16 + cand * ld16, 3 * ld16, B, B, D, dtype16, 1, epi, st);
+    if (resb_applicable(D) && B >= 8 * kBM)
+      rc = launch_gemm_resb(ctx, e16, 3 * ld16, e16 + cand * ld16, 3 * ld16, B, B, D, dtype16, epi, st);
+    else
+      rc = launch_gemm<0, 0>(ctx, e16, 3 * ld16, e16 + cand * ld16, 3 * ld16, B, B, D, dtype16, 1, epi, st);
   }
   if (rc >= 0) {
     mine_finalize_kernel<<<grid, 256, 0, st>>>(E32, ld32, D, semi, beyond, B, neg_row, d_an);

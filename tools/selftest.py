@@ -205,6 +205,23 @@ def group_gemm_epilogues():
   report("epi MASK_LEAKY", o, ref, 2e-3)
 
 
+def group_gemm_resb():
+  # K <= 256, K-major x K-major, M >= 1024 -> resident-B kernel
+  gemm_case(4096, 5000, 256, 0, 0)
+  gemm_case(3000, 700, 200, 0, 0)
+  gemm_case(1024, 256, 64, 0, 0, torch.bfloat16)
+  gemm_case(20000, 1000, 256, 0, 0)
+  gemm_case(1300, 70000, 256, 0, 0)
+  M, H, D = 4000, 5000, 256
+  W2 = mk((H, D), torch.float16, 0.03)
+  dz = mk((M, D), torch.float16)
+  mask = mk((M, H), torch.float16)
+  ref = (dz.float() @ W2.float().t()) * torch.where(mask.float() > 0, 1.0, 0.2)
+  o = torch.empty((M, H), device=dev, dtype=torch.float16)
+  ops.gemm16(dz, W2, M, H, D, 0, 0, EPI_MASK_LEAKY, o, alpha=0.2, aux1=mask)
+  report("resb epi MASK_LEAKY", o, ref, 2e-3)
+
+
 def group_gemm_perf():
   for (M, N, K, amn, bmn) in [(196608, 5000, 1500, 0, 1), (196608, 256, 5000, 0, 1), (196608, 5000, 256, 0, 0),
                               (1500, 5000, 196608, 1, 1), (5000, 256, 196608, 1, 1), (8192, 8192, 8192, 0, 0)]:
