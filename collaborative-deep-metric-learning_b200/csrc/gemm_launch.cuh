@@ -4,7 +4,25 @@
 #include "ctx.cuh"
 #include "gemm_sm100.cuh"
 
+#include <stdlib.h>
+
 namespace cdml {
+
+// CDML_TRACE=1: announce every tensor-core launch on stderr and synchronise after it (bring-up aid).
+inline bool trace_on() {
+  static int on = -1;
+  if (on < 0) on = getenv("CDML_TRACE") != nullptr ? 1 : 0;
+  return on == 1;
+}
+inline int trace_sync(const char* what, long M, long N, long K, int grid, cudaStream_t st) {
+  if (!trace_on()) return 0;
+  fprintf(stderr, "[cdml] %s M=%ld N=%ld K=%ld grid=%d ... ", what, M, N, K, grid);
+  fflush(stderr);
+  cudaError_t e = cudaStreamSynchronize(st);
+  fprintf(stderr, "%s\n", cudaGetErrorString(e));
+  fflush(stderr);
+  return e == cudaSuccess ? 0 : -2;
+}
 
 constexpr int kBN = 256;
 constexpr int kStages = 4;
@@ -62,6 +80,7 @@ static int launch_gemm(cdml_ctx* ctx, const void* A, int64_t lda, const void* B,
   const int grid = static_cast<int>(units < ctx->num_sms ? units : ctx->num_sms);
   kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, s, epi);
   CDML_CHECK_CUDA(cudaGetLastError());
+  if (trace_sync("gemm_tcgen05", M, N, K, grid, stream)) return -2;
   return s.num_splits;
 }
 
@@ -110,6 +129,7 @@ static int launch_gemm_resb(cdml_ctx* ctx, const void* A, int64_t lda, const voi
   const int grid = static_cast<int>(units < ctx->num_sms ? units : ctx->num_sms);
   kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, s, epi);
   CDML_CHECK_CUDA(cudaGetLastError());
+  if (trace_sync("gemm_resb", M, N, K, grid, stream)) return -2;
   return 1;
 }
 

@@ -11,7 +11,7 @@ static int launch_any(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, 
     if (num_splits <= 1 && resb_applicable(K) && M >= 8 * kBM)
       return launch_gemm_resb(ctx, A, lda, B, ldb, M, N, K, dtype16, epi, stream);
   }
-  return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, num_splits, epi, stream);
+  return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, num_splits, epi, stream);
 }
 
 template <int AMN, int BMN>
