@@ -23,7 +23,7 @@
 namespace cdml {
 
 constexpr int kCandCap = 2048;   // candidate list capacity per query
-constexpr int kKeepCap = 1024;   // survivors of the approximate prune that get an exact re-rank
+constexpr int kKeepCap = 2048;   // survivors of the approximate prune that get an exact re-rank
 constexpr int kMaxGroups = 4096; // sample groups per query (sample <= 131072 rows)
 constexpr int kRefineThreads = 256;
 
@@ -254,7 +254,7 @@ knn_refine_kernel(const float* __restrict__ Q, int64_t ldq, int d, const float* 
                   const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_val,
                   const int32_t* __restrict__ cnt, int cap, int k, int metric, float slack_scale, float slack_abs,
                   int64_t id_offset, float* __restrict__ D, int64_t* __restrict__ I, int64_t out_ld,
-                  int32_t* __restrict__ overflow) {
+                  int32_t* __restrict__ overflow, int n_all) {
   __shared__ uint32_t skey[kCandCap];
   __shared__ int32_t sidx[kCandCap];
   __shared__ unsigned long long kept[kKeepCap];
@@ -262,7 +262,7 @@ knn_refine_kernel(const float* __restrict__ Q, int64_t ldq, int d, const float* 
   __shared__ int n_keep;
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
-  const int n = cnt[q];
+  const int n = n_all > 0 ? 0 : cnt[q];   // n_all > 0: tiny database, every row is re-ranked exactly (no scan, no prune)
   if (n > cap) {  // too many nominees (mass ties): exact fallback handles this query
     if (tid == 0) overflow[q] = 1;
     return;
@@ -290,6 +290,10 @@ knn_refine_kernel(const float* __restrict__ Q, int64_t ldq, int d, const float* 
       const int pos = atomicAdd(&n_keep, 1);
       if (pos < kKeepCap) kept[pos] = static_cast<unsigned long long>(static_cast<uint32_t>(sidx[i]));
     }
+  }
+  if (n_all > 0) {
+    for (int i = tid; i < n_all; i += kRefineThreads) kept[i] = static_cast<unsigned long long>(i);
+    if (tid == 0) n_keep = n_all;
   }
   __syncthreads();
   const int nk = n_keep;
@@ -635,30 +639,38 @@ int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, i
     row_sumsq32_kernel<<<grid, 256, 0, st>>>(Qc, qc, d, ldq, ix->qss, 0.f, nullptr);
     CDML_CHECK_CUDA(cudaMemsetAsync(ix->cnt, 0, sizeof(int32_t) * qc, st));
     CDML_CHECK_CUDA(cudaMemsetAsync(ix->overflow, 0, sizeof(int32_t) * qc, st));
-    if (ix->Ns > 0 && ix->Ns / 32 >= k) {
-      EpiKnnGroupMax<kBN> ea{ix->hs, ix->gmax, ix->ldg};
-      if (resb_applicable(ix->dpad) && qc >= 8 * kBM)
-        rc = launch_gemm_resb(ctx, ix->q16, ix->dpad, ix->xs16, ix->dpad, qc, ix->Ns, ix->dpad, CDML_F16, ea, st);
-      else
-        rc = launch_gemm<0, 0>(ctx, ix->q16, ix->dpad, ix->xs16, ix->dpad, qc, ix->Ns, ix->dpad, CDML_F16, 1, ea, st);
-      if (rc < 0) return rc;
-      knn_kth_kernel<<<static_cast<int>(qc), kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, static_cast<int>(ix->Ns / 32), k,
-                                                                    ix->qss, slack_scale, slack_abs, ix->thr);
-    } else {
-      fill_f32_kernel<<<64, 256, 0, st>>>(ix->thr, qc, -INFINITY);
-    }
     CDML_CHECK_CUDA(cudaMemsetAsync(ix->log_count, 0, sizeof(int32_t) * (ctx->num_sms + 1), st));
-    EpiKnnCollect<kBN> eb{ix->h, ix->thr, ix->log, ix->log_count, ix->log_count + ctx->num_sms, ix->log_cap};
-    if (resb_applicable(ix->dpad) && ix->N >= 8 * kBM)
-      rc = launch_gemm_resb(ctx, ix->x16, ix->dpad, ix->q16, ix->dpad, ix->N, qc, ix->dpad, CDML_F16, eb, st);
-    else
-      rc = launch_gemm<0, 0>(ctx, ix->x16, ix->dpad, ix->q16, ix->dpad, ix->N, qc, ix->dpad, CDML_F16, 1, eb, st);
-    if (rc < 0) return rc;
-    knn_bin_kernel<<<dim3(32, ctx->num_sms), 256, 0, st>>>(ix->log, ix->log_count, ix->log_cap, ix->cand_idx, ix->cand_val,
-                                                          ix->cnt, kCandCap);
-    knn_refine_kernel<<<static_cast<int>(qc), kRefineThreads, 0, st>>>(
-        Qc, ldq, d, ix->qss, ix->x32, d, ix->xss, ix->cand_idx, ix->cand_val, ix->cnt, kCandCap, k, ix->metric,
-        slack_scale, slack_abs, id_offset, D + q0 * k, I + q0 * k, k, ix->overflow);
+    const bool tiny = ix->N <= kKeepCap;   // tiny database: exact re-rank of every row, no tensor-core scan
+    if (!tiny) {
+      if (ix->Ns > 0 && ix->Ns / 32 >= k) {
+        EpiKnnGroupMax<kBN> ea{ix->hs, ix->gmax, ix->ldg};
+        if (resb_applicable(ix->dpad) && qc >= 8 * kBM)
+          rc = launch_gemm_resb(ctx, ix->q16, ix->dpad, ix->xs16, ix->dpad, qc, ix->Ns, ix->dpad, CDML_F16, ea, st);
+        else
+          rc = launch_gemm<0, 0>(ctx, ix->q16, ix->dpad, ix->xs16, ix->dpad, qc, ix->Ns, ix->dpad, CDML_F16, 1, ea, st);
+        if (rc < 0) return rc;
+        knn_kth_kernel<<<static_cast<int>(qc), kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, static_cast<int>(ix->Ns / 32), k,
+                                                                      ix->qss, slack_scale, slack_abs, ix->thr);
+      } else {
+        fill_f32_kernel<<<64, 256, 0, st>>>(ix->thr, qc, -INFINITY);
+      }
+      EpiKnnCollect<kBN> eb{ix->h, ix->thr, ix->log, ix->log_count, ix->log_count + ctx->num_sms, ix->log_cap};
+      if (resb_applicable(ix->dpad) && ix->N >= 8 * kBM)
+        rc = launch_gemm_resb(ctx, ix->x16, ix->dpad, ix->q16, ix->dpad, ix->N, qc, ix->dpad, CDML_F16, eb, st);
+      else
+        rc = launch_gemm<0, 0>(ctx, ix->x16, ix->dpad, ix->q16, ix->dpad, ix->N, qc, ix->dpad, CDML_F16, 1, eb, st);
+      if (rc < 0) return rc;
+      knn_bin_kernel<<<dim3(32, ctx->num_sms), 256, 0, st>>>(ix->log, ix->log_count, ix->log_cap, ix->cand_idx, ix->cand_val,
+                                                            ix->cnt, kCandCap);
+      knn_refine_kernel<<<static_cast<int>(qc), kRefineThreads, 0, st>>>(
+          Qc, ldq, d, ix->qss, ix->x32, d, ix->xss, ix->cand_idx, ix->cand_val, ix->cnt, kCandCap, k, ix->metric,
+          slack_scale, slack_abs, id_offset, D + q0 * k, I + q0 * k, k, ix->overflow, 0);
+    } else {
+      knn_refine_kernel<<<static_cast<int>(qc), kRefineThreads, 0, st>>>(
+          Qc, ldq, d, ix->qss, ix->x32, d, ix->xss, ix->cand_idx, ix->cand_val, ix->cnt, kCandCap, k, ix->metric,
+          slack_scale, slack_abs, id_offset, D + q0 * k, I + q0 * k, k, ix->overflow, static_cast<int>(ix->N));
+      ix->stats[0] += ix->N * qc;
+    }
     CDML_CHECK_CUDA(cudaGetLastError());
     host_cnt.resize(qc), host_ovf.resize(qc);
     CDML_CHECK_CUDA(cudaMemcpyAsync(host_cnt.data(), ix->cnt, sizeof(int32_t) * qc, cudaMemcpyDeviceToHost, st));

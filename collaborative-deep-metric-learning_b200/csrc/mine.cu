@@ -3,8 +3,8 @@
 // For triplet i with dp = |a_i - p_i|^2, over the candidate rows r = 3j+1, 3j+2 (positives and negatives of the
 // batch) whose guid is neither a_i nor p_i:
 //   (1) argmin d(a_i, r) with dp < d < dp + margin, else (2) argmin d with d >= dp + margin, else (3) keep row 3i+2.
-// The B x 2B distance matrix is a tcgen05 GEMM (anchors x candidates, fp16 operands) whose epilogue keeps two running
-// (distance,row) minima per anchor in registers and folds them into global 64-bit keys with atomicMin, so the matrix
+// The B x 2B distance matrix is a tcgen05 GEMM (anchors x candidates, fp16 operands) whose epilogue keeps a running
+// (distance,row) minimum per anchor and folds it into a global 64-bit key with atomicMin, so the matrix
 // never reaches HBM.  d = 2 - 2 a.c (unit-norm embeddings).  Ties -> lowest row.
 #include <algorithm>
 
@@ -14,58 +14,62 @@ namespace cdml {
 
 constexpr unsigned long long kNoCand = ~0ull;
 
+// (1)/(2) collapse into ONE criterion: the chosen row is argmin d over valid candidates with d > dp -- if that minimum
+// is below dp+margin it is the semi-hard pick, otherwise it is exactly the closest beyond-margin pick.
+// Common path per score: d = 2-2s, keep min over (d > dp).  Only when a 32-column chunk can beat the anchor's current
+// best (a bound read from the global key at tile start; rare after the first tiles) are guids checked and the row
+// recorded.  Result: 64-bit key (float bits of d << 32 | row) folded with atomicMin -> ties go to the lowest row.
 template <int BN>
 struct EpiMine {
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   const float* dp;        // [B] exact |a-p|^2
   const int32_t* guid;    // [B,3] int32 guids
-  unsigned long long* semi;    // [B] best semi-hard (float bits << 32 | row)
-  unsigned long long* beyond;  // [B]
-  float margin;
+  unsigned long long* best;  // [B] (float bits of d) << 32 | row
   int cand;  // 1: columns are the positives' rows 3j+1, 2: the negatives' rows 3j+2
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
-    const int lane = threadIdx.x & 31;
     const bool row_ok = row < s.M;
-    const float dpi = row_ok ? __ldg(dp + row) : 0.f;
-    const float lim = dpi + margin;
-    const int ga = row_ok ? __ldg(guid + 3 * row) : 0;
-    const int gp = row_ok ? __ldg(guid + 3 * row + 1) : 0;
-    float sd = __int_as_float(0x7f800000), bd = __int_as_float(0x7f800000);
-    int sr = -1, br = -1;
+    const float inf = __int_as_float(0x7f800000);
+    const float dpi = row_ok ? __ldg(dp + row) : inf;  // rows beyond M never qualify
+    float bound = inf;
+    if (row_ok) bound = __uint_as_float(static_cast<uint32_t>(best[row] >> 32));  // 0xffffffff (NaN) when empty
+    if (!(bound == bound)) bound = inf;
+    float bd = inf;
+    int br = -1;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int nb = n0 + c * 32;
       if (nb >= s.N) break;
       uint32_t v[32];
       tmem_ld_32x32(taddr + c * 32, v);
-      // one coalesced load of the chunk's 32 candidate guids, broadcast per column by shuffle
-      const int g_lane = nb + lane < s.N ? __ldg(guid + 3 * (nb + lane) + cand) : ga;  // beyond N: never valid
       tmem_ld_wait();
+      float m = inf;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int col = nb + j;
-        const int gj = __shfl_sync(0xffffffffu, g_lane, j);
-        const float d = fmaxf(fmaf(-2.f, __uint_as_float(v[j]), 2.f), 0.f);
-        const bool valid = gj != ga && gj != gp;
-        const bool is_semi = valid && d > dpi && d < lim && d < sd;
-        const bool is_beyond = valid && d >= lim && d < bd;
-        sd = is_semi ? d : sd, sr = is_semi ? 3 * col + cand : sr;
-        bd = is_beyond ? d : bd, br = is_beyond ? 3 * col + cand : br;
+        const float d = fmaf(-2.f, __uint_as_float(v[j]), 2.f);
+        m = fminf(m, d > dpi ? d : inf);
+      }
+      if (m <= bound && m < inf) {  // rare: some column of this chunk may improve the anchor's best
+        const int ga = __ldg(guid + 3 * row), gp = __ldg(guid + 3 * row + 1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float d = fmaxf(fmaf(-2.f, __uint_as_float(v[j]), 2.f), 0.f);
+          if (d > dpi && d <= bound && nb + j < s.N && d < bd) {
+            const int gj = __ldg(guid + 3 * (nb + j) + cand);
+            if (gj != ga && gj != gp) bd = d, br = 3 * (nb + j) + cand;
+          }
+        }
+        bound = fminf(bound, bd);
       }
     }
-    if (row_ok) {
-      if (sr >= 0)
-        atomicMin(semi + row, (static_cast<unsigned long long>(__float_as_uint(sd)) << 32) | static_cast<uint32_t>(sr));
-      if (br >= 0)
-        atomicMin(beyond + row, (static_cast<unsigned long long>(__float_as_uint(bd)) << 32) | static_cast<uint32_t>(br));
-    }
+    if (br >= 0)
+      atomicMin(best + row, (static_cast<unsigned long long>(__float_as_uint(bd)) << 32) | static_cast<uint32_t>(br));
   }
 };
 
 __global__ void mine_prepare_kernel(const float* __restrict__ E, int64_t ld, int D, const int64_t* __restrict__ guid64,
                                     int64_t B, float* __restrict__ dp, int32_t* __restrict__ guid32,
-                                    unsigned long long* __restrict__ semi, unsigned long long* __restrict__ beyond) {
+                                    unsigned long long* __restrict__ best) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + warp; i < B; i += static_cast<int64_t>(gridDim.x) * 8) {
     const float* a = E + 3 * i * ld;
@@ -77,20 +81,18 @@ __global__ void mine_prepare_kernel(const float* __restrict__ E, int64_t ld, int
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) dp[i] = s, semi[i] = kNoCand, beyond[i] = kNoCand;
+    if (lane == 0) dp[i] = s, best[i] = kNoCand;
     if (lane < 3) guid32[3 * i + lane] = static_cast<int32_t>(guid64[3 * i + lane]);
   }
 }
 
 __global__ void mine_finalize_kernel(const float* __restrict__ E, int64_t ld, int D,
-                                     const unsigned long long* __restrict__ semi,
-                                     const unsigned long long* __restrict__ beyond, int64_t B,
+                                     const unsigned long long* __restrict__ best, int64_t B,
                                      int32_t* __restrict__ neg_row, float* __restrict__ d_an) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + warp; i < B; i += static_cast<int64_t>(gridDim.x) * 8) {
-    const unsigned long long ks = semi[i], kb = beyond[i];
-    const int r = ks != kNoCand ? static_cast<int>(static_cast<uint32_t>(ks))
-                                : (kb != kNoCand ? static_cast<int>(static_cast<uint32_t>(kb)) : static_cast<int>(3 * i + 2));
+    const unsigned long long kb = best[i];
+    const int r = kb != kNoCand ? static_cast<int>(static_cast<uint32_t>(kb)) : static_cast<int>(3 * i + 2);
     if (lane == 0) neg_row[i] = r;
     if (d_an != nullptr) {  // exact fp32 distance of the chosen negative
       const float* a = E + 3 * i * ld;
@@ -118,20 +120,19 @@ extern "C" int cdml_mine_semihard(cdml_ctx* ctx, const void* E16, int64_t ld16, 
   CDML_REQUIRE(B > 0 && 3 * B < (1ll << 31) && D > 0 && D % 8 == 0 && ld16 >= D && ld32 >= D,
                "cdml_mine_semihard: bad geometry B=%lld D=%d", (long long)B, D);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // scratch: dp [B] f32 | guid32 [3B] i32 | semi [B] u64 | beyond [B] u64
+  // scratch: best [B] u64 | dp [B] f32 | guid32 [3B] i32
   uint8_t* ws = nullptr;
-  const size_t bytes = static_cast<size_t>(B) * (4 + 12 + 8 + 8) + 64;
+  const size_t bytes = static_cast<size_t>(B) * (8 + 4 + 12) + 64;
   CDML_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), bytes, st));
-  unsigned long long* semi = reinterpret_cast<unsigned long long*>(ws);
-  unsigned long long* beyond = semi + B;
-  float* dp = reinterpret_cast<float*>(beyond + B);
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(ws);
+  float* dp = reinterpret_cast<float*>(best + B);
   int32_t* guid32 = reinterpret_cast<int32_t*>(dp + B);
   const int grid = static_cast<int>(std::min<int64_t>((B + 7) / 8, ctx->num_sms * 8));
-  mine_prepare_kernel<<<grid, 256, 0, st>>>(E32, ld32, D, guid, B, dp, guid32, semi, beyond);
+  mine_prepare_kernel<<<grid, 256, 0, st>>>(E32, ld32, D, guid, B, dp, guid32, best);
   int rc = 0;
   const uint16_t* e16 = static_cast<const uint16_t*>(E16);
   for (int cand = 1; cand <= 2 && rc >= 0; ++cand) {
-    EpiMine<kBN> epi{dp, guid32, semi, beyond, margin, cand};
+    EpiMine<kBN> epi{dp, guid32, best, cand};
     // A: anchors = rows 0,3,6,.. (pitch 3*ld16); B: candidates = rows cand, cand+3, .. ; both K-major, K = D
     if (resb_applicable(D) && B >= 8 * kBM)
       rc = launch_gemm_resb(ctx, e16, 3 * ld16, e16 + cand * ld16, 3 * ld16, B, B, D, dtype16, epi, st);
@@ -139,7 +140,7 @@ extern "C" int cdml_mine_semihard(cdml_ctx* ctx, const void* E16, int64_t ld16, 
       rc = launch_gemm<0, 0>(ctx, e16, 3 * ld16, e16 + cand * ld16, 3 * ld16, B, B, D, dtype16, 1, epi, st);
   }
   if (rc >= 0) {
-    mine_finalize_kernel<<<grid, 256, 0, st>>>(E32, ld32, D, semi, beyond, B, neg_row, d_an);
+    mine_finalize_kernel<<<grid, 256, 0, st>>>(E32, ld32, D, best, B, neg_row, d_an);
     rc = cudaGetLastError() == cudaSuccess ? 0 : -2;
   }
   cudaFreeAsync(ws, st);
