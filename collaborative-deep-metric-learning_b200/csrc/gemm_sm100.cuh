@@ -9,7 +9,9 @@
 // epilogue warps (tcgen05.ld -> fused bias / leaky-ReLU / L2-norm / mask -> global) overlap the next
 // tile's main loop.  Optional split-K writes fp32 partials that a separate kernel reduces in fixed order.
 //
-// Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4..7 epilogue.
+// Warp roles (384 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 spare, w4..11 epilogue.  Two
+// epilogue warps share each TMEM lane quarter and split the tile's columns, so every SM sub-partition has two
+// epilogue warps to hide TMEM / global-memory latency behind each other.
 #pragma once
 #include "common.cuh"
 
@@ -18,7 +20,7 @@ namespace cdml {
 constexpr int kBM = 128;  // tile rows   (TMEM lanes)
 constexpr int kBK = 64;   // 16-bit elements per k-block = one 128 B swizzle span
 constexpr int kUK = 16;   // K per tcgen05.mma (kind::f16)
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;  // 4 control warps + 8 epilogue warps (two per TMEM lane quarter)
 
 struct GemmShape {
   int M, N, K;
@@ -39,9 +41,10 @@ struct GemmSmem {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Epilogues.  run() is executed by each of the 4 epilogue warps; thread <-> one output row.
+// Epilogues.  run() is executed by the epilogue warps; thread <-> one output row, 32-column chunks [c0,c1) of the tile.
 //   taddr : TMEM address of (lane quarter, first accumulator column of this tile)
 //   row   : global output row of this thread;  n0 : first global column of the tile
+//   kSplitColumns: the two warps of a lane quarter each take half of the chunks; otherwise one warp takes all.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float leaky(float v, float alpha) { return v > 0.f ? v : alpha * v; }
 // Bias of the 32 columns starting at nb: one coalesced load (lane j <-> column nb+j), handed to every thread's
@@ -54,6 +57,7 @@ __device__ __forceinline__ float chunk_bias(const float* bias, int nb, int N) {
 // fp32 store (optionally bias + leaky).  Split-K partials land at out + split * split_stride.
 template <int BN>
 struct EpiStoreF32 {
+  static constexpr bool kSplitColumns = true;
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   float* out;
@@ -61,11 +65,11 @@ struct EpiStoreF32 {
   int64_t split_stride;
   const float* bias;  // nullable
   float alpha;        // 1.0f = identity
-  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int split, const GemmShape& s) const {
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int split, const GemmShape& s, int c0, int c1) const {
     float* orow = out + static_cast<int64_t>(split) * split_stride + static_cast<int64_t>(row) * ld;
     const bool row_ok = row < s.M;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c0; c < c1; ++c) {
       const int nb = n0 + c * 32;
       if (nb >= s.N) break;
       uint32_t v[32];
@@ -94,17 +98,18 @@ struct EpiStoreF32 {
 // 16-bit store of leaky(acc + bias): the hidden-layer forward epilogue (models.py:19-30).
 template <int BN, int kBf16>
 struct EpiStore16 {
+  static constexpr bool kSplitColumns = true;
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   uint16_t* out;
   int64_t ld;
   const float* bias;  // nullable
   float alpha;
-  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1) const {
     uint16_t* orow = out + static_cast<int64_t>(row) * ld;
     const bool row_ok = row < s.M;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c0; c < c1; ++c) {
       const int nb = n0 + c * 32;
       if (nb >= s.N) break;
       uint32_t v[32];
@@ -137,6 +142,7 @@ struct EpiStore16 {
 // Requires the whole row in one tile (N <= BN).  Writes e (fp32), rinv[row], optional 16-bit e.
 template <int BN, int kBf16>
 struct EpiL2Norm {
+  static constexpr bool kSplitColumns = false;  // the row norm needs every column of the row in one thread
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   float* out;  // [M, ld] fp32 embedding
@@ -146,11 +152,11 @@ struct EpiL2Norm {
   float* rinv;      // [M] nullable
   uint16_t* out16;  // [M, ld16] nullable
   int64_t ld16;
-  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1) const {
     const bool row_ok = row < s.M;
     float ss = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c0; c < c1; ++c) {
       const int nb = n0 + c * 32;
       if (nb >= s.N) break;
       uint32_t v[32];
@@ -168,7 +174,7 @@ struct EpiL2Norm {
     if (row_ok && rinv != nullptr) rinv[row] = r;
     float* orow = out + static_cast<int64_t>(row) * ld;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c0; c < c1; ++c) {
       const int nb = n0 + c * 32;
       if (nb >= s.N) break;
       uint32_t v[32];
@@ -207,6 +213,7 @@ struct EpiL2Norm {
 // forward output -- sign(leaky(z)) == sign(z), so no pre-activation stash is needed.
 template <int BN, int kBf16>
 struct EpiMaskLeaky {
+  static constexpr bool kSplitColumns = true;
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   uint16_t* out;
@@ -214,12 +221,12 @@ struct EpiMaskLeaky {
   const uint16_t* mask;
   int64_t ld_mask;
   float alpha;
-  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1) const {
     const bool row_ok = row < s.M;
     uint16_t* orow = out + static_cast<int64_t>(row) * ld;
     const uint16_t* mrow = mask + static_cast<int64_t>(row) * ld_mask;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c0; c < c1; ++c) {
       const int nb = n0 + c * 32;
       if (nb >= s.N) break;
       uint32_t v[32];
@@ -307,7 +314,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 4);
+      mbar_init(tempty_bar(i), 8);
     }
     fence_mbar_init();
   }
@@ -390,6 +397,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;
     int it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
       const int split = u / tiles, t = u - split * tiles;
@@ -399,7 +407,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_wait(tfull_bar(as), ap, 400 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      epi.run(taddr, m0 + q * 32 + lane, n0, split, s);
+      if constexpr (Epi::kSplitColumns) {
+        epi.run(taddr, m0 + q * 32 + lane, n0, split, s, half * (BN / 64), (half + 1) * (BN / 64));
+      } else {
+        if (half == 0) epi.run(taddr, m0 + q * 32 + lane, n0, split, s, 0, BN / 32);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -478,7 +490,7 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     mbar_init(b_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 4);
+      mbar_init(tempty_bar(i), 8);
     }
     fence_mbar_init();
   }
@@ -551,6 +563,7 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     int it = 0;
     GemmShape gs;
     gs.M = s.M, gs.N = s.N, gs.K = s.K, gs.m_tiles = s.m_tiles, gs.n_tiles = s.n_tiles, gs.num_kb = s.num_kb;
@@ -564,7 +577,11 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         mbar_wait(tfull_bar(as), ap, 400 + as);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-        epi.run(taddr, t * kBM + q * 32 + lane, nblk * BN, 0, gs);
+        if constexpr (Epi::kSplitColumns) {
+          epi.run(taddr, t * kBM + q * 32 + lane, nblk * BN, 0, gs, half * (BN / 64), (half + 1) * (BN / 64));
+        } else {
+          if (half == 0) epi.run(taddr, t * kBM + q * 32 + lane, nblk * BN, 0, gs, 0, BN / 32);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));

@@ -52,15 +52,18 @@ __device__ __forceinline__ float4 ld4_or(const float* p, int col, int N, float f
 // ---- pass A epilogue: thread <-> query row; best score of each 32-column (index-row) group ----
 template <int BN>
 struct EpiKnnGroupMax {
+  static constexpr bool kSplitColumns = true;
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   const float* h;  // [Ns] ||x||^2/2 of the sampled rows (zeros for IP); 16-byte aligned
   float* gmax;     // [nq, ldg]
   int64_t ldg;
-  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
-    float g[BN / 32];
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
+                                      int /*c1*/) const {
+    float g[BN / 64];   // this warp's half of the tile: 4 groups of 32 columns
 #pragma unroll
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int cc = 0; cc < BN / 64; ++cc) {
+      const int c = c0 + cc;
       const int nb = n0 + c * 32;
       float best = neg_inf();
       if (nb < s.N) {  // warp-uniform
@@ -78,13 +81,11 @@ struct EpiKnnGroupMax {
           best = fmaxf(best, __uint_as_float(v[4 * j + 3]) - hv[j].w);
         }
       }
-      g[c] = best;
+      g[cc] = best;
     }
-    if (row < s.M) {
-      float4* p = reinterpret_cast<float4*>(gmax + static_cast<int64_t>(row) * ldg + n0 / 32);
-#pragma unroll
-      for (int c = 0; c < BN / 128; ++c) p[c] = make_float4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
-    }
+    static_assert(BN == 256, "one float4 of group maxima per warp half");
+    if (row < s.M)
+      *reinterpret_cast<float4*>(gmax + static_cast<int64_t>(row) * ldg + n0 / 32 + c0) = make_float4(g[0], g[1], g[2], g[3]);
   }
 };
 
@@ -99,6 +100,7 @@ __device__ __forceinline__ unsigned int& knn_log_cursor() {
 
 template <int BN>
 struct EpiKnnCollect {
+  static constexpr bool kSplitColumns = true;
   const float* h;    // [N] ||x||^2/2 (zeros for IP)
   const float* thr;  // [nq] score bound per query
   uint4* log;        // [gridDim.x, log_cap] entries (query, row, score bits, 0)
@@ -111,12 +113,13 @@ struct EpiKnnCollect {
     log_count[blockIdx.x] = static_cast<int32_t>(n < log_cap ? n : log_cap);
     if (n > log_cap) atomicOr(log_overflow, 1);
   }
-  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
+                                      int c1) const {
     const bool row_ok = row < s.M;
     const float hr = row_ok ? __ldg(h + row) : pos_inf();  // rows beyond M: score -inf, never pass
     uint4* my_log = log + static_cast<size_t>(blockIdx.x) * log_cap;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c0; c < c1; ++c) {
       const int nb = n0 + c * 32;
       if (nb >= s.N) break;
       uint32_t v[32];

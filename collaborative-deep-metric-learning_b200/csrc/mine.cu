@@ -21,13 +21,15 @@ constexpr unsigned long long kNoCand = ~0ull;
 // recorded.  Result: 64-bit key (float bits of d << 32 | row) folded with atomicMin -> ties go to the lowest row.
 template <int BN>
 struct EpiMine {
+  static constexpr bool kSplitColumns = true;
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   const float* dp;        // [B] exact |a-p|^2
   const int32_t* guid;    // [B,3] int32 guids
   unsigned long long* best;  // [B] (float bits of d) << 32 | row
   int cand;  // 1: columns are the positives' rows 3j+1, 2: the negatives' rows 3j+2
-  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s) const {
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
+                                      int c1) const {
     const bool row_ok = row < s.M;
     const float inf = __int_as_float(0x7f800000);
     const float dpi = row_ok ? __ldg(dp + row) : inf;  // rows beyond M never qualify
@@ -37,7 +39,7 @@ struct EpiMine {
     float bd = inf;
     int br = -1;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c0; c < c1; ++c) {
       const int nb = n0 + c * 32;
       if (nb >= s.N) break;
       uint32_t v[32];
