@@ -64,12 +64,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+  // the suspend-time hint lets the hardware park the thread instead of spinning through issue slots that the
+  // epilogue warps of the same SM sub-partition need
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(0x989680)
       : "memory");
   return ok != 0;
 }
@@ -83,8 +85,9 @@ static __device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (global_timer_ns() - t0 > 4000000000ull) mbar_timeout(tag, parity);
+    if ((++spins & 255u) == 0u && global_timer_ns() - t0 > 4000000000ull) mbar_timeout(tag, parity);
   }
 }
 

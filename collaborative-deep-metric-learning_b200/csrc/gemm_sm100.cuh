@@ -221,38 +221,38 @@ struct EpiMaskLeaky {
   const uint16_t* mask;
   int64_t ld_mask;
   float alpha;
+  // 32 mask values (16 packed pairs) of columns [nb, nb+32) of this thread's row; zeros outside the matrix
+  __device__ __forceinline__ void load_mask(const uint16_t* mrow, bool row_ok, int nb, int N, uint32_t (&mk)[16]) const {
+    if (row_ok && nb + 32 <= N && (ld_mask & 7) == 0) {
+      const uint4* mp = reinterpret_cast<const uint4*>(mrow + nb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 t = __ldg(mp + j);
+        mk[4 * j] = t.x, mk[4 * j + 1] = t.y, mk[4 * j + 2] = t.z, mk[4 * j + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t lo = (row_ok && nb + 2 * j < N) ? mrow[nb + 2 * j] : 0u;
+        const uint32_t hi = (row_ok && nb + 2 * j + 1 < N) ? mrow[nb + 2 * j + 1] : 0u;
+        mk[j] = lo | (hi << 16);
+      }
+    }
+  }
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1) const {
     const bool row_ok = row < s.M;
     uint16_t* orow = out + static_cast<int64_t>(row) * ld;
     const uint16_t* mrow = mask + static_cast<int64_t>(row) * ld_mask;
+    uint32_t mk[16], mk_next[16];
+    load_mask(mrow, row_ok && n0 + c0 * 32 < s.N, n0 + c0 * 32, s.N, mk);
 #pragma unroll 1
     for (int c = c0; c < c1; ++c) {
       const int nb = n0 + c * 32;
       if (nb >= s.N) break;
       uint32_t v[32];
       tmem_ld_32x32(taddr + c * 32, v);
-      const bool vec = nb + 32 <= s.N && (ld & 7) == 0 && (ld_mask & 7) == 0;
-      uint32_t mk[16];
-      if (row_ok) {
-        if (vec) {
-          const uint4* mp = reinterpret_cast<const uint4*>(mrow + nb);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 t = __ldg(mp + j);
-            mk[4 * j] = t.x, mk[4 * j + 1] = t.y, mk[4 * j + 2] = t.z, mk[4 * j + 3] = t.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const uint32_t lo = (nb + 2 * j < s.N) ? mrow[nb + 2 * j] : 0u;
-            const uint32_t hi = (nb + 2 * j + 1 < s.N) ? mrow[nb + 2 * j + 1] : 0u;
-            mk[j] = lo | (hi << 16);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) mk[j] = 0u;
-      }
+      // the forward activation of the NEXT chunk is requested now, so its DRAM latency hides behind this chunk
+      load_mask(mrow, row_ok && c + 1 < c1 && nb + 32 < s.N, nb + 32, s.N, mk_next);
       tmem_ld_wait();
       uint32_t pk[16];
 #pragma unroll
@@ -263,7 +263,7 @@ struct EpiMaskLeaky {
         pk[j] = pack2<kBf16>(x0, x1);
       }
       if (row_ok) {
-        if (vec) {
+        if (nb + 32 <= s.N && (ld & 7) == 0) {
           uint4* p = reinterpret_cast<uint4*>(orow + nb);
 #pragma unroll
           for (int j = 0; j < 4; ++j) p[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -273,6 +273,8 @@ struct EpiMaskLeaky {
             if (nb + j < s.N) orow[nb + j] = static_cast<uint16_t>(pk[j >> 1] >> ((j & 1) * 16));
         }
       }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) mk[j] = mk_next[j];
     }
   }
 };

@@ -46,6 +46,8 @@ def gemm_case(M, N, K, amn, bmn, dt=torch.float16, splits=1, tag=""):
     out = torch.full((M, N), float("nan"), device=dev)
     ops.gemm16(A, B, M, N, K, amn, bmn, EPI_STORE_F32, out)
   else:
+    if splits <= 0:
+      splits = max(ops.auto_splits(A, M, N, K), 1)
     parts = torch.full((splits, M, N), float("nan"), device=dev)
     used = ops.gemm16(A, B, M, N, K, amn, bmn, EPI_STORE_F32, parts, num_splits=splits, split_stride=M * N)
     out = torch.empty((M, N), device=dev)
