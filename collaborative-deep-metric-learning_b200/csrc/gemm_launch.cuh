@@ -69,6 +69,9 @@ static int launch_gemm(cdml_ctx* ctx, const void* A, int64_t lda, const void* B,
   s.kb_per_split = (s.num_kb + num_splits - 1) / num_splits;
   s.num_splits = (s.num_kb + s.kb_per_split - 1) / s.kb_per_split;
   s.idesc = make_idesc_f16(dtype16 == CDML_BF16 ? 1 : 0, AMN, BMN, kBM, kBN);
+  // Split-K (weight gradients): every k-block of the larger operand should be shared by ALL tiles that run
+  // concurrently, so that it is fetched from HBM once per split.
+  s.m_fastest = (s.num_splits > 1 && N >= M) ? 1 : 0;
 
   auto kern = gemm_tcgen05_kernel<AMN, BMN, kBN, kStages, Epi>;
   static bool attr_set = false;  // per template instantiation
@@ -85,7 +88,7 @@ static int launch_gemm(cdml_ctx* ctx, const void* A, int64_t lda, const void* B,
 }
 
 // Resident-B launch (K <= 256, both operands K-major).  Chooses the row-tile chunking so that units fill whole waves.
-constexpr int kResBStages = 4;
+constexpr int kResBStages = 6;  // 128 KB B panel + 6 x 16 KB A stages = 224 KB of the 227 KB
 inline bool resb_applicable(int64_t K) { return K <= 4 * kBK; }
 
 template <class Epi>

@@ -28,6 +28,7 @@ struct GemmShape {
   int num_kb;        // ceil(K / 64)
   int kb_per_split;  // k-blocks handled by one split
   int num_splits;    // every split owns >= 1 k-block
+  int m_fastest;     // tile order inside a split: 1 = consecutive CTAs walk down M (share the B panel), 0 = along N
   uint32_t idesc;
 };
 
@@ -339,7 +340,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint32_t phase = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int split = u / tiles, t = u - split * tiles;
-      const int m0 = (t / s.n_tiles) * kBM, n0 = (t % s.n_tiles) * BN;
+      const int m0 = (s.m_fastest ? t % s.m_tiles : t / s.n_tiles) * kBM;
+      const int n0 = (s.m_fastest ? t / s.m_tiles : t % s.n_tiles) * BN;
       const int kb0 = split * s.kb_per_split;
       const int kb1 = min(s.num_kb, kb0 + s.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -403,7 +405,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     int it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
       const int split = u / tiles, t = u - split * tiles;
-      const int m0 = (t / s.n_tiles) * kBM, n0 = (t % s.n_tiles) * BN;
+      const int m0 = (s.m_fastest ? t % s.m_tiles : t / s.n_tiles) * kBM;
+      const int n0 = (s.m_fastest ? t / s.m_tiles : t % s.n_tiles) * BN;
       const int as = it & 1;
       const uint32_t ap = (it >> 1) & 1;
       mbar_wait(tfull_bar(as), ap, 400 + as);
@@ -569,7 +572,7 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     int it = 0;
     GemmShape gs;
     gs.M = s.M, gs.N = s.N, gs.K = s.K, gs.m_tiles = s.m_tiles, gs.n_tiles = s.n_tiles, gs.num_kb = s.num_kb;
-    gs.kb_per_split = s.num_kb, gs.num_splits = 1, gs.idesc = s.idesc;
+    gs.kb_per_split = s.num_kb, gs.num_splits = 1, gs.m_fastest = 0, gs.idesc = s.idesc;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int nblk = u / s.m_chunks, chunk = u - nblk * s.m_chunks;
       const int t0 = chunk * s.tiles_per_chunk, t1 = min(s.m_tiles, t0 + s.tiles_per_chunk);

@@ -243,6 +243,56 @@ colsum16_stage1(const uint16_t* __restrict__ X, int64_t R, int64_t N, int64_t ld
   }
 }
 
+// Vectorised variant: each lane owns 8 consecutive columns (one 16-byte load per row), a warp covers 256 columns,
+// the 8 warps of the block stride the rows of the chunk.  Needs ld % 8 == 0 and a 16-byte aligned base.
+constexpr int kColStripV = 256;
+template <int kBf16>
+__global__ void __launch_bounds__(kRowThreads)
+colsum16_stage1_vec(const uint16_t* __restrict__ X, int64_t R, int64_t N, int64_t ld, int64_t rows_per_chunk,
+                    float* __restrict__ partial) {
+  __shared__ float sh[kWarpsPerBlock][kColStripV];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kColStripV + 8 * lane;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_chunk;
+  const int64_t r1 = r0 + rows_per_chunk < R ? r0 + rows_per_chunk : R;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  if (c0 + 8 <= N) {
+    int64_t r = r0 + warp;
+    for (; r + 3 * kWarpsPerBlock < r1; r += 4 * kWarpsPerBlock) {   // 4 independent 16-byte loads in flight
+      uint4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = __ldg(reinterpret_cast<const uint4*>(X + (r + u * kWarpsPerBlock) * ld + c0));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 f0 = unpack2<kBf16>(t[u].x), f1 = unpack2<kBf16>(t[u].y), f2 = unpack2<kBf16>(t[u].z),
+                     f3 = unpack2<kBf16>(t[u].w);
+        a[0] += f0.x, a[1] += f0.y, a[2] += f1.x, a[3] += f1.y, a[4] += f2.x, a[5] += f2.y, a[6] += f3.x, a[7] += f3.y;
+      }
+    }
+    for (; r < r1; r += kWarpsPerBlock) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(X + r * ld + c0));
+      const float2 f0 = unpack2<kBf16>(t.x), f1 = unpack2<kBf16>(t.y), f2 = unpack2<kBf16>(t.z), f3 = unpack2<kBf16>(t.w);
+      a[0] += f0.x, a[1] += f0.y, a[2] += f1.x, a[3] += f1.y, a[4] += f2.x, a[5] += f2.y, a[6] += f3.x, a[7] += f3.y;
+    }
+  } else {
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < N)
+        for (int64_t r = r0 + warp; r < r1; r += kWarpsPerBlock) a[j] += unpack2<kBf16>(static_cast<uint32_t>(X[r * ld + c0 + j])).x;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[warp][8 * lane + j] = a[j];
+  __syncthreads();
+  {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; ++w) t += sh[w][threadIdx.x];
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * kColStripV + threadIdx.x;
+    if (c < N) partial[static_cast<int64_t>(blockIdx.y) * N + c] = t;
+  }
+}
+
 __global__ void sum_partials_kernel(const float* __restrict__ parts, int num_parts, int64_t stride, int64_t n,
                                     float scale, float* __restrict__ out) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -442,11 +492,16 @@ int cdml_colsum16(cdml_ctx* ctx, const void* X, int64_t R, int64_t N, int64_t ld
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t chunks = cdml_colsum_workspace_floats(R, N) / N;
   const int64_t rows_per_chunk = (R + chunks - 1) / chunks;
-  dim3 grid(static_cast<unsigned>((N + kColStrip - 1) / kColStrip), static_cast<unsigned>(chunks));
-  if (dtype16 == CDML_BF16)
-    colsum16_stage1<1><<<grid, kRowThreads, 0, st>>>(static_cast<const uint16_t*>(X), R, N, ld, rows_per_chunk, workspace);
-  else
-    colsum16_stage1<0><<<grid, kRowThreads, 0, st>>>(static_cast<const uint16_t*>(X), R, N, ld, rows_per_chunk, workspace);
+  const uint16_t* x = static_cast<const uint16_t*>(X);
+  if (ld % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    dim3 grid(static_cast<unsigned>((N + kColStripV - 1) / kColStripV), static_cast<unsigned>(chunks));
+    if (dtype16 == CDML_BF16) colsum16_stage1_vec<1><<<grid, kRowThreads, 0, st>>>(x, R, N, ld, rows_per_chunk, workspace);
+    else colsum16_stage1_vec<0><<<grid, kRowThreads, 0, st>>>(x, R, N, ld, rows_per_chunk, workspace);
+  } else {
+    dim3 grid(static_cast<unsigned>((N + kColStrip - 1) / kColStrip), static_cast<unsigned>(chunks));
+    if (dtype16 == CDML_BF16) colsum16_stage1<1><<<grid, kRowThreads, 0, st>>>(x, R, N, ld, rows_per_chunk, workspace);
+    else colsum16_stage1<0><<<grid, kRowThreads, 0, st>>>(x, R, N, ld, rows_per_chunk, workspace);
+  }
   CDML_CHECK_CUDA(cudaGetLastError());
   return cdml_sum_partials(ctx, workspace, static_cast<int>(chunks), N, N, 1.0f, out, stream);
 }
