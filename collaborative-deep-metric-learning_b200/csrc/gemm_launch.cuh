@@ -88,7 +88,7 @@ static int launch_gemm(cdml_ctx* ctx, const void* A, int64_t lda, const void* B,
 }
 
 // Resident-B launch (K <= 256, both operands K-major).  Chooses the row-tile chunking so that units fill whole waves.
-constexpr int kResBStages = 6;  // 128 KB B panel + 6 x 16 KB A stages = 224 KB of the 227 KB
+constexpr int kResBStages = 4;  // 6 stages (224 KB) leave no L1 for the epilogue's global loads and measured slower
 inline bool resb_applicable(int64_t K) { return K <= 4 * kBK; }
 
 template <class Epi>
