@@ -126,7 +126,7 @@ def run_reference(args):
           "note": "TensorFlow 1.13 / faiss are not installable offline; this arm times the oracle port of the reference "
                   "path (numpy/BLAS, all host threads) on a bounded sample of the workload; the reference has no in-batch "
                   "mining (SURVEY Q4), so the port trains on the reader's random negatives"}
-  print(json.dumps(line))
+  emit(line)
 
 
 def workload_config(args, mine):
@@ -138,6 +138,16 @@ def workload_config(args, mine):
 
 
 # --------------------------------------------------------------------------------------------------
+def emit(line):
+  """The one JSON line goes to the REAL stdout; everything else this process prints (NCCL banners, library chatter)
+  was redirected to stderr at start-up."""
+  os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
@@ -327,7 +337,7 @@ def main():
     line["cpu_baseline"] = cpu_train_baseline()
     if not args.no_knn:
       line["knn"]["cpu_baseline"] = cpu_knn_baseline(N=min(args.knn_n, 1000000))
-  print(json.dumps(line))
+  emit(line)
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()

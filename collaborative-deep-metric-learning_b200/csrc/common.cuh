@@ -158,6 +158,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 16-byte shared-memory accesses by shared-space address (epilogue staging buffers)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
 //   K-major : rows of 128 B (64 x 16-bit along K); 8-row groups are SBO = 1024 B apart.
 //   MN-major: 128 B (64 x 16-bit along M/N) per K row; 8-K-row groups SBO = 1024 B apart,

@@ -89,7 +89,11 @@ static int launch_gemm(cdml_ctx* ctx, const void* A, int64_t lda, const void* B,
 
 // Resident-B launch (K <= 256, both operands K-major).  Chooses the row-tile chunking so that units fill whole waves.
 constexpr int kResBStages = 4;  // 6 stages (224 KB) leave no L1 for the epilogue's global loads and measured slower
-inline bool resb_applicable(int64_t K) { return K <= 4 * kBK; }
+inline bool resb_applicable(int64_t K) {
+  static int off = -1;   // CDML_NO_RESB=1 forces the generic kernel (A/B measurement aid)
+  if (off < 0) off = getenv("CDML_NO_RESB") != nullptr ? 1 : 0;
+  return off == 0 && K <= 4 * kBK;
+}
 
 template <class Epi>
 static int launch_gemm_resb(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,

@@ -53,6 +53,14 @@ static int dispatch_epilogue(cdml_ctx* ctx, const void* A, int64_t lda, const vo
       EpiMaskLeaky<kBN, 0> e{static_cast<uint16_t*>(out), ld_out, static_cast<const uint16_t*>(aux1), ld_aux1, alpha};
       return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
     }
+    case 100: {
+      EpiNull<kBN, 0> e{static_cast<float*>(out)};
+      return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+    }
+    case 101: {
+      EpiNull<kBN, 1> e{static_cast<float*>(out)};
+      return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+    }
     default:
       set_error("cdml_gemm16: unknown epilogue %d", epilogue);
       return -1;

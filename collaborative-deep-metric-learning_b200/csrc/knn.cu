@@ -59,7 +59,7 @@ struct EpiKnnGroupMax {
   float* gmax;     // [nq, ldg]
   int64_t ldg;
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
-                                      int /*c1*/) const {
+                                      int /*c1*/, uint32_t /*stg*/) const {
     float g[BN / 64];   // this warp's half of the tile: 4 groups of 32 columns
 #pragma unroll
     for (int cc = 0; cc < BN / 64; ++cc) {
@@ -114,7 +114,7 @@ struct EpiKnnCollect {
     if (n > log_cap) atomicOr(log_overflow, 1);
   }
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
-                                      int c1) const {
+                                      int c1, uint32_t /*stg*/) const {
     const bool row_ok = row < s.M;
     const float hr = row_ok ? __ldg(h + row) : pos_inf();  // rows beyond M: score -inf, never pass
     uint4* my_log = log + static_cast<size_t>(blockIdx.x) * log_cap;

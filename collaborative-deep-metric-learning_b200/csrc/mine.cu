@@ -29,7 +29,7 @@ struct EpiMine {
   unsigned long long* best;  // [B] (float bits of d) << 32 | row
   int cand;  // 1: columns are the positives' rows 3j+1, 2: the negatives' rows 3j+2
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
-                                      int c1) const {
+                                      int c1, uint32_t /*stg*/) const {
     const bool row_ok = row < s.M;
     const float inf = __int_as_float(0x7f800000);
     const float dpi = row_ok ? __ldg(dp + row) : inf;  // rows beyond M never qualify

@@ -253,6 +253,35 @@ def group_gemm_perf():
                                                                            splits, ms, 2.0 * M * N * K / ms / 1e9), flush=True)
 
 
+
+
+def group_gemm_null():
+  """main loop only (epi 100) / + TMEM reads (epi 101) / + fp16 stores (epi 1), each shape timed 3x in one process"""
+  shapes = [(196608, 5000, 256, 0, 0), (65536, 65536, 256, 0, 0), (196608, 5000, 1500, 0, 1), (8192, 8192, 8192, 0, 0)]
+  for (M, N, K, amn, bmn) in shapes:
+    A = mk((K, (M + 7) // 8 * 8) if amn else (M, (K + 7) // 8 * 8), torch.float16, 0.05)
+    B = mk((K, N) if bmn else (N, (K + 7) // 8 * 8), torch.float16, 0.05)
+    out = torch.empty((M, N), device=dev, dtype=torch.float16) if M * N <= 2 ** 31 else torch.empty((16,), device=dev)
+    for epi in (100, 101, 1):
+      if epi == 1 and out.dim() == 1:
+        continue
+      res = []
+      for rep in range(3):
+        for _ in range(2):
+          ops.gemm16(A, B, M, N, K, amn, bmn, epi, out, ld_out=N)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+          ops.gemm16(A, B, M, N, K, amn, bmn, epi, out, ld_out=N)
+        e1.record()
+        torch.cuda.synchronize()
+        res.append(e0.elapsed_time(e1) / 5)
+      ms = min(res)
+      print("null M=%d N=%d K=%d epi=%d resb=%s: %.3f ms (runs %s)  %.1f TFLOP/s" %
+            (M, N, K, epi, "off" if os.environ.get("CDML_NO_RESB") else "on", ms, ["%.3f" % r for r in res], 2.0 * M * N * K / ms / 1e9), flush=True)
+
+
 if __name__ == "__main__":
   t0 = time.time()
   globals()["group_" + sys.argv[1]]()
