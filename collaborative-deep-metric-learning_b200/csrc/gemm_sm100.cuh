@@ -268,37 +268,61 @@ struct EpiMaskLeaky {
   const uint16_t* mask;
   int64_t ld_mask;
   float alpha;
-  // 32 mask values (16 packed pairs) of columns [nb, nb+32) of this thread's row; zeros outside the matrix
-  __device__ __forceinline__ void load_mask(const uint16_t* mrow, bool row_ok, int nb, int N, uint32_t (&mk)[16]) const {
-    if (row_ok && nb + 32 <= N && (ld_mask & 7) == 0) {
-      const uint4* mp = reinterpret_cast<const uint4*>(mrow + nb);
+  // Coalesced fetch of a 32-row x 32-column mask chunk: lane l reads 16 bytes of row 8i + l/4 (i = 0..3), so one load
+  // instruction covers 8 rows x 64 contiguous bytes.  Zeros outside the matrix.
+  __device__ __forceinline__ void fetch_mask(int row_base, int nb, int M, int N, bool active, uint4 (&raw)[4]) const {
+    const int lane = threadIdx.x & 31;
+    const int col = nb + 8 * (lane & 3);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 t = __ldg(mp + j);
-        mk[4 * j] = t.x, mk[4 * j + 1] = t.y, mk[4 * j + 2] = t.z, mk[4 * j + 3] = t.w;
-      }
-    } else {
+    for (int i = 0; i < 4; ++i) {
+      const int grow = row_base + 8 * i + (lane >> 2);
+      raw[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (active && grow < M) {
+        const uint16_t* p = mask + static_cast<int64_t>(grow) * ld_mask + col;
+        if ((ld_mask & 7) == 0 && col + 8 <= N) {
+          raw[i] = __ldg(reinterpret_cast<const uint4*>(p));
+        } else {
+          uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const uint32_t lo = (row_ok && nb + 2 * j < N) ? mrow[nb + 2 * j] : 0u;
-        const uint32_t hi = (row_ok && nb + 2 * j + 1 < N) ? mrow[nb + 2 * j + 1] : 0u;
-        mk[j] = lo | (hi << 16);
+          for (int e = 0; e < 8; ++e)
+            if (col + e < N) w[e >> 1] |= static_cast<uint32_t>(p[e]) << ((e & 1) * 16);
+          raw[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
     }
   }
-  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1, uint32_t stg) const {
-    const bool row_ok = row < s.M;
-    const uint16_t* mrow = mask + static_cast<int64_t>(row) * ld_mask;
-    uint32_t mk[16], mk_next[16];
-    load_mask(mrow, row_ok && n0 + c0 * 32 < s.N, n0 + c0 * 32, s.N, mk);
+  // Through the warp's staging buffer: every thread ends up with the 32 mask values of ITS row.
+  __device__ __forceinline__ void transpose_mask(uint32_t stg, const uint4 (&raw)[4], uint32_t (&mk)[16]) const {
+    const int lane = threadIdx.x & 31;
+    const int cch = lane & 3;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = 8 * i + (lane >> 2);
+      sts128(stg + r * 64 + ((cch ^ ((r >> 1) & 3)) << 4), raw[i].x, raw[i].y, raw[i].z, raw[i].w);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 t = lds128(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+      mk[4 * j] = t.x, mk[4 * j + 1] = t.y, mk[4 * j + 2] = t.z, mk[4 * j + 3] = t.w;
+    }
+  }
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1,
+                                      uint32_t stg) const {
+    const int row_base = row - static_cast<int>(threadIdx.x & 31);
+    uint4 raw[4];
+    fetch_mask(row_base, n0 + c0 * 32, s.M, s.N, n0 + c0 * 32 < s.N, raw);
 #pragma unroll 1
     for (int c = c0; c < c1; ++c) {
       const int nb = n0 + c * 32;
       if (nb >= s.N) break;
       uint32_t v[32];
       tmem_ld_32x32(taddr + c * 32, v);
+      uint32_t mk[16];
+      transpose_mask(stg, raw, mk);
       // the forward activation of the NEXT chunk is requested now, so its DRAM latency hides behind this chunk
-      load_mask(mrow, row_ok && c + 1 < c1 && nb + 32 < s.N, nb + 32, s.N, mk_next);
+      fetch_mask(row_base, nb + 32, s.M, s.N, c + 1 < c1 && nb + 32 < s.N, raw);
       tmem_ld_wait();
       uint32_t pk[16];
 #pragma unroll
@@ -308,9 +332,7 @@ struct EpiMaskLeaky {
         const float x1 = __uint_as_float(v[2 * j + 1]) * (m.y > 0.f ? 1.f : alpha);
         pk[j] = pack2<kBf16>(x0, x1);
       }
-      store_chunk16(out, ld, row - static_cast<int>(threadIdx.x & 31), nb, s.M, s.N, stg, pk);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) mk[j] = mk_next[j];
+      store_chunk16(out, ld, row_base, nb, s.M, s.N, stg, pk);
     }
   }
 };

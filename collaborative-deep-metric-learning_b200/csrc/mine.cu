@@ -28,14 +28,21 @@ struct EpiMine {
   const int32_t* guid;    // [B,3] int32 guids
   unsigned long long* best;  // [B] (float bits of d) << 32 | row
   int cand;  // 1: columns are the positives' rows 3j+1, 2: the negatives' rows 3j+2
+  // Works in score space: d = 2 - 2s, so "d > dp" is "s < s_hi" and the closest candidate is the LARGEST such score.
+  // Hot loop per score: one compare + one predicated max.  The chunk's 32 candidate guids are parked in the warp's
+  // staging buffer (one coalesced load per chunk) so the rare re-scan needs no global loads.
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
-                                      int c1, uint32_t /*stg*/) const {
+                                      int c1, uint32_t stg) const {
+    const int lane = threadIdx.x & 31;
     const bool row_ok = row < s.M;
     const float inf = __int_as_float(0x7f800000);
-    const float dpi = row_ok ? __ldg(dp + row) : inf;  // rows beyond M never qualify
-    float bound = inf;
-    if (row_ok) bound = __uint_as_float(static_cast<uint32_t>(best[row] >> 32));  // 0xffffffff (NaN) when empty
-    if (!(bound == bound)) bound = inf;
+    const float dpi = row_ok ? __ldg(dp + row) : inf;
+    const float s_hi = row_ok ? 1.f - 0.5f * dpi : -inf;      // scores must stay BELOW this (rows beyond M: nothing does)
+    const int ga = row_ok ? __ldg(guid + 3 * row) : 0, gp = row_ok ? __ldg(guid + 3 * row + 1) : 0;
+    float bound_d = inf;                                       // best distance known for this anchor (any tile)
+    if (row_ok) bound_d = __uint_as_float(static_cast<uint32_t>(best[row] >> 32));
+    if (!(bound_d == bound_d)) bound_d = inf;                  // empty key reads as NaN
+    float s_lo = 1.f - 0.5f * bound_d;                         // a chunk matters only if it holds a score >= this
     float bd = inf;
     int br = -1;
 #pragma unroll 1
@@ -44,24 +51,29 @@ struct EpiMine {
       if (nb >= s.N) break;
       uint32_t v[32];
       tmem_ld_32x32(taddr + c * 32, v);
+      const int g_lane = nb + lane < s.N ? __ldg(guid + 3 * (nb + lane) + cand) : ga;   // beyond N: never valid
+      __syncwarp();
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + lane * 4), "r"(g_lane) : "memory");
       tmem_ld_wait();
-      float m = inf;
+      float m = -inf;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float d = fmaf(-2.f, __uint_as_float(v[j]), 2.f);
-        m = fminf(m, d > dpi ? d : inf);
+        const float sc = __uint_as_float(v[j]);
+        m = sc < s_hi ? fmaxf(m, sc) : m;
       }
-      if (m <= bound && m < inf) {  // rare: some column of this chunk may improve the anchor's best
-        const int ga = __ldg(guid + 3 * row), gp = __ldg(guid + 3 * row + 1);
+      __syncwarp();                                            // guids visible to every lane of the warp
+      if (m >= s_lo && m > -inf) {                             // rare: this chunk may improve the anchor's best
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float d = fmaxf(fmaf(-2.f, __uint_as_float(v[j]), 2.f), 0.f);
-          if (d > dpi && d <= bound && nb + j < s.N && d < bd) {
-            const int gj = __ldg(guid + 3 * (nb + j) + cand);
+          const float sc = __uint_as_float(v[j]);
+          const float d = fmaxf(fmaf(-2.f, sc, 2.f), 0.f);
+          if (sc < s_hi && sc >= s_lo && d > dpi && d < bd) {
+            int gj;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gj) : "r"(stg + j * 4) : "memory");
             if (gj != ga && gj != gp) bd = d, br = 3 * (nb + j) + cand;
           }
         }
-        bound = fminf(bound, bd);
+        if (br >= 0) s_lo = fmaxf(s_lo, 1.f - 0.5f * bd);
       }
     }
     if (br >= 0)
