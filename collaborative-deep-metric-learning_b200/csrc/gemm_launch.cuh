@@ -3,6 +3,7 @@
 #include "../../include/cdml.h"
 #include "ctx.cuh"
 #include "gemm_sm100.cuh"
+#include "gemm2_sm100.cuh"
 
 #include <stdlib.h>
 
@@ -47,9 +48,69 @@ inline int pick_splits(int num_sms, int tiles, int num_kb) {
   return best;
 }
 
+// CDML_2CTA=0 disables the CTA-pair kernel (A/B measurement aid); it is used for tiles of >= 8 k-blocks.
+inline bool two_cta_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CDML_2CTA");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+template <int AMN, int BMN, class Epi>
+static int launch_gemm2(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
+                        int64_t K, int dtype16, int num_splits, const Epi& epi, cudaStream_t stream) {
+  using L = Gemm2Smem;
+  CUtensorMap ta, tb;
+  int rc;
+  if (AMN == 0) rc = make_tmap_2d(ctx, &ta, A, dtype16, K, M, lda, kBK, kBM);
+  else rc = make_tmap_2d(ctx, &ta, A, dtype16, M, K, lda, 64, kBK);
+  if (rc) return rc;
+  if (BMN == 0) rc = make_tmap_2d(ctx, &tb, B, dtype16, K, N, ldb, kBK, kBN2 / 2);
+  else rc = make_tmap_2d(ctx, &tb, B, dtype16, N, K, ldb, 64, kBK);
+  if (rc) return rc;
+  GemmShape s;
+  s.M = static_cast<int>(M), s.N = static_cast<int>(N), s.K = static_cast<int>(K);
+  s.m_tiles = (s.M + 2 * kBM - 1) / (2 * kBM);   // 256-row pair tiles
+  s.n_tiles = (s.N + kBN2 - 1) / kBN2;
+  s.num_kb = (s.K + kBK - 1) / kBK;
+  num_splits = max(1, min(num_splits, s.num_kb));
+  s.kb_per_split = (s.num_kb + num_splits - 1) / num_splits;
+  s.num_splits = (s.num_kb + s.kb_per_split - 1) / s.kb_per_split;
+  s.idesc = make_idesc_f16(dtype16 == CDML_BF16 ? 1 : 0, AMN, BMN, 2 * kBM, kBN2);
+  s.m_fastest = (s.num_splits > 1 && N >= M) ? 1 : 0;
+  auto kern = gemm2_tcgen05_kernel<AMN, BMN, Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDML_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  const long units = static_cast<long>(s.m_tiles) * s.n_tiles * s.num_splits;
+  const int clusters = static_cast<int>(units < ctx->num_sms / 2 ? units : ctx->num_sms / 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CDML_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, s, epi));
+  if (trace_sync("gemm2_tcgen05", M, N, K, 2 * clusters, stream)) return -2;
+  return s.num_splits;
+}
+
 template <int AMN, int BMN, class Epi>
 static int launch_gemm(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
                        int64_t K, int dtype16, int num_splits, const Epi& epi, cudaStream_t stream) {
+  {
+    const int64_t kb_per = ((K + kBK - 1) / kBK + max(num_splits, 1) - 1) / max(num_splits, 1);
+    if (two_cta_enabled() && M >= 2 * kBM && kb_per >= 8)
+      return launch_gemm2<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, num_splits, epi, stream);
+  }
   using L = GemmSmem<kBN, kStages>;
   CUtensorMap ta, tb;
   int rc;

@@ -3,6 +3,6 @@
 mkdir -p gpurun_out
 for g in "$@"; do
   echo "=== $g ===" | tee -a gpurun_out/selftest.log
-  timeout 120 python tools/selftest.py "$g" 2>&1 | tail -80 | tee -a gpurun_out/selftest.log
+  timeout 60 python tools/selftest.py "$g" 2>&1 | tail -80 | tee -a gpurun_out/selftest.log
   echo "exit=${PIPESTATUS[0]}" | tee -a gpurun_out/selftest.log
 done
