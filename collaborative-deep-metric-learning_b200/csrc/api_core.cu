@@ -33,6 +33,22 @@ int make_tmap_2d(cdml_ctx* ctx, CUtensorMap* map, const void* ptr, int dtype16, 
                (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
   return 0;
 }
+void* ctx_scratch(cdml_ctx* ctx, size_t bytes) {
+  if (ctx->scratch_bytes >= bytes) return ctx->scratch;
+  if (ctx->scratch != nullptr) {
+    cudaDeviceSynchronize();   // growth is rare; nobody may still be using the old block
+    cudaFree(ctx->scratch);
+    ctx->scratch = nullptr, ctx->scratch_bytes = 0;
+  }
+  const size_t want = bytes + bytes / 2 + (1 << 20);
+  if (cudaMalloc(&ctx->scratch, want) != cudaSuccess) {
+    ctx->scratch = nullptr;
+    set_error("ctx_scratch: cudaMalloc of %zu bytes failed", want);
+    return nullptr;
+  }
+  ctx->scratch_bytes = want;
+  return ctx->scratch;
+}
 }  // namespace cdml
 
 extern "C" {
@@ -55,6 +71,14 @@ int cdml_ctx_create(int device, cdml_ctx** out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   c->encode_tiled = nullptr;
+  c->scratch = nullptr, c->scratch_bytes = 0;
+  {  // keep stream-ordered allocations cached across synchronisation points
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -76,6 +100,7 @@ int cdml_ctx_create(int device, cdml_ctx** out) {
 int cdml_ctx_destroy(cdml_ctx* ctx) {
   if (ctx == nullptr) return 0;
   cudaFree(ctx->dev_flags);
+  cudaFree(ctx->scratch);
   delete ctx;
   return 0;
 }

@@ -11,7 +11,14 @@ struct cdml_ctx {
   int num_sms;
   int32_t* dev_flags;  // device error word
   cdml_encode_tiled_fn encode_tiled;
+  void* scratch;         // grow-only device scratch for kernels that need a few MB of workspace (mining)
+  size_t scratch_bytes;
 };
+
+namespace cdml {
+// Returns a device buffer of at least `bytes` owned by the context (re-allocated only when it must grow).
+void* ctx_scratch(cdml_ctx* ctx, size_t bytes);
+}
 
 namespace cdml {
 // 2-D tensor map over a row-major 16-bit matrix: `inner` contiguous elements, `outer` rows of pitch ld elements.

@@ -135,9 +135,9 @@ extern "C" int cdml_mine_semihard(cdml_ctx* ctx, const void* E16, int64_t ld16, 
                "cdml_mine_semihard: bad geometry B=%lld D=%d", (long long)B, D);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // scratch: best [B] u64 | dp [B] f32 | guid32 [3B] i32
-  uint8_t* ws = nullptr;
   const size_t bytes = static_cast<size_t>(B) * (8 + 4 + 12) + 64;
-  CDML_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), bytes, st));
+  uint8_t* ws = static_cast<uint8_t*>(ctx_scratch(ctx, bytes));
+  if (ws == nullptr) return -2;
   unsigned long long* best = reinterpret_cast<unsigned long long*>(ws);
   float* dp = reinterpret_cast<float*>(best + B);
   int32_t* guid32 = reinterpret_cast<int32_t*>(dp + B);
@@ -157,6 +157,5 @@ extern "C" int cdml_mine_semihard(cdml_ctx* ctx, const void* E16, int64_t ld16, 
     mine_finalize_kernel<<<grid, 256, 0, st>>>(E32, ld32, D, best, B, neg_row, d_an);
     rc = cudaGetLastError() == cudaSuccess ? 0 : -2;
   }
-  cudaFreeAsync(ws, st);
   return rc < 0 ? rc : 0;
 }

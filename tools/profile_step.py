@@ -63,3 +63,21 @@ total = t0.elapsed_time(t1) / 3
 print("step %.3f ms (B=%d, mine=%s)" % (total, B, not args.no_mine))
 for tag, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
   print("  %-48s calls/step=%d  %.3f ms/step" % (tag, len(v) // 3, sum(v) / 3))
+
+# ---- e2e view: host wall time per step when the host reads the loss after every step
+import time
+for n in names:
+  setattr(ops, n, orig[n])
+host = torch.empty(4).pin_memory()
+torch.cuda.synchronize()
+walls, launches = [], []
+for _ in range(8):
+  t_a = time.perf_counter()
+  st = eng.train_step_indices(table16, idx, mine=not args.no_mine)
+  t_b = time.perf_counter()
+  host.copy_(st, non_blocking=True)
+  torch.cuda.current_stream().synchronize()
+  t_c = time.perf_counter()
+  walls.append((t_c - t_a) * 1e3)
+  launches.append((t_b - t_a) * 1e3)
+print("e2e per-step wall %.3f ms (host launch phase %.3f ms) over %s" % (sorted(walls)[len(walls) // 2], sorted(launches)[len(launches) // 2], ["%.2f" % w for w in walls]))
