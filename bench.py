@@ -264,27 +264,58 @@ def main():
     timings.setdefault((M, N, K, amn, bmn, epi), []).append((a, b))
     return r
 
+  mine_orig = ops.mine_semihard
+  mine_ev = []
+
+  def timed_mine(*a, **kw):
+    x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x.record()
+    r = mine_orig(*a, **kw)
+    y.record()
+    mine_ev.append((x, y))
+    return r
+
   ops.gemm16 = timed_gemm16
   engine.ops.gemm16 = timed_gemm16
+  ops.mine_semihard = timed_mine
   reps = min(5, args.steps)
   for i in range(reps):
     step(i, idx_all[i])
   torch.cuda.synchronize()
   ops.gemm16 = orig
   engine.ops.gemm16 = orig
+  ops.mine_semihard = mine_orig
   kern = []
+  if mine_ev:
+    avg = float(np.mean([a.elapsed_time(b) for a, b in mine_ev]))
+    kern.append({"gemm": "mining scan M=%d N=%d K=256 Ak Bk, selection epilogue (per launch; 2 launches/step, time incl. prepare/finalize)" % (B, B),
+                 "key": (0, 0, 99), "ms": avg / 2, "tflops": 2.0 * B * B * 256 / (avg / 2) / 1e9, "bytes": 2 * (2 * B * 256)})
   for (M, N, K, amn, bmn, epi), evs in timings.items():
     avg = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    out_bytes = M * N * (4 if epi in (0, 2) else 2) * (2 if epi == 3 else 1)      # MASK_LEAKY also reads the mask
     kern.append({"gemm": "M=%d N=%d K=%d A%s B%s epi=%d" % (M, N, K, "mn" if amn else "k", "mn" if bmn else "k", epi),
-                 "ms": avg, "tflops": 2.0 * M * N * K / avg / 1e9})
+                 "key": (int(amn), int(bmn), int(epi)), "ms": avg, "tflops": 2.0 * M * N * K / avg / 1e9,
+                 "bytes": 2 * (M * K + N * K) + out_bytes})
   kern.sort(key=lambda r: -r["ms"])
   pk = peaks()
   top = kern[0]
-  roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel " + top["gemm"], "achieved": top["tflops"],
+  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), if present
+  traffic, traffic_src = None, None
+  prof = os.path.join(ROOT, "profiles", "r01_ncu_step_gemms_final_summary.json")
+  if os.path.exists(prof) and args.batch == 65536:
+    want = {(0, 1, 1): "EpiStore16", (0, 1, 2): "EpiL2Norm", (1, 1, 0): "EpiStoreF32", (0, 0, 3): "EpiMaskLeaky"}.get(top["key"])
+    cands = [k for k in json.load(open(prof))["kernels"] if want and want in k["kernel"]]
+    if cands:
+      best = max(cands, key=lambda k: k["duration_ms"])
+      traffic = (best["dram_read_GB"] + best["dram_write_GB"]) * 1e9
+      traffic_src = "profiles/r01_ncu_step_gemms_final_summary.json: " + best["kernel"]
+  roofline = {"bound": "tensor", "kernel": "cdml gemm tcgen05 " + top["gemm"], "achieved": top["tflops"],
               "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": top["tflops"] / pk["bf16_tflops_sustained"],
-              "traffic": None, "peak_source": "%s bf16_tflops_sustained (kernel timed inside the step)" % pk["source"],
+              "traffic": traffic, "traffic_source": traffic_src,
+              "algorithmic_bytes": top["bytes"],
+              "peak_source": "%s bf16_tflops_sustained (kernel timed inside the step)" % pk["source"],
               "step_tensor_frac": (FLOP_PER_TRIPLET * value / world / 1e12) / pk["bf16_tflops_sustained"],
-              "gemms": kern}
+              "gemms": [{k: v for k, v in g.items() if k != "key"} for g in kern]}
 
   if rank != 0:
     if world > 1:
