@@ -210,14 +210,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       const int n0 = (s.m_fastest ? t / s.m_tiles : t % s.n_tiles) * BN;
       const int as = it & 1;
       const uint32_t ap = (it >> 1) & 1;
+      const int ec0 = Epi::kSplitColumns ? half * (BN / 64) : 0, ec1 = Epi::kSplitColumns ? (half + 1) * (BN / 64) : BN / 32;
+      typename Epi::State est;
+      if (Epi::kSplitColumns || half == 0) epi.pre(est, m0 + q * 32 + lane, n0, s, ec0, ec1);
       mbar_wait(tfull_bar(as), ap, 400 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      if constexpr (Epi::kSplitColumns) {
-        epi.run(taddr, m0 + q * 32 + lane, n0, split, s, half * (BN / 64), (half + 1) * (BN / 64), stg);
-      } else {
-        if (half == 0) epi.run(taddr, m0 + q * 32 + lane, n0, split, s, 0, BN / 32, stg);
-      }
+      if (Epi::kSplitColumns || half == 0) epi.run(taddr, m0 + q * 32 + lane, n0, split, s, ec0, ec1, stg, est);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(as) & kPeerBitMask);  // the leader's barrier collects both CTAs

@@ -126,6 +126,8 @@ __device__ __forceinline__ void store_chunk32(float* out, int64_t ld, int row_ba
 template <int BN>
 struct EpiStoreF32 {
   static constexpr bool kSplitColumns = true;
+  struct State {};
+  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int) const {}
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   float* out;
@@ -133,7 +135,7 @@ struct EpiStoreF32 {
   int64_t split_stride;
   const float* bias;  // nullable
   float alpha;        // 1.0f = identity
-  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int split, const GemmShape& s, int c0, int c1, uint32_t stg) const {
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int split, const GemmShape& s, int c0, int c1, uint32_t stg, State& st) const {
     float* orow = out + static_cast<int64_t>(split) * split_stride + static_cast<int64_t>(row) * ld;
     const bool row_ok = row < s.M;
 #pragma unroll 1
@@ -167,13 +169,15 @@ struct EpiStoreF32 {
 template <int BN, int kBf16>
 struct EpiStore16 {
   static constexpr bool kSplitColumns = true;
+  struct State {};
+  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int) const {}
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   uint16_t* out;
   int64_t ld;
   const float* bias;  // nullable
   float alpha;
-  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1, uint32_t stg) const {
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1, uint32_t stg, State& st) const {
 #pragma unroll 1
     for (int c = c0; c < c1; ++c) {
       const int nb = n0 + c * 32;
@@ -199,6 +203,8 @@ struct EpiStore16 {
 template <int BN, int kBf16>
 struct EpiL2Norm {
   static constexpr bool kSplitColumns = false;  // the row norm needs every column of the row in one thread
+  struct State {};
+  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int) const {}
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   float* out;  // [M, ld] fp32 embedding
@@ -208,7 +214,7 @@ struct EpiL2Norm {
   float* rinv;      // [M] nullable
   uint16_t* out16;  // [M, ld16] nullable
   int64_t ld16;
-  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1, uint32_t stg) const {
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1, uint32_t stg, State& st) const {
     const bool row_ok = row < s.M;
     float ss = 0.f;
 #pragma unroll 1
@@ -261,6 +267,9 @@ struct EpiL2Norm {
 template <int BN, int kBf16>
 struct EpiMaskLeaky {
   static constexpr bool kSplitColumns = true;
+  struct State {
+    uint4 raw[4][4];   // the four 32x32 mask chunks of this warp's half-tile, in the coalesced fetch layout
+  };
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   uint16_t* out;
@@ -308,31 +317,38 @@ struct EpiMaskLeaky {
       mk[4 * j] = t.x, mk[4 * j + 1] = t.y, mk[4 * j + 2] = t.z, mk[4 * j + 3] = t.w;
     }
   }
-  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1,
-                                      uint32_t stg) const {
+  // Requested BEFORE the accumulator is waited for: all four mask chunks of this warp's half-tile (64 registers).  The
+  // epilogue is bound by HBM latency x bytes in flight; the fetch overlaps the tile's MMAs instead of following them.
+  __device__ __forceinline__ void pre(State& st, int row, int n0, const GemmShape& s, int c0, int c1) const {
+    static_assert(BN == 256, "a warp owns 4 chunks of the tile");
     const int row_base = row - static_cast<int>(threadIdx.x & 31);
-    uint4 raw[4];
-    fetch_mask(row_base, n0 + c0 * 32, s.M, s.N, n0 + c0 * 32 < s.N, raw);
-#pragma unroll 1
-    for (int c = c0; c < c1; ++c) {
-      const int nb = n0 + c * 32;
-      if (nb >= s.N) break;
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + c * 32, v);
-      uint32_t mk[16];
-      transpose_mask(stg, raw, mk);
-      // the forward activation of the NEXT chunk is requested now, so its DRAM latency hides behind this chunk
-      fetch_mask(row_base, nb + 32, s.M, s.N, c + 1 < c1 && nb + 32 < s.N, raw);
-      tmem_ld_wait();
-      uint32_t pk[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float2 m = unpack2<kBf16>(mk[j]);
-        const float x0 = __uint_as_float(v[2 * j]) * (m.x > 0.f ? 1.f : alpha);
-        const float x1 = __uint_as_float(v[2 * j + 1]) * (m.y > 0.f ? 1.f : alpha);
-        pk[j] = pack2<kBf16>(x0, x1);
+    for (int cc = 0; cc < 4; ++cc)
+      fetch_mask(row_base, n0 + (c0 + cc) * 32, s.M, s.N, c0 + cc < c1 && n0 + (c0 + cc) * 32 < s.N, st.raw[cc]);
+  }
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1,
+                                      uint32_t stg, State& st) const {
+    const int row_base = row - static_cast<int>(threadIdx.x & 31);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = c0 + cc;
+      const int nb = n0 + c * 32;
+      if (c < c1 && nb < s.N) {   // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        uint32_t mk[16];
+        transpose_mask(stg, st.raw[cc], mk);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 m = unpack2<kBf16>(mk[j]);
+          const float x0 = __uint_as_float(v[2 * j]) * (m.x > 0.f ? 1.f : alpha);
+          const float x1 = __uint_as_float(v[2 * j + 1]) * (m.y > 0.f ? 1.f : alpha);
+          pk[j] = pack2<kBf16>(x0, x1);
+        }
+        store_chunk16(out, ld, row_base, nb, s.M, s.N, stg, pk);
       }
-      store_chunk16(out, ld, row_base, nb, s.M, s.N, stg, pk);
     }
   }
 };
@@ -342,10 +358,12 @@ struct EpiMaskLeaky {
 template <int BN, int kReadTmem>
 struct EpiNull {
   static constexpr bool kSplitColumns = true;
+  struct State {};
+  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int) const {}
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   float* out;
-  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1, uint32_t stg) const {
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1, uint32_t stg, State& st) const {
     if (kReadTmem) {
       uint32_t acc = 0u;
 #pragma unroll 1
@@ -491,14 +509,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const int n0 = (s.m_fastest ? t / s.m_tiles : t % s.n_tiles) * BN;
       const int as = it & 1;
       const uint32_t ap = (it >> 1) & 1;
+      const int ec0 = Epi::kSplitColumns ? half * (BN / 64) : 0, ec1 = Epi::kSplitColumns ? (half + 1) * (BN / 64) : BN / 32;
+      typename Epi::State est;
+      if (Epi::kSplitColumns || half == 0) epi.pre(est, m0 + q * 32 + lane, n0, s, ec0, ec1);  // loads that do not need the accumulator
       mbar_wait(tfull_bar(as), ap, 400 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      if constexpr (Epi::kSplitColumns) {
-        epi.run(taddr, m0 + q * 32 + lane, n0, split, s, half * (BN / 64), (half + 1) * (BN / 64), stg);
-      } else {
-        if (half == 0) epi.run(taddr, m0 + q * 32 + lane, n0, split, s, 0, BN / 32, stg);
-      }
+      if (Epi::kSplitColumns || half == 0) epi.run(taddr, m0 + q * 32 + lane, n0, split, s, ec0, ec1, stg, est);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -663,14 +680,13 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       for (int t = t0; t < t1; ++t, ++it) {
         const int as = it & 1;
         const uint32_t ap = (it >> 1) & 1;
+        const int ec0 = Epi::kSplitColumns ? half * (BN / 64) : 0, ec1 = Epi::kSplitColumns ? (half + 1) * (BN / 64) : BN / 32;
+        typename Epi::State est;
+        if (Epi::kSplitColumns || half == 0) epi.pre(est, t * kBM + q * 32 + lane, nblk * BN, gs, ec0, ec1);
         mbar_wait(tfull_bar(as), ap, 400 + as);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-        if constexpr (Epi::kSplitColumns) {
-          epi.run(taddr, t * kBM + q * 32 + lane, nblk * BN, 0, gs, half * (BN / 64), (half + 1) * (BN / 64), stg);
-        } else {
-          if (half == 0) epi.run(taddr, t * kBM + q * 32 + lane, nblk * BN, 0, gs, 0, BN / 32, stg);
-        }
+        if (Epi::kSplitColumns || half == 0) epi.run(taddr, t * kBM + q * 32 + lane, nblk * BN, 0, gs, ec0, ec1, stg, est);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));

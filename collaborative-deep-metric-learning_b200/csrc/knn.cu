@@ -53,13 +53,15 @@ __device__ __forceinline__ float4 ld4_or(const float* p, int col, int N, float f
 template <int BN>
 struct EpiKnnGroupMax {
   static constexpr bool kSplitColumns = true;
+  struct State {};
+  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int) const {}
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   const float* h;  // [Ns] ||x||^2/2 of the sampled rows (zeros for IP); 16-byte aligned
   float* gmax;     // [nq, ldg]
   int64_t ldg;
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
-                                      int /*c1*/, uint32_t /*stg*/) const {
+                                      int /*c1*/, uint32_t /*stg*/, State& /*st*/) const {
     float g[BN / 64];   // this warp's half of the tile: 4 groups of 32 columns
 #pragma unroll
     for (int cc = 0; cc < BN / 64; ++cc) {
@@ -107,6 +109,8 @@ struct EpiKnnCollect {
   int32_t* log_count;  // [gridDim.x]
   int32_t* log_overflow;
   unsigned int log_cap;
+  struct State {};
+  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int) const {}
   __device__ __forceinline__ void block_begin() const { knn_log_cursor() = 0u; }
   __device__ __forceinline__ void block_end() const {
     const unsigned int n = knn_log_cursor();
@@ -114,7 +118,7 @@ struct EpiKnnCollect {
     if (n > log_cap) atomicOr(log_overflow, 1);
   }
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
-                                      int c1, uint32_t /*stg*/) const {
+                                      int c1, uint32_t /*stg*/, State& /*st*/) const {
     const bool row_ok = row < s.M;
     const float hr = row_ok ? __ldg(h + row) : pos_inf();  // rows beyond M: score -inf, never pass
     uint4* my_log = log + static_cast<size_t>(blockIdx.x) * log_cap;

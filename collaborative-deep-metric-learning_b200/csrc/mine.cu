@@ -22,6 +22,19 @@ constexpr unsigned long long kNoCand = ~0ull;
 template <int BN>
 struct EpiMine {
   static constexpr bool kSplitColumns = true;
+  struct State {
+    float dpi, bound_d;
+    int ga, gp;
+  };
+  // the anchor's constants do not depend on the accumulator: fetched while the tile's MMAs are still running
+  __device__ __forceinline__ void pre(State& st, int row, int /*n0*/, const GemmShape& s, int, int) const {
+    const bool row_ok = row < s.M;
+    const float inf = __int_as_float(0x7f800000);
+    st.dpi = row_ok ? __ldg(dp + row) : inf;
+    st.ga = row_ok ? __ldg(guid + 3 * row) : 0;
+    st.gp = row_ok ? __ldg(guid + 3 * row + 1) : 0;
+    st.bound_d = row_ok ? __uint_as_float(static_cast<uint32_t>(best[row] >> 32)) : inf;   // empty key reads as NaN
+  }
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
   const float* dp;        // [B] exact |a-p|^2
@@ -32,15 +45,14 @@ struct EpiMine {
   // Hot loop per score: one compare + one predicated max.  The chunk's 32 candidate guids are parked in the warp's
   // staging buffer (one coalesced load per chunk) so the rare re-scan needs no global loads.
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
-                                      int c1, uint32_t stg) const {
+                                      int c1, uint32_t stg, State& st) const {
     const int lane = threadIdx.x & 31;
     const bool row_ok = row < s.M;
     const float inf = __int_as_float(0x7f800000);
-    const float dpi = row_ok ? __ldg(dp + row) : inf;
+    const float dpi = st.dpi;
     const float s_hi = row_ok ? 1.f - 0.5f * dpi : -inf;      // scores must stay BELOW this (rows beyond M: nothing does)
-    const int ga = row_ok ? __ldg(guid + 3 * row) : 0, gp = row_ok ? __ldg(guid + 3 * row + 1) : 0;
-    float bound_d = inf;                                       // best distance known for this anchor (any tile)
-    if (row_ok) bound_d = __uint_as_float(static_cast<uint32_t>(best[row] >> 32));
+    const int ga = st.ga, gp = st.gp;
+    float bound_d = st.bound_d;                                // best distance known for this anchor (any tile)
     if (!(bound_d == bound_d)) bound_d = inf;                  // empty key reads as NaN
     float s_lo = 1.f - 0.5f * bound_d;                         // a chunk matters only if it holds a score >= this
     float bd = inf;
