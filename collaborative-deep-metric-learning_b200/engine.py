@@ -23,6 +23,12 @@ def _pad8(n):
   return (n + 7) // 8 * 8
 
 
+def _pad64(n):
+  """Row pitch of 16-bit activation matrices: a multiple of 64 elements = 128 bytes, so that every row starts on a
+  cache line and the epilogues' 64-byte row pieces never straddle 32-byte sectors (1.3x DRAM over-fetch otherwise)."""
+  return (n + 63) // 64 * 64
+
+
 class TowerEngine:
   """Stack of `fully_connected` layers with input/output L2-normalisation (VNet: dims=[1500,5000,256])."""
 
@@ -48,7 +54,7 @@ class TowerEngine:
     self.pg = process_group
     self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
     self.F = self.dims[0]
-    self.F_pad = _pad8(self.F)
+    self.F_pad = _pad64(self.F)
 
     # ---- flat fp32 parameter / gradient / Adam buffers; per-tensor views ----
     sizes = []
@@ -125,12 +131,15 @@ class TowerEngine:
       return buf
     dev, t16 = self.device, self.t16
     D = self.dims[-1]
-    buf = {"acts": [torch.empty((R, self.dims[l + 1]), dtype=t16, device=dev) for l in range(self.L - 1)],
+    def mat16(cols):
+      return torch.empty((R, _pad64(cols)), dtype=t16, device=dev)[:, :cols]
+
+    buf = {"acts": [mat16(self.dims[l + 1]) for l in range(self.L - 1)],
            "e": torch.empty((R, D), dtype=torch.float32, device=dev),
            "rinv": torch.empty((R,), dtype=torch.float32, device=dev)}
     if train:
       B = R // 3
-      buf["dz"] = [torch.empty((R, self.dims[l + 1]), dtype=t16, device=dev) for l in range(self.L)]
+      buf["dz"] = [mat16(self.dims[l + 1]) for l in range(self.L)]
       buf["G"] = torch.empty((R, D), dtype=torch.float32, device=dev)
       buf["loss"] = {k: torch.empty((B,), dtype=torch.float32, device=dev) for k in ("pos_dist", "neg_dist", "hinge_dist")}
       buf["loss"]["stats"] = torch.empty((4,), dtype=torch.float32, device=dev)
