@@ -134,6 +134,7 @@ def workload_config(args, mine):
                       "feature table %d guids resident in HBM" % (args.batch, "on" if mine else "off", args.guids),
           "tower": DIMS, "batch_per_gpu": args.batch, "guids": args.guids, "mining": bool(mine), "margin": 0.8,
           "optimizer": "adam(tf1) lr=1e-3", "parallelism": "dp%d" % args.gpus,
+          "cuda_graph": bool(args.gpus == 1 and not getattr(args, "no_graph", False)),
           "l2_policy": "inputs_exceed_l2 (table+activations per step >> 126 MB)"}
 
 
@@ -159,6 +160,7 @@ def main():
   ap.add_argument("--no-mine", action="store_true")
   ap.add_argument("--no-knn", action="store_true")
   ap.add_argument("--no-cpu", action="store_true")
+  ap.add_argument("--no-graph", action="store_true")
   ap.add_argument("--knn-n", type=int, default=1000000)
   ap.add_argument("--knn-queries", type=int, default=65536)
   args = ap.parse_args()
@@ -208,8 +210,13 @@ def main():
       dist.barrier()
     torch.cuda.synchronize()
 
-  def step(i, idx_dev):
-    return eng.train_step_indices(table16, idx_dev, mine=mine)
+  # Single GPU: the whole step is one CUDA-graph launch (the product's fast path); N>1 launches eagerly (NCCL inside).
+  replay = eng.capture_step(table16, B, mine=mine) if (world == 1 and not args.no_graph) else None
+
+  def step(i, idx_any):
+    if replay is not None:
+      return replay(idx_any)
+    return eng.train_step_indices(table16, idx_any, mine=mine)
 
   # ---- value: device-resident indices, CUDA events, max over ranks
   for i in range(args.warmup):
@@ -241,8 +248,11 @@ def main():
   idx_dev = torch.empty((B, 3), dtype=torch.int64, device=dev)
   e0.record()
   for i in range(args.steps):
-    idx_dev.copy_(idx_host[args.warmup + i], non_blocking=True)
-    st = step(i, idx_dev)
+    if replay is not None:
+      st = step(i, idx_host[args.warmup + i])                             # pinned host -> static device buffer -> graph
+    else:
+      idx_dev.copy_(idx_host[args.warmup + i], non_blocking=True)
+      st = step(i, idx_dev)
     stats_host.copy_(st, non_blocking=True)
     torch.cuda.current_stream().synchronize()                             # the host reads the loss every step
   e1.record()
@@ -280,7 +290,7 @@ def main():
   ops.mine_semihard = timed_mine
   reps = min(5, args.steps)
   for i in range(reps):
-    step(i, idx_all[i])
+    eng.train_step_indices(table16, idx_all[i], mine=mine)                # eager: events around every launch
   torch.cuda.synchronize()
   ops.gemm16 = orig
   engine.ops.gemm16 = orig

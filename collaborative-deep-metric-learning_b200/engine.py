@@ -241,6 +241,39 @@ class TowerEngine:
       ops.adam_apply(self.b[l], self._view(self.m, 2 * l + 1), self._view(self.v, 2 * l + 1), self.gb[l], self.scalars,
                      self.beta1, self.beta2, self.eps, scale)
 
+  # ------------------------------------------------------------------ CUDA graph
+  def capture_step(self, table16, B, mine=False):
+    """Capture one full optimisation step (gather -> fwd -> [mining] -> loss -> bwd -> Adam) in a CUDA graph and return
+    `replay(idx) -> stats`: `idx` [B,3] int64 (device or pinned host) is copied into the graph's static index buffer,
+    then ONE graph launch replaces the ~30 kernel launches of the step (the host launch phase, ~0.35 ms, is what
+    bounds small batches such as config 1's B=1024).  Single-GPU only: with N>1 ranks the step contains an NCCL
+    all-reduce and is launched eagerly."""
+    if self.world > 1:
+      raise RuntimeError("capture_step is single-GPU; data-parallel steps are launched eagerly")
+    static_idx = torch.zeros((B, 3), dtype=torch.int64, device=self.device)
+    static_idx[:, 1], static_idx[:, 2] = 1 % table16.shape[0], 2 % table16.shape[0]
+    snap = (self.w.clone(), self.m.clone(), self.v.clone(), self.step_counter.clone())   # warm-up must not train
+    side = torch.cuda.Stream(device=self.device)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                      # warm-up on the capture stream: buffers, scratch, smem attributes
+      for _ in range(2):
+        self.train_step_indices(table16, static_idx, mine=mine)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+      stats = self.train_step_indices(table16, static_idx, mine=mine)
+    self.w.copy_(snap[0]), self.m.copy_(snap[1]), self.v.copy_(snap[2]), self.step_counter.copy_(snap[3])
+    self.refresh_shadows()
+    torch.cuda.synchronize()
+    self._graph_keepalive = (graph, static_idx, stats)
+
+    def replay(idx):
+      static_idx.copy_(idx, non_blocking=True)
+      graph.replay()
+      return stats
+    return replay
+
   # loss only (no update) -- used by tests and by the summaries of train.py
   def loss_rows(self, x16, B):
     buf = self.forward_rows(x16, 3 * B, train=True)

@@ -175,6 +175,30 @@ def test_training_step_gradients_loss_and_adam(cd):
     assert np.abs(b - tr.params[l][1]).max() < 2.5e-2
 
 
+def test_cuda_graph_step_equals_eager_step(cd):
+  G, F, B = 1500, 1500, 256
+  dims = [F, 5000, 256]
+  feats = O.synth_features(G, F, 0)
+  params = O.init_tower(dims, seed=2)
+  trips = [O.synth_triplets(B, G, 40 + t) for t in range(4)]
+  runs = []
+  for use_graph in (False, True):
+    eng = cd.engine.TowerEngine(dims, device=cd.dev, base_lr=1e-3, margin=0.8, init_params=params)
+    table16 = eng.prepare_table(dev_t(cd, feats))
+    replay = eng.capture_step(table16, B, mine=True) if use_graph else None
+    assert eng.global_step == 0                                  # capture warm-up must not train
+    losses = []
+    for t in trips:
+      idx = dev_t(cd, t)
+      st = replay(idx) if use_graph else eng.train_step_indices(table16, idx, mine=True)
+      losses.append(float(st[0].item()))
+    runs.append((losses, eng.get_params(), eng.global_step))
+  assert runs[0][2] == runs[1][2] == 4
+  assert np.allclose(runs[0][0], runs[1][0], rtol=1e-5)
+  for (W0, b0), (W1, b1) in zip(runs[0][1], runs[1][1]):
+    assert np.abs(W0 - W1).max() < 5e-3 and np.abs(b0 - b1).max() < 5e-3     # same kernels; atomics order in mined dE only
+
+
 def test_trainer_end_to_end_small(cd, tmp_path):
   G, F = 600, 1500
   feats = O.synth_features(G, F, 0)
