@@ -313,7 +313,8 @@ def main():
   traffic, traffic_src = None, None
   prof = os.path.join(ROOT, "profiles", "r01_ncu_step_gemms_final_summary.json")
   if os.path.exists(prof) and args.batch == 65536:
-    want = {(0, 1, 1): "EpiStore16", (0, 1, 2): "EpiL2Norm", (1, 1, 0): "EpiStoreF32", (0, 0, 3): "EpiMaskLeaky"}.get(top["key"])
+    want = {(0, 1, 1): "EpiStore16", (0, 1, 2): "EpiL2Norm", (1, 1, 0): "EpiStoreF32", (0, 0, 3): "EpiMaskLeaky",
+            (0, 0, 99): "EpiMine"}.get(top["key"])
     cands = [k for k in json.load(open(prof))["kernels"] if want and want in k["kernel"]]
     if cands:
       best = max(cands, key=lambda k: k["duration_ms"])

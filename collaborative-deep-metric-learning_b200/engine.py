@@ -261,8 +261,11 @@ class TowerEngine:
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
+    launches0 = ops.launch_count()
     with torch.cuda.graph(graph):
       stats = self.train_step_indices(table16, static_idx, mine=mine)
+    launches_per_step = ops.launch_count() - launches0
+    ops._count(-launches_per_step)                     # nothing ran during capture
     self.w.copy_(snap[0]), self.m.copy_(snap[1]), self.v.copy_(snap[2]), self.step_counter.copy_(snap[3])
     self.refresh_shadows()
     torch.cuda.synchronize()
@@ -271,7 +274,9 @@ class TowerEngine:
     def replay(idx):
       static_idx.copy_(idx, non_blocking=True)
       graph.replay()
+      ops._count(launches_per_step)                    # kernels of libcdml inside one replay
       return stats
+    replay.launches_per_step = launches_per_step
     return replay
 
   # loss only (no update) -- used by tests and by the summaries of train.py
