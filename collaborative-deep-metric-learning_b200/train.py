@@ -194,6 +194,8 @@ class Trainer():
     predictor = Prediction(sess=engine)
     fused = hasattr(self.pipe, "get_batch_indices")
     table16 = engine.prepare_table(self.pipe.device_features()) if fused else None
+    # single GPU: the whole step is one CUDA-graph launch; data-parallel steps (NCCL inside) are launched eagerly
+    replay = engine.capture_step(table16, self.batch_size, mine=self.mine_semihard) if (fused and engine.world == 1) else None
 
     world = engine.world
     global_step_np = 0
@@ -224,7 +226,7 @@ class Trainer():
 
         batch_start_time = time.time()
         if fused:
-          stats = engine.train_step_indices(table16, batch, mine=self.mine_semihard)
+          stats = replay(batch) if replay is not None else engine.train_step_indices(table16, batch, mine=self.mine_semihard)
         else:
           if batch.shape[1:] != (3, F):
             continue
