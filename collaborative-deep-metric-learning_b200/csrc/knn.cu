@@ -109,8 +109,13 @@ struct EpiKnnCollect {
   int32_t* log_count;  // [gridDim.x]
   int32_t* log_overflow;
   unsigned int log_cap;
-  struct State {};
-  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int) const {}
+  struct State {
+    float hr;
+  };
+  // the row's half norm does not depend on the accumulator: fetched while the tile's MMAs are still running
+  __device__ __forceinline__ void pre(State& st, int row, int, const GemmShape& s, int, int) const {
+    st.hr = row < s.M ? __ldg(h + row) : pos_inf();   // rows beyond M: score -inf, never pass
+  }
   __device__ __forceinline__ void block_begin() const { knn_log_cursor() = 0u; }
   __device__ __forceinline__ void block_end() const {
     const unsigned int n = knn_log_cursor();
@@ -118,9 +123,8 @@ struct EpiKnnCollect {
     if (n > log_cap) atomicOr(log_overflow, 1);
   }
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
-                                      int c1, uint32_t /*stg*/, State& /*st*/) const {
-    const bool row_ok = row < s.M;
-    const float hr = row_ok ? __ldg(h + row) : pos_inf();  // rows beyond M: score -inf, never pass
+                                      int c1, uint32_t /*stg*/, State& st) const {
+    const float hr = st.hr;
     uint4* my_log = log + static_cast<size_t>(blockIdx.x) * log_cap;
 #pragma unroll 1
     for (int c = c0; c < c1; ++c) {

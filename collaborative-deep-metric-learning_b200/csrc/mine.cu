@@ -25,15 +25,23 @@ struct EpiMine {
   struct State {
     float dpi, bound_d;
     int ga, gp;
+    int g[4];   // candidate guid of column (chunk c0+i, lane) for the warp's four chunks
   };
   // the anchor's constants do not depend on the accumulator: fetched while the tile's MMAs are still running
-  __device__ __forceinline__ void pre(State& st, int row, int /*n0*/, const GemmShape& s, int, int) const {
+  __device__ __forceinline__ void pre(State& st, int row, int n0, const GemmShape& s, int c0, int c1) const {
+    static_assert(BN == 256, "a warp owns 4 chunks of the tile");
+    const int lane = threadIdx.x & 31;
     const bool row_ok = row < s.M;
     const float inf = __int_as_float(0x7f800000);
     st.dpi = row_ok ? __ldg(dp + row) : inf;
     st.ga = row_ok ? __ldg(guid + 3 * row) : 0;
     st.gp = row_ok ? __ldg(guid + 3 * row + 1) : 0;
     st.bound_d = row_ok ? __uint_as_float(static_cast<uint32_t>(best[row] >> 32)) : inf;   // empty key reads as NaN
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = n0 + (c0 + i) * 32 + lane;
+      st.g[i] = (c0 + i < c1 && col < s.N) ? __ldg(guid + 3 * col + cand) : -1;
+    }
   }
   __device__ __forceinline__ void block_begin() const {}
   __device__ __forceinline__ void block_end() const {}
@@ -57,13 +65,14 @@ struct EpiMine {
     float s_lo = 1.f - 0.5f * bound_d;                         // a chunk matters only if it holds a score >= this
     float bd = inf;
     int br = -1;
-#pragma unroll 1
-    for (int c = c0; c < c1; ++c) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = c0 + cc;
       const int nb = n0 + c * 32;
-      if (nb >= s.N) break;
+      if (c >= c1 || nb >= s.N) break;
       uint32_t v[32];
       tmem_ld_32x32(taddr + c * 32, v);
-      const int g_lane = nb + lane < s.N ? __ldg(guid + 3 * (nb + lane) + cand) : ga;   // beyond N: never valid
+      const int g_lane = nb + lane < s.N ? st.g[cc] : ga;   // beyond N: never valid
       __syncwarp();
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + lane * 4), "r"(g_lane) : "memory");
       tmem_ld_wait();
