@@ -189,6 +189,29 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int fmt, int a_mn_major, i
 }
 
 // ----------------------------------------------------------------------------------------------
+// Packed fp32x2 arithmetic and 3-input min/max (sm_100: FADD2 / FMNMX3 / VIMNMX3).  The selection epilogues of the
+// KNN and mining scans are issue-bound (two epilogue warps per SM sub-partition against a 2048-cycle K=256 tile);
+// these halve the instructions per accumulator element.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 sub2(float a0, float a1, float b0, float b1) {   // (a0-b0, a1-b1) in one FADD2
+  float2 r;
+  asm("{\n\t.reg .b64 a, b, c;\n\t"
+      "mov.b64 a, {%2, %3};\n\t"
+      "mov.b64 b, {%4, %5};\n\t"
+      "sub.f32x2 c, a, b;\n\t"
+      "mov.b64 {%0, %1}, c;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u32(a, b, c); }
+
+// ----------------------------------------------------------------------------------------------
 // 16-bit element helpers (dtype 0 = fp16, 1 = bf16)
 // ----------------------------------------------------------------------------------------------
 template <int kBf16>

@@ -123,7 +123,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     tmem_alloc2(tmem_slot, kTmemCols);
     tmem_relinquish2();
   }
-  if (threadIdx.x == 96) epi.block_begin();
+  if (threadIdx.x == 96) epi.block_begin(base + L::kEpiOff);
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -212,7 +212,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       const uint32_t ap = (it >> 1) & 1;
       const int ec0 = Epi::kSplitColumns ? half * (BN / 64) : 0, ec1 = Epi::kSplitColumns ? (half + 1) * (BN / 64) : BN / 32;
       typename Epi::State est;
-      if (Epi::kSplitColumns || half == 0) epi.pre(est, m0 + q * 32 + lane, n0, s, ec0, ec1);
+      if (Epi::kSplitColumns || half == 0) epi.pre(est, m0 + q * 32 + lane, n0, s, ec0, ec1, stg);
       mbar_wait(tfull_bar(as), ap, 400 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -226,7 +226,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   // Nobody may leave while the peer can still touch this CTA's shared memory / barriers.
   tc_fence_before();
   cluster_sync_all();
-  if (threadIdx.x == 96) epi.block_end();
+  if (threadIdx.x == 96) epi.block_end(base + L::kEpiOff);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc2(tmem_base, kTmemCols);

@@ -127,9 +127,9 @@ template <int BN>
 struct EpiStoreF32 {
   static constexpr bool kSplitColumns = true;
   struct State {};
-  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int) const {}
-  __device__ __forceinline__ void block_begin() const {}
-  __device__ __forceinline__ void block_end() const {}
+  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
+  __device__ __forceinline__ void block_begin(uint32_t) const {}
+  __device__ __forceinline__ void block_end(uint32_t) const {}
   float* out;
   int64_t ld;
   int64_t split_stride;
@@ -170,9 +170,9 @@ template <int BN, int kBf16>
 struct EpiStore16 {
   static constexpr bool kSplitColumns = true;
   struct State {};
-  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int) const {}
-  __device__ __forceinline__ void block_begin() const {}
-  __device__ __forceinline__ void block_end() const {}
+  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
+  __device__ __forceinline__ void block_begin(uint32_t) const {}
+  __device__ __forceinline__ void block_end(uint32_t) const {}
   uint16_t* out;
   int64_t ld;
   const float* bias;  // nullable
@@ -204,9 +204,9 @@ template <int BN, int kBf16>
 struct EpiL2Norm {
   static constexpr bool kSplitColumns = false;  // the row norm needs every column of the row in one thread
   struct State {};
-  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int) const {}
-  __device__ __forceinline__ void block_begin() const {}
-  __device__ __forceinline__ void block_end() const {}
+  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
+  __device__ __forceinline__ void block_begin(uint32_t) const {}
+  __device__ __forceinline__ void block_end(uint32_t) const {}
   float* out;  // [M, ld] fp32 embedding
   int64_t ld;
   const float* bias;
@@ -270,8 +270,8 @@ struct EpiMaskLeaky {
   struct State {
     uint4 raw[4][4];   // the four 32x32 mask chunks of this warp's half-tile, in the coalesced fetch layout
   };
-  __device__ __forceinline__ void block_begin() const {}
-  __device__ __forceinline__ void block_end() const {}
+  __device__ __forceinline__ void block_begin(uint32_t) const {}
+  __device__ __forceinline__ void block_end(uint32_t) const {}
   uint16_t* out;
   int64_t ld;
   const uint16_t* mask;
@@ -319,7 +319,7 @@ struct EpiMaskLeaky {
   }
   // Requested BEFORE the accumulator is waited for: all four mask chunks of this warp's half-tile (64 registers).  The
   // epilogue is bound by HBM latency x bytes in flight; the fetch overlaps the tile's MMAs instead of following them.
-  __device__ __forceinline__ void pre(State& st, int row, int n0, const GemmShape& s, int c0, int c1) const {
+  __device__ __forceinline__ void pre(State& st, int row, int n0, const GemmShape& s, int c0, int c1, uint32_t /*stg*/) const {
     static_assert(BN == 256, "a warp owns 4 chunks of the tile");
     const int row_base = row - static_cast<int>(threadIdx.x & 31);
 #pragma unroll
@@ -359,9 +359,9 @@ template <int BN, int kReadTmem>
 struct EpiNull {
   static constexpr bool kSplitColumns = true;
   struct State {};
-  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int) const {}
-  __device__ __forceinline__ void block_begin() const {}
-  __device__ __forceinline__ void block_end() const {}
+  __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
+  __device__ __forceinline__ void block_begin(uint32_t) const {}
+  __device__ __forceinline__ void block_end(uint32_t) const {}
   float* out;
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1, uint32_t stg, State& st) const {
     if (kReadTmem) {
@@ -424,7 +424,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
-  if (threadIdx.x == 96) epi.block_begin();  // warp 3: per-CTA epilogue state (e.g. the KNN candidate log cursor)
+  if (threadIdx.x == 96) epi.block_begin(base + L::kEpiOff);  // warp 3: per-CTA epilogue state (e.g. the KNN candidate log cursor)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -511,7 +511,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const uint32_t ap = (it >> 1) & 1;
       const int ec0 = Epi::kSplitColumns ? half * (BN / 64) : 0, ec1 = Epi::kSplitColumns ? (half + 1) * (BN / 64) : BN / 32;
       typename Epi::State est;
-      if (Epi::kSplitColumns || half == 0) epi.pre(est, m0 + q * 32 + lane, n0, s, ec0, ec1);  // loads that do not need the accumulator
+      if (Epi::kSplitColumns || half == 0) epi.pre(est, m0 + q * 32 + lane, n0, s, ec0, ec1, stg);  // loads that do not need the accumulator
       mbar_wait(tfull_bar(as), ap, 400 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -524,7 +524,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 96) epi.block_end();
+  if (threadIdx.x == 96) epi.block_end(base + L::kEpiOff);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -603,20 +603,23 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
-  if (threadIdx.x == 96) epi.block_begin();
+  if (threadIdx.x == 96) epi.block_begin(base + L::kEpiOff);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int units = s.n_tiles * s.m_chunks;
-  // unit u -> column block u / m_chunks, row tiles [chunk*tpc, min(m_tiles, (chunk+1)*tpc))
+  // unit u -> column block u % n_tiles, row tiles [chunk*tpc, min(m_tiles, (chunk+1)*tpc)) with chunk = u / n_tiles.
+  // Column block fastest: the CTAs that run concurrently sweep the SAME rows of A against different resident panels, so
+  // an A tile comes from HBM once and from L2 for every other column block (the KNN index scan streams 512 MB of rows
+  // per 256 queries; with chunk-fastest order every CTA streamed a different range and the scan ran at HBM latency).
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0, bphase = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int nblk = u / s.m_chunks, chunk = u - nblk * s.m_chunks;
+      const int chunk = u / s.n_tiles, nblk = u - chunk * s.n_tiles;
       const int t0 = chunk * s.tiles_per_chunk, t1 = min(s.m_tiles, t0 + s.tiles_per_chunk);
       if (t0 >= t1) continue;
       mbar_wait(b_empty, bphase ^ 1, 500);
@@ -637,7 +640,7 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     int stage = 0, it = 0;
     uint32_t phase = 0, bphase = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int nblk = u / s.m_chunks, chunk = u - nblk * s.m_chunks;
+      const int chunk = u / s.n_tiles, nblk = u - chunk * s.n_tiles;
       const int t0 = chunk * s.tiles_per_chunk, t1 = min(s.m_tiles, t0 + s.tiles_per_chunk);
       if (t0 >= t1) continue;
       mbar_wait(b_full, bphase, 600);
@@ -675,14 +678,14 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     gs.M = s.M, gs.N = s.N, gs.K = s.K, gs.m_tiles = s.m_tiles, gs.n_tiles = s.n_tiles, gs.num_kb = s.num_kb;
     gs.kb_per_split = s.num_kb, gs.num_splits = 1, gs.m_fastest = 0, gs.idesc = s.idesc;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int nblk = u / s.m_chunks, chunk = u - nblk * s.m_chunks;
+      const int chunk = u / s.n_tiles, nblk = u - chunk * s.n_tiles;
       const int t0 = chunk * s.tiles_per_chunk, t1 = min(s.m_tiles, t0 + s.tiles_per_chunk);
       for (int t = t0; t < t1; ++t, ++it) {
         const int as = it & 1;
         const uint32_t ap = (it >> 1) & 1;
         const int ec0 = Epi::kSplitColumns ? half * (BN / 64) : 0, ec1 = Epi::kSplitColumns ? (half + 1) * (BN / 64) : BN / 32;
         typename Epi::State est;
-        if (Epi::kSplitColumns || half == 0) epi.pre(est, t * kBM + q * 32 + lane, nblk * BN, gs, ec0, ec1);
+        if (Epi::kSplitColumns || half == 0) epi.pre(est, t * kBM + q * 32 + lane, nblk * BN, gs, ec0, ec1, stg);
         mbar_wait(tfull_bar(as), ap, 400 + as);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -696,7 +699,7 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
 
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 96) epi.block_end();
+  if (threadIdx.x == 96) epi.block_end(base + L::kEpiOff);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);

@@ -28,7 +28,7 @@ struct EpiMine {
     int g[4];   // candidate guid of column (chunk c0+i, lane) for the warp's four chunks
   };
   // the anchor's constants do not depend on the accumulator: fetched while the tile's MMAs are still running
-  __device__ __forceinline__ void pre(State& st, int row, int n0, const GemmShape& s, int c0, int c1) const {
+  __device__ __forceinline__ void pre(State& st, int row, int n0, const GemmShape& s, int c0, int c1, uint32_t /*stg*/) const {
     static_assert(BN == 256, "a warp owns 4 chunks of the tile");
     const int lane = threadIdx.x & 31;
     const bool row_ok = row < s.M;
@@ -43,14 +43,14 @@ struct EpiMine {
       st.g[i] = (c0 + i < c1 && col < s.N) ? __ldg(guid + 3 * col + cand) : -1;
     }
   }
-  __device__ __forceinline__ void block_begin() const {}
-  __device__ __forceinline__ void block_end() const {}
+  __device__ __forceinline__ void block_begin(uint32_t) const {}
+  __device__ __forceinline__ void block_end(uint32_t) const {}
   const float* dp;        // [B] exact |a-p|^2
   const int32_t* guid;    // [B,3] int32 guids
   unsigned long long* best;  // [B] (float bits of d) << 32 | row
   int cand;  // 1: columns are the positives' rows 3j+1, 2: the negatives' rows 3j+2
   // Works in score space: d = 2 - 2s, so "d > dp" is "s < s_hi" and the closest candidate is the LARGEST such score.
-  // Hot loop per score: one compare + one predicated max.  The chunk's 32 candidate guids are parked in the warp's
+  // The chunk's 32 candidate guids are parked in the warp's
   // staging buffer (one coalesced load per chunk) so the rare re-scan needs no global loads.
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
                                       int c1, uint32_t stg, State& st) const {
@@ -76,14 +76,21 @@ struct EpiMine {
       __syncwarp();
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + lane * 4), "r"(g_lane) : "memory");
       tmem_ld_wait();
-      float m = -inf;
+      // Hot loop, one instruction per score: t = s_hi - score in packed fp32x2 subtracts, then a 3-input UNSIGNED
+      // minimum over the raw bits.  Positive floats order like their bit patterns and every negative float is
+      // >= 0x80000000, so the minimum is the smallest t > 0 (the closest candidate with d > dp) whenever one exists.
+      uint32_t u0 = 0xffffffffu, u1 = 0xffffffffu;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float sc = __uint_as_float(v[j]);
-        m = sc < s_hi ? fmaxf(m, sc) : m;
+      for (int j = 0; j < 8; ++j) {
+        const float2 lo = sub2(s_hi, s_hi, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]));
+        const float2 hi = sub2(s_hi, s_hi, __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        u0 = umin3(u0, __float_as_uint(lo.x), __float_as_uint(lo.y));
+        u1 = umin3(u1, __float_as_uint(hi.x), __float_as_uint(hi.y));
       }
       __syncwarp();                                            // guids visible to every lane of the warp
-      if (m >= s_lo && m > -inf) {                             // rare: this chunk may improve the anchor's best
+      // the chunk matters only if it holds a score in [s_lo, s_hi), i.e. 0 <= t <= s_hi - s_lo (monotone in fp32;
+      // t == +0 is a harmless false alarm: the re-scan below applies the exact conditions)
+      if (min(u0, u1) <= __float_as_uint(s_hi - s_lo)) {       // rare: this chunk may improve the anchor's best
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float sc = __uint_as_float(v[j]);

