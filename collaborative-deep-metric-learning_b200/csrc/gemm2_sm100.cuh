@@ -212,7 +212,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       const uint32_t ap = (it >> 1) & 1;
       const int ec0 = Epi::kSplitColumns ? half * (BN / 64) : 0, ec1 = Epi::kSplitColumns ? (half + 1) * (BN / 64) : BN / 32;
       typename Epi::State est;
-      if (Epi::kSplitColumns || half == 0) epi.pre(est, m0 + q * 32 + lane, n0, s, ec0, ec1, stg);
+      if (Epi::kSplitColumns || half == 0) {
+        epi.cols(n0, s, ec0, ec1, stg);
+        epi.pre(est, m0 + q * 32 + lane, n0, s, ec0, ec1, stg);
+      }
       mbar_wait(tfull_bar(as), ap, 400 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;

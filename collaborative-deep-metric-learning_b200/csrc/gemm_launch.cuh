@@ -158,7 +158,7 @@ inline bool resb_applicable(int64_t K) {
 
 template <class Epi>
 static int launch_gemm_resb(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
-                            int64_t K, int dtype16, const Epi& epi, cudaStream_t stream) {
+                            int64_t K, int dtype16, const Epi& epi, cudaStream_t stream, int n_fastest = 0) {
   using L = ResBSmem<kBN, kResBStages>;
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(ctx, &ta, A, dtype16, K, M, lda, kBK, kBM);
@@ -186,6 +186,7 @@ static int launch_gemm_resb(cdml_ctx* ctx, const void* A, int64_t lda, const voi
   }
   s.m_chunks = best;
   s.tiles_per_chunk = (s.m_tiles + best - 1) / best;
+  s.n_fastest = n_fastest;
   s.idesc = make_idesc_f16(dtype16 == CDML_BF16 ? 1 : 0, 0, 0, kBM, kBN);
   auto kern = gemm_resb_tcgen05_kernel<kBN, kResBStages, Epi>;
   static bool attr_set = false;

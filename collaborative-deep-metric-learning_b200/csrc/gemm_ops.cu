@@ -9,7 +9,7 @@ static int launch_any(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, 
                       int dtype16, int num_splits, const Epi& epi, cudaStream_t stream) {
   if constexpr (AMN == 0 && BMN == 0) {
     if (num_splits <= 1 && resb_applicable(K) && M >= 8 * kBM)
-      return launch_gemm_resb(ctx, A, lda, B, ldb, M, N, K, dtype16, epi, stream);
+      return launch_gemm_resb(ctx, A, lda, B, ldb, M, N, K, dtype16, epi, stream, 1);
   }
   return launch_gemm<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, num_splits, epi, stream);
 }

@@ -122,12 +122,39 @@ __device__ __forceinline__ void store_chunk32(float* out, int64_t ld, int row_ba
   }
 }
 
+// Per-warp cache of the 128 per-column 32-bit constants of the warp's four chunks (KNN bounds / half norms, mining
+// candidate guids) in its 2 KB staging slice, tagged with the column block: the resident-B kernel sweeps hundreds of
+// row tiles against one column block, and per-chunk global loads of these constants were measured to cost ~25% of
+// the KNN scan.  Slice layout: [0,128) scratch of the epilogue's rare path | [128,640) constants | [640] tag = n0+1.
+constexpr uint32_t kColCacheOff = 128, kColTagOff = 640, kWarpSliceBytes = 2048;
+__device__ __forceinline__ void col_cache_reset(uint32_t epi_smem) {   // one thread, before the CTA-wide barrier
+  for (int w = 0; w < 8; ++w)
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(epi_smem + w * kWarpSliceBytes + kColTagOff), "r"(0u) : "memory");
+}
+template <class Fetch>
+__device__ __forceinline__ void col_cache_fill(uint32_t stg, int n0, int c0, Fetch&& fetch) {   // whole warp
+  uint32_t tag;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tag) : "r"(stg + kColTagOff) : "memory");
+  if (tag == static_cast<uint32_t>(n0 + 1)) return;   // warp-uniform
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t v = fetch(n0 + (c0 + i) * 32 + lane);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + kColCacheOff + 4 * (32 * i + lane)), "r"(v) : "memory");
+  }
+  if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + kColTagOff), "r"(n0 + 1) : "memory");
+  __syncwarp();
+}
+
 // fp32 store (optionally bias + leaky).  Split-K partials land at out + split * split_stride.
 template <int BN>
 struct EpiStoreF32 {
   static constexpr bool kSplitColumns = true;
   struct State {};
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
+  static constexpr bool kPrefetchNext = false;
+  __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
   float* out;
@@ -171,6 +198,8 @@ struct EpiStore16 {
   static constexpr bool kSplitColumns = true;
   struct State {};
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
+  static constexpr bool kPrefetchNext = false;
+  __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
   uint16_t* out;
@@ -205,6 +234,8 @@ struct EpiL2Norm {
   static constexpr bool kSplitColumns = false;  // the row norm needs every column of the row in one thread
   struct State {};
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
+  static constexpr bool kPrefetchNext = false;
+  __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
   float* out;  // [M, ld] fp32 embedding
@@ -270,6 +301,8 @@ struct EpiMaskLeaky {
   struct State {
     uint4 raw[4][4];   // the four 32x32 mask chunks of this warp's half-tile, in the coalesced fetch layout
   };
+  static constexpr bool kPrefetchNext = false;
+  __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
   uint16_t* out;
@@ -360,6 +393,8 @@ struct EpiNull {
   static constexpr bool kSplitColumns = true;
   struct State {};
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
+  static constexpr bool kPrefetchNext = false;
+  __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
   float* out;
@@ -511,7 +546,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const uint32_t ap = (it >> 1) & 1;
       const int ec0 = Epi::kSplitColumns ? half * (BN / 64) : 0, ec1 = Epi::kSplitColumns ? (half + 1) * (BN / 64) : BN / 32;
       typename Epi::State est;
-      if (Epi::kSplitColumns || half == 0) epi.pre(est, m0 + q * 32 + lane, n0, s, ec0, ec1, stg);  // loads that do not need the accumulator
+      if (Epi::kSplitColumns || half == 0) {
+        epi.cols(n0, s, ec0, ec1, stg);                           // per-column constants cached in the warp's staging slice
+        epi.pre(est, m0 + q * 32 + lane, n0, s, ec0, ec1, stg);  // loads that do not need the accumulator
+      }
       mbar_wait(tfull_bar(as), ap, 400 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -544,6 +582,7 @@ struct ResBShape {
   int m_tiles, n_tiles, num_kb;
   int m_chunks;         // row-tile chunks per column block
   int tiles_per_chunk;  // ceil(m_tiles / m_chunks)
+  int n_fastest;        // unit order: 1 = column block fastest (concurrent CTAs share A rows), 0 = row chunk fastest
   uint32_t idesc;
 };
 
@@ -610,16 +649,17 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int units = s.n_tiles * s.m_chunks;
-  // unit u -> column block u % n_tiles, row tiles [chunk*tpc, min(m_tiles, (chunk+1)*tpc)) with chunk = u / n_tiles.
-  // Column block fastest: the CTAs that run concurrently sweep the SAME rows of A against different resident panels, so
-  // an A tile comes from HBM once and from L2 for every other column block (the KNN index scan streams 512 MB of rows
-  // per 256 queries; with chunk-fastest order every CTA streamed a different range and the scan ran at HBM latency).
+  // unit u -> (column block, row tiles [chunk*tpc, min(m_tiles, (chunk+1)*tpc))).  n_fastest = 1: column block fastest,
+  // the CTAs that run concurrently sweep the SAME rows of A against different resident panels (an A tile comes from HBM
+  // once and from L2 for the other column blocks -- the KNN index scan streams 512 MB of rows per 256 queries).
+  // n_fastest = 0: row chunk fastest, concurrent CTAs visit DIFFERENT rows (mining: the per-anchor running bound that
+  // prunes its epilogue has been tightened by earlier visits instead of 148 CTAs meeting the anchor cold at once).
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0, bphase = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int chunk = u / s.n_tiles, nblk = u - chunk * s.n_tiles;
+      const int chunk = s.n_fastest ? u / s.n_tiles : u % s.m_chunks, nblk = s.n_fastest ? u % s.n_tiles : u / s.m_chunks;
       const int t0 = chunk * s.tiles_per_chunk, t1 = min(s.m_tiles, t0 + s.tiles_per_chunk);
       if (t0 >= t1) continue;
       mbar_wait(b_empty, bphase ^ 1, 500);
@@ -640,7 +680,7 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     int stage = 0, it = 0;
     uint32_t phase = 0, bphase = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int chunk = u / s.n_tiles, nblk = u - chunk * s.n_tiles;
+      const int chunk = s.n_fastest ? u / s.n_tiles : u % s.m_chunks, nblk = s.n_fastest ? u % s.n_tiles : u / s.m_chunks;
       const int t0 = chunk * s.tiles_per_chunk, t1 = min(s.m_tiles, t0 + s.tiles_per_chunk);
       if (t0 >= t1) continue;
       mbar_wait(b_full, bphase, 600);
@@ -677,23 +717,60 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     GemmShape gs;
     gs.M = s.M, gs.N = s.N, gs.K = s.K, gs.m_tiles = s.m_tiles, gs.n_tiles = s.n_tiles, gs.num_kb = s.num_kb;
     gs.kb_per_split = s.num_kb, gs.num_splits = 1, gs.m_fastest = 0, gs.idesc = s.idesc;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int chunk = u / s.n_tiles, nblk = u - chunk * s.n_tiles;
-      const int t0 = chunk * s.tiles_per_chunk, t1 = min(s.m_tiles, t0 + s.tiles_per_chunk);
-      for (int t = t0; t < t1; ++t, ++it) {
-        const int as = it & 1;
-        const uint32_t ap = (it >> 1) & 1;
-        const int ec0 = Epi::kSplitColumns ? half * (BN / 64) : 0, ec1 = Epi::kSplitColumns ? (half + 1) * (BN / 64) : BN / 32;
-        typename Epi::State est;
-        if (Epi::kSplitColumns || half == 0) epi.pre(est, t * kBM + q * 32 + lane, nblk * BN, gs, ec0, ec1, stg);
-        mbar_wait(tfull_bar(as), ap, 400 + as);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-        if (Epi::kSplitColumns || half == 0) epi.run(taddr, t * kBM + q * 32 + lane, nblk * BN, 0, gs, ec0, ec1, stg, est);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+    // (unit, row tile) iterator; `nxt` runs one tile ahead so that an epilogue with kPrefetchNext can issue the next
+    // tile's accumulator-independent loads (row constants) BEFORE it processes the current tile: when the epilogue is
+    // the bottleneck the accumulator is already complete at the wait and those loads would sit on the critical path.
+    struct TileIter {
+      int u, t, t1, nblk;
+      bool valid;
+    };
+    auto seek = [&](TileIter& ti) {   // first non-empty unit at or after ti.u
+      ti.valid = false;
+      for (; ti.u < units; ti.u += gridDim.x) {
+        const int chunk = s.n_fastest ? ti.u / s.n_tiles : ti.u % s.m_chunks;
+        const int t0 = chunk * s.tiles_per_chunk, t1 = min(s.m_tiles, t0 + s.tiles_per_chunk);
+        if (t0 < t1) {
+          ti.t = t0, ti.t1 = t1, ti.nblk = s.n_fastest ? ti.u % s.n_tiles : ti.u / s.m_chunks, ti.valid = true;
+          return;
+        }
       }
+    };
+    const bool active = Epi::kSplitColumns || half == 0;
+    const int ec0 = Epi::kSplitColumns ? half * (BN / 64) : 0, ec1 = Epi::kSplitColumns ? (half + 1) * (BN / 64) : BN / 32;
+    TileIter cur;
+    cur.u = blockIdx.x;
+    seek(cur);
+    typename Epi::State est;
+    if (cur.valid && active) {
+      epi.cols(cur.nblk * BN, gs, ec0, ec1, stg);
+      epi.pre(est, cur.t * kBM + q * 32 + lane, cur.nblk * BN, gs, ec0, ec1, stg);
+    }
+    while (cur.valid) {
+      TileIter nxt = cur;
+      if (++nxt.t >= nxt.t1) {
+        nxt.u += gridDim.x;
+        seek(nxt);
+      }
+      const int as = it & 1;
+      const uint32_t ap = (it >> 1) & 1;
+      typename Epi::State est_next;
+      mbar_wait(tfull_bar(as), ap, 400 + as);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      if (active) {
+        if (Epi::kPrefetchNext && nxt.valid) epi.pre(est_next, nxt.t * kBM + q * 32 + lane, nxt.nblk * BN, gs, ec0, ec1, stg);
+        epi.run(taddr, cur.t * kBM + q * 32 + lane, cur.nblk * BN, 0, gs, ec0, ec1, stg, est);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (active && nxt.valid) {
+        epi.cols(nxt.nblk * BN, gs, ec0, ec1, stg);   // the previous tile no longer reads the column cache
+        if (!Epi::kPrefetchNext) epi.pre(est_next, nxt.t * kBM + q * 32 + lane, nxt.nblk * BN, gs, ec0, ec1, stg);
+      }
+      est = est_next;
+      cur = nxt;
+      ++it;
     }
   }
 

@@ -53,42 +53,48 @@ __device__ __forceinline__ float4 ld4_or(const float* p, int col, int N, float f
 template <int BN>
 struct EpiKnnGroupMax {
   static constexpr bool kSplitColumns = true;
+  static constexpr bool kPrefetchNext = false;
   struct State {};
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
-  __device__ __forceinline__ void block_begin(uint32_t) const {}
+  __device__ __forceinline__ void block_begin(uint32_t epi_smem) const { col_cache_reset(epi_smem); }
   __device__ __forceinline__ void block_end(uint32_t) const {}
-  const float* h;  // [Ns] ||x||^2/2 of the sampled rows (zeros for IP); 16-byte aligned
+  const float* h;  // [Ns] ||x||^2/2 of the sampled rows (zeros for IP)
   float* gmax;     // [nq, ldg]
   int64_t ldg;
+  // half norms of the warp's 128 columns (sample rows), once per column block; beyond N: +inf -> score -inf
+  __device__ __forceinline__ void cols(int n0, const GemmShape& s, int c0, int /*c1*/, uint32_t stg) const {
+    static_assert(BN == 256, "a warp owns 4 chunks (128 columns) of the tile");
+    col_cache_fill(stg, n0, c0, [&](int col) { return __float_as_uint(col < s.N ? __ldg(h + col) : pos_inf()); });
+  }
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
-                                      int /*c1*/, uint32_t /*stg*/, State& /*st*/) const {
-    float g[BN / 64];   // this warp's half of the tile: 4 groups of 32 columns
+                                      int /*c1*/, uint32_t stg, State& /*st*/) const {
+    float g[4];   // this warp's half of the tile: 4 groups of 32 columns
+    uint32_t va[32], vb[32];
+    // packed subtract + 3-input max: one instruction per accumulator element; next chunk's TMEM read in flight
+    auto group = [&](const uint32_t (&v)[32], int cc) {
+      const uint32_t hbase = stg + kColCacheOff + 128 * cc;
+      float b0 = neg_inf(), b1 = neg_inf();
 #pragma unroll
-    for (int cc = 0; cc < BN / 64; ++cc) {
-      const int c = c0 + cc;
-      const int nb = n0 + c * 32;
-      float best = neg_inf();
-      if (nb < s.N) {  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        float4 hv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) hv[j] = ld4_or(h, nb + 4 * j, s.N, pos_inf());  // beyond N: score -inf
-        tmem_ld_wait();
-        // packed subtract + 3-input max: one instruction per accumulator element
-        float b0 = neg_inf(), b1 = neg_inf();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 lo = sub2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), hv[j].x, hv[j].y);
-          const float2 hi = sub2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]), hv[j].z, hv[j].w);
-          b0 = fmax3(b0, lo.x, lo.y);
-          b1 = fmax3(b1, hi.x, hi.y);
-        }
-        best = fmaxf(b0, b1);
+      for (int j = 0; j < 8; ++j) {
+        const uint4 t = lds128(hbase + 16 * j);   // broadcast read
+        const float2 lo = sub2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(t.x), __uint_as_float(t.y));
+        const float2 hi = sub2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]), __uint_as_float(t.z), __uint_as_float(t.w));
+        b0 = fmax3(b0, lo.x, lo.y);
+        b1 = fmax3(b1, hi.x, hi.y);
       }
-      g[cc] = best;
+      return fmaxf(b0, b1);
+    };
+    auto ok = [&](int cc) { return n0 + (c0 + cc) * 32 < s.N; };   // warp-uniform
+    tmem_ld_32x32(taddr + c0 * 32, va);
+#pragma unroll
+    for (int cc = 0; cc < 4; cc += 2) {
+      tmem_ld_wait();
+      if (ok(cc + 1)) tmem_ld_32x32(taddr + (c0 + cc + 1) * 32, vb);
+      g[cc] = ok(cc) ? group(va, cc) : neg_inf();
+      tmem_ld_wait();
+      if (cc + 2 < 4 && ok(cc + 2)) tmem_ld_32x32(taddr + (c0 + cc + 2) * 32, va);
+      g[cc + 1] = ok(cc + 1) ? group(vb, cc + 1) : neg_inf();
     }
-    static_assert(BN == 256, "one float4 of group maxima per warp half");
     if (row < s.M)
       *reinterpret_cast<float4*>(gmax + static_cast<int64_t>(row) * ldg + n0 / 32 + c0) = make_float4(g[0], g[1], g[2], g[3]);
   }
@@ -101,8 +107,8 @@ struct EpiKnnGroupMax {
 // CTA-wide shared-atomic cursor with its round trip per hit +6.5 ms -- hence the cached bounds and private cursors.
 // Staging layout per warp (2 KB): [0,128) row hand-over of the hit path | [128,640) the 128 bounds of this warp's
 // columns | [640] tag = n0+1 of the cached bounds | [644] log cursor.
-constexpr uint32_t kKnnWarpStage = 2048;
-constexpr uint32_t kKnnThrOff = 128, kKnnTagOff = 640, kKnnCurOff = 644;
+constexpr uint32_t kKnnWarpStage = kWarpSliceBytes;
+constexpr uint32_t kKnnThrOff = kColCacheOff, kKnnCurOff = 644;
 constexpr int kKnnLogsPerCta = 8;   // one per epilogue warp
 
 template <int BN>
@@ -117,11 +123,11 @@ struct EpiKnnCollect {
   struct State {
     float hr;
   };
+  static constexpr bool kPrefetchNext = true;   // pre() only loads a row constant into registers
   __device__ __forceinline__ void block_begin(uint32_t epi_smem) const {
-    for (int w = 0; w < kKnnLogsPerCta; ++w) {
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(epi_smem + w * kKnnWarpStage + kKnnTagOff), "r"(0u) : "memory");
+    col_cache_reset(epi_smem);
+    for (int w = 0; w < kKnnLogsPerCta; ++w)
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(epi_smem + w * kKnnWarpStage + kKnnCurOff), "r"(0u) : "memory");
-    }
   }
   __device__ __forceinline__ void block_end(uint32_t epi_smem) const {
     for (int w = 0; w < kKnnLogsPerCta; ++w) {
@@ -131,25 +137,14 @@ struct EpiKnnCollect {
       if (n > warp_cap) atomicOr(log_overflow, 1);
     }
   }
-  // Before the accumulator is waited for: the row's half norm, and (once per column block -- the resident-B kernel
-  // sweeps many row tiles against the same 256 queries) the warp's 128 bounds into its staging slice.
-  __device__ __forceinline__ void pre(State& st, int row, int n0, const GemmShape& s, int c0, int /*c1*/, uint32_t stg) const {
-    static_assert(BN == 256, "a warp owns 4 chunks (128 columns) of the tile");
+  // the row's half norm does not depend on the accumulator (issued one tile ahead by the resident-B kernel)
+  __device__ __forceinline__ void pre(State& st, int row, int, const GemmShape& s, int, int, uint32_t) const {
     st.hr = row < s.M ? __ldg(h + row) : pos_inf();   // rows beyond M: score -inf, never pass
-    const int lane = threadIdx.x & 31;
-    uint32_t tag;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tag) : "r"(stg + kKnnTagOff) : "memory");
-    if (tag != static_cast<uint32_t>(n0 + 1)) {        // warp-uniform
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int col = n0 + (c0 + i) * 32 + lane;
-        const float t = col < s.N ? __ldg(thr + col) : pos_inf();   // beyond N: never pass
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg + kKnnThrOff + 4 * (32 * i + lane)), "f"(t) : "memory");
-      }
-      if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + kKnnTagOff), "r"(n0 + 1) : "memory");
-      __syncwarp();
-    }
+  }
+  // the bounds of the warp's 128 columns (queries), once per column block; beyond N: +inf, never pass
+  __device__ __forceinline__ void cols(int n0, const GemmShape& s, int c0, int /*c1*/, uint32_t stg) const {
+    static_assert(BN == 256, "a warp owns 4 chunks (128 columns) of the tile");
+    col_cache_fill(stg, n0, c0, [&](int col) { return __float_as_uint(col < s.N ? __ldg(thr + col) : pos_inf()); });
   }
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
                                       int c1, uint32_t stg, State& st) const {
@@ -726,7 +721,7 @@ int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, i
       }
       EpiKnnCollect<kBN> eb{ix->h, ix->thr, ix->log, ix->log_count, ix->log_count + ctx->num_sms * kKnnLogsPerCta, ix->log_cap};
       if (resb_applicable(ix->dpad) && ix->N >= 8 * kBM)
-        rc = launch_gemm_resb(ctx, ix->x16, ix->dpad, ix->q16, ix->dpad, ix->N, qc, ix->dpad, CDML_F16, eb, st);
+        rc = launch_gemm_resb(ctx, ix->x16, ix->dpad, ix->q16, ix->dpad, ix->N, qc, ix->dpad, CDML_F16, eb, st, 1);   // column block fastest: 14.4 vs 16.2 ms
       else
         rc = launch_gemm<0, 0>(ctx, ix->x16, ix->dpad, ix->q16, ix->dpad, ix->N, qc, ix->dpad, CDML_F16, 1, eb, st);
       if (rc < 0) return rc;

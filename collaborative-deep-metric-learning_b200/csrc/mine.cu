@@ -19,39 +19,35 @@ constexpr unsigned long long kNoCand = ~0ull;
 // Common path per score: d = 2-2s, keep min over (d > dp).  Only when a 32-column chunk can beat the anchor's current
 // best (a bound read from the global key at tile start; rare after the first tiles) are guids checked and the row
 // recorded.  Result: 64-bit key (float bits of d << 32 | row) folded with atomicMin -> ties go to the lowest row.
-template <int BN>
+template <int BN, int kVariant = 0>
 struct EpiMine {
   static constexpr bool kSplitColumns = true;
+  static constexpr bool kPrefetchNext = (kVariant & 1) == 0;   // pre() only loads the anchor's constants into registers
   struct State {
     float dpi, bound_d;
     int ga, gp;
-    int g[4];   // candidate guid of column (chunk c0+i, lane) for the warp's four chunks
   };
-  // the anchor's constants do not depend on the accumulator: fetched while the tile's MMAs are still running
-  __device__ __forceinline__ void pre(State& st, int row, int n0, const GemmShape& s, int c0, int c1, uint32_t /*stg*/) const {
-    static_assert(BN == 256, "a warp owns 4 chunks of the tile");
-    const int lane = threadIdx.x & 31;
+  const float* dp;        // [B] exact |a-p|^2
+  const int32_t* guid;    // [B,3] int32 guids
+  unsigned long long* best;  // [B] (float bits of d) << 32 | row
+  int cand;  // 1: columns are the positives' rows 3j+1, 2: the negatives' rows 3j+2
+  // the anchor's constants do not depend on the accumulator: the resident-B kernel issues them one tile ahead
+  __device__ __forceinline__ void pre(State& st, int row, int /*n0*/, const GemmShape& s, int, int, uint32_t) const {
     const bool row_ok = row < s.M;
     const float inf = __int_as_float(0x7f800000);
     st.dpi = row_ok ? __ldg(dp + row) : inf;
     st.ga = row_ok ? __ldg(guid + 3 * row) : 0;
     st.gp = row_ok ? __ldg(guid + 3 * row + 1) : 0;
     st.bound_d = row_ok ? __uint_as_float(static_cast<uint32_t>(best[row] >> 32)) : inf;   // empty key reads as NaN
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int col = n0 + (c0 + i) * 32 + lane;
-      st.g[i] = (c0 + i < c1 && col < s.N) ? __ldg(guid + 3 * col + cand) : -1;
-    }
   }
-  __device__ __forceinline__ void block_begin(uint32_t) const {}
+  // candidate guids of the warp's 128 columns, once per column block (-1 beyond N: the re-scan skips them)
+  __device__ __forceinline__ void cols(int n0, const GemmShape& s, int c0, int /*c1*/, uint32_t stg) const {
+    static_assert(BN == 256, "a warp owns 4 chunks (128 columns) of the tile");
+    col_cache_fill(stg, n0, c0, [&](int col) { return static_cast<uint32_t>(col < s.N ? __ldg(guid + 3 * col + cand) : -1); });
+  }
+  __device__ __forceinline__ void block_begin(uint32_t epi_smem) const { col_cache_reset(epi_smem); }
   __device__ __forceinline__ void block_end(uint32_t) const {}
-  const float* dp;        // [B] exact |a-p|^2
-  const int32_t* guid;    // [B,3] int32 guids
-  unsigned long long* best;  // [B] (float bits of d) << 32 | row
-  int cand;  // 1: columns are the positives' rows 3j+1, 2: the negatives' rows 3j+2
   // Works in score space: d = 2 - 2s, so "d > dp" is "s < s_hi" and the closest candidate is the LARGEST such score.
-  // The chunk's 32 candidate guids are parked in the warp's
-  // staging buffer (one coalesced load per chunk) so the rare re-scan needs no global loads.
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0,
                                       int c1, uint32_t stg, State& st) const {
     const int lane = threadIdx.x & 31;
@@ -65,17 +61,9 @@ struct EpiMine {
     float s_lo = 1.f - 0.5f * bound_d;                         // a chunk matters only if it holds a score >= this
     float bd = inf;
     int br = -1;
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int c = c0 + cc;
-      const int nb = n0 + c * 32;
-      if (c >= c1 || nb >= s.N) break;
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + c * 32, v);
-      const int g_lane = nb + lane < s.N ? st.g[cc] : ga;   // beyond N: never valid
-      __syncwarp();
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + lane * 4), "r"(g_lane) : "memory");
-      tmem_ld_wait();
+    uint32_t va[32], vb[32];
+    auto chunk = [&](const uint32_t (&v)[32], int cc) {
+      const int nb = n0 + (c0 + cc) * 32;
       // Hot loop, one instruction per score: t = s_hi - score in packed fp32x2 subtracts, then a 3-input UNSIGNED
       // minimum over the raw bits.  Positive floats order like their bit patterns and every negative float is
       // >= 0x80000000, so the minimum is the smallest t > 0 (the closest candidate with d > dp) whenever one exists.
@@ -87,21 +75,62 @@ struct EpiMine {
         u0 = umin3(u0, __float_as_uint(lo.x), __float_as_uint(lo.y));
         u1 = umin3(u1, __float_as_uint(hi.x), __float_as_uint(hi.y));
       }
-      __syncwarp();                                            // guids visible to every lane of the warp
       // the chunk matters only if it holds a score in [s_lo, s_hi), i.e. 0 <= t <= s_hi - s_lo (monotone in fp32;
       // t == +0 is a harmless false alarm: the re-scan below applies the exact conditions)
-      if (min(u0, u1) <= __float_as_uint(s_hi - s_lo)) {       // rare: this chunk may improve the anchor's best
+      unsigned int hits = __ballot_sync(0xffffffffu, min(u0, u1) <= __float_as_uint(s_hi - s_lo));
+      // Re-scan (rare once the anchors' bounds have tightened): the triggering row's 32 scores go through the warp's
+      // staging slice so that lane j examines column j -- compact code (the former per-thread unrolled scan made the
+      // kernel 70 KB of SASS and the epilogue instruction-cache bound), same selection: minimum d, ties -> lowest row.
+      if (hits != 0u) {
+        int g_lane;   // candidate guid of column nb + lane (column cache)
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(g_lane) : "r"(stg + kColCacheOff + 128 * cc + 4 * lane) : "memory");
+        do {
+          const int src = __ffs(hits) - 1;
+          hits &= hits - 1u;
+          __syncwarp();
+          if (lane == src) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float sc = __uint_as_float(v[j]);
-          const float d = fmaxf(fmaf(-2.f, sc, 2.f), 0.f);
-          if (sc < s_hi && sc >= s_lo && d > dpi && d < bd) {
-            int gj;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gj) : "r"(stg + j * 4) : "memory");
-            if (gj != ga && gj != gp) bd = d, br = 3 * (nb + j) + cand;
+            for (int j = 0; j < 8; ++j) sts128(stg + 16 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
+          __syncwarp();
+          float sc;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sc) : "r"(stg + 4 * lane) : "memory");
+          const float hi_s = __shfl_sync(0xffffffffu, s_hi, src), lo_s = __shfl_sync(0xffffffffu, s_lo, src);
+          const float dp_s = __shfl_sync(0xffffffffu, dpi, src), bd_s = __shfl_sync(0xffffffffu, bd, src);
+          const int ga_s = __shfl_sync(0xffffffffu, ga, src), gp_s = __shfl_sync(0xffffffffu, gp, src);
+          const float d = fmaxf(fmaf(-2.f, sc, 2.f), 0.f);
+          const bool pass = sc < hi_s && sc >= lo_s && d > dp_s && d < bd_s && g_lane != ga_s && g_lane != gp_s && g_lane >= 0;
+          const uint32_t kmin = __reduce_min_sync(0xffffffffu, pass ? __float_as_uint(d) : 0xffffffffu);   // d >= 0: bits order
+          if (kmin != 0xffffffffu) {   // warp-uniform
+            const int col = __ffs(__ballot_sync(0xffffffffu, pass && __float_as_uint(d) == kmin)) - 1;
+            if (lane == src) {
+              bd = __uint_as_float(kmin), br = 3 * (nb + col) + cand;
+              s_lo = fmaxf(s_lo, 1.f - 0.5f * bd);
+            }
+          }
+        } while (hits != 0u);
+      }
+    };
+    auto ok = [&](int cc) { return c0 + cc < c1 && n0 + (c0 + cc) * 32 < s.N; };   // warp-uniform
+    if constexpr ((kVariant & 2) == 0) {
+      tmem_ld_32x32(taddr + c0 * 32, va);
+#pragma unroll
+      for (int cc = 0; cc < 4; cc += 2) {
+        tmem_ld_wait();
+        if (ok(cc + 1)) tmem_ld_32x32(taddr + (c0 + cc + 1) * 32, vb);
+        if (ok(cc)) chunk(va, cc);
+        tmem_ld_wait();
+        if (cc + 2 < 4 && ok(cc + 2)) tmem_ld_32x32(taddr + (c0 + cc + 2) * 32, va);
+        if (ok(cc + 1)) chunk(vb, cc + 1);
+      }
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        if (ok(cc)) {
+          tmem_ld_32x32(taddr + (c0 + cc) * 32, va);
+          tmem_ld_wait();
+          chunk(va, cc);
         }
-        if (br >= 0) s_lo = fmaxf(s_lo, 1.f - 0.5f * bd);
       }
     }
     if (br >= 0)
@@ -174,8 +203,10 @@ extern "C" int cdml_mine_semihard(cdml_ctx* ctx, const void* E16, int64_t ld16, 
   int rc = 0;
   const uint16_t* e16 = static_cast<const uint16_t*>(E16);
   for (int cand = 1; cand <= 2 && rc >= 0; ++cand) {
-    EpiMine<kBN> epi{dp, guid32, best, cand};
-    // A: anchors = rows 0,3,6,.. (pitch 3*ld16); B: candidates = rows cand, cand+3, .. ; both K-major, K = D
+    // A: anchors = rows 0,3,6,.. (pitch 3*ld16); B: candidates = rows cand, cand+3, .. ; both K-major, K = D.
+    // Variant 1 (measured best of the four on B200: 3.79 ms vs 4.17-4.25): pipelined TMEM reads, anchor constants
+    // fetched after the previous tile is released (a one-tile-ahead fetch of the running bound makes it staler).
+    EpiMine<kBN, 1> epi{dp, guid32, best, cand};
     if (resb_applicable(D) && B >= 8 * kBM)
       rc = launch_gemm_resb(ctx, e16, 3 * ld16, e16 + cand * ld16, 3 * ld16, B, B, D, dtype16, epi, st);
     else
