@@ -194,7 +194,7 @@ def main():
   for s in range(0, G, 65536):                                            # normalise+cast in slabs (K2 folded, one-off)
     rows = min(65536, G - s)
     slab = torch.rand((rows, F), generator=gen, device=dev, dtype=torch.float32)
-    ops.rows_normalize_cast(slab, 0, 1, 1e-12, ld_out=eng.F_pad, out16=table16[s:s + rows])
+    eng.prepare_table(slab, out=table16[s:s + rows])
   del slab
   gen.manual_seed(100 + rank)
   nbatch = args.steps + args.warmup

@@ -32,6 +32,7 @@ _SIGNATURES = {
   "cdml_adam_prepare": (c_int, [_P, _P, c_float, c_float, c_float, c_int, c_float, c_float, _P, _P]),
   "cdml_adam_apply": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, _P, c_int, _P]),
   "cdml_cast16": (c_int, [_P, _P, c_int64, _P, c_int, _P]),
+  "cdml_fill_column16": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_float, c_int, _P]),
   "cdml_mine_semihard": (c_int, [_P, _P, c_int64, c_int, _P, c_int64, _P, c_int64, c_int, c_float, _P, _P, _P]),
   "cdml_knn_index_build": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, POINTER(c_void_p)]),
   "cdml_knn_index_destroy": (c_int, [_P]),

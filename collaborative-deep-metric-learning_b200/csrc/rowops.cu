@@ -350,6 +350,12 @@ __global__ void adam_apply_kernel(float* __restrict__ w, float* __restrict__ m, 
   }
 }
 
+__global__ void fill_column16_kernel(uint16_t* __restrict__ X, int64_t rows, int64_t ld, int64_t col, uint16_t bits) {
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < rows;
+       r += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    X[r * ld + col] = bits;
+}
+
 template <int kBf16>
 __global__ void cast16_kernel(const float* __restrict__ in, int64_t n, uint16_t* __restrict__ out) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -555,6 +561,24 @@ int cdml_cast16(cdml_ctx* ctx, const float* in, int64_t n, void* out16, int dtyp
   const int grid = flat_grid(ctx, n, 256);
   if (dtype16 == CDML_BF16) cast16_kernel<1><<<grid, 256, 0, st>>>(in, n, static_cast<uint16_t*>(out16));
   else cast16_kernel<0><<<grid, 256, 0, st>>>(in, n, static_cast<uint16_t*>(out16));
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cdml_fill_column16(cdml_ctx* ctx, void* X16, int64_t rows, int64_t ld, int64_t col, float value, int dtype16,
+                       void* stream) {
+  CDML_REQUIRE(ctx && X16 && rows >= 0 && col >= 0 && col < ld, "cdml_fill_column16: bad argument");
+  if (rows == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint16_t bits;
+  if (dtype16 == CDML_BF16) {
+    const __nv_bfloat16 b = __float2bfloat16(value);
+    bits = *reinterpret_cast<const uint16_t*>(&b);
+  } else {
+    const __half h = __float2half(value);
+    bits = *reinterpret_cast<const uint16_t*>(&h);
+  }
+  fill_column16_kernel<<<flat_grid(ctx, rows, 256), 256, 0, st>>>(static_cast<uint16_t*>(X16), rows, ld, col, bits);
   CDML_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

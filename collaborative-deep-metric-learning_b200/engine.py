@@ -55,6 +55,8 @@ class TowerEngine:
     self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
     self.F = self.dims[0]
     self.F_pad = _pad64(self.F)
+    self.fused_bias_grad = True    # bias gradients as an extra row of the weight-gradient GEMMs (no colsum kernels)
+    self._ones_checked = {}
 
     # ---- flat fp32 parameter / gradient / Adam buffers; per-tensor views ----
     sizes = []
@@ -134,7 +136,15 @@ class TowerEngine:
     def mat16(cols):
       return torch.empty((R, _pad64(cols)), dtype=t16, device=dev)[:, :cols]
 
-    buf = {"acts": [mat16(self.dims[l + 1]) for l in range(self.L - 1)],
+    def act16(cols):
+      # hidden activations feed the next layer's weight-gradient GEMM as [h | 1]: the spare pitch column `cols` holds 1.0
+      # (written once; the forward epilogue only writes columns < cols, the forward GEMM of the next layer reads K = cols)
+      m = mat16(cols)
+      if train and self._bias_row_ok(cols, m.stride(0)):
+        ops.fill_column16(m, cols, 1.0)
+      return m
+
+    buf = {"acts": [act16(self.dims[l + 1]) for l in range(self.L - 1)],
            "e": torch.empty((R, D), dtype=torch.float32, device=dev),
            "rinv": torch.empty((R,), dtype=torch.float32, device=dev)}
     if train:
@@ -143,8 +153,11 @@ class TowerEngine:
       buf["G"] = torch.empty((R, D), dtype=torch.float32, device=dev)
       buf["loss"] = {k: torch.empty((B,), dtype=torch.float32, device=dev) for k in ("pos_dist", "neg_dist", "hinge_dist")}
       buf["loss"]["stats"] = torch.empty((4,), dtype=torch.float32, device=dev)
-      buf["splits"] = [ops.auto_splits(self.w, self.dims[l], self.dims[l + 1], R) for l in range(self.L)]
-      part = max(s * self.dims[l] * self.dims[l + 1] if s > 1 else 0 for l, s in enumerate(buf["splits"]))
+      # rows of the weight-gradient GEMM: in (+1 when the bias gradient rides along as the row of the ones column)
+      in_pitch = [self.F_pad] + [a.stride(0) for a in buf["acts"]]
+      buf["wrows"] = [self.dims[l] + (1 if self._bias_row_ok(self.dims[l], in_pitch[l]) else 0) for l in range(self.L)]
+      buf["splits"] = [ops.auto_splits(self.w, buf["wrows"][l], self.dims[l + 1], R) for l in range(self.L)]
+      part = max(s * buf["wrows"][l] * self.dims[l + 1] if s > 1 else 0 for l, s in enumerate(buf["splits"]))
       buf["partials"] = torch.empty((max(part, 1),), dtype=torch.float32, device=dev)
       buf["colsum_ws"] = torch.empty((max(ops.colsum_workspace_floats(R, d) for d in self.dims[1:]),),
                                      dtype=torch.float32, device=dev)
@@ -152,6 +165,11 @@ class TowerEngine:
       self._bufs.clear()
     self._bufs[key] = buf
     return buf
+
+  def _bias_row_ok(self, width, pitch):
+    """[x | 1]^T . dz = [dW ; db]: possible when the input matrix has a spare pitch column for the ones and the bias
+    gradient directly follows the weight gradient in the flat buffer (true whenever in*out is a multiple of 8)."""
+    return self.fused_bias_grad and pitch > width
 
   # ------------------------------------------------------------------ forward
   def forward_rows(self, x16, R, train=False, want_e16=None):
@@ -176,10 +194,25 @@ class TowerEngine:
     return buf["e"]
 
   # ------------------------------------------------------------------ training
-  def prepare_table(self, features):
+  def prepare_table(self, features, out=None):
     """K2 folded into a one-off table transform: fp32 [G,F] -> L2-normalised 16-bit [G,F_pad] resident in HBM."""
-    x16, _, _ = ops.rows_normalize_cast(features, self.dtype16, 1, 1e-12, ld_out=self.F_pad)
+    x16, _, _ = ops.rows_normalize_cast(features, self.dtype16, 1, 1e-12, ld_out=self.F_pad, out16=out)
+    if self._bias_row_ok(self.F, x16.stride(0)):
+      ops.fill_column16(x16, self.F, 1.0)     # the ones column of [x | 1] (first padding column; never read by the forward GEMM)
     return x16
+
+  def _input_has_ones(self, x16):
+    """First use of an input matrix: does its padding column F hold the ones `prepare_table` plants?  (One 2-byte
+    read per distinct buffer; a table built by other means silently falls back to the column-sum kernel.)"""
+    key = (x16.data_ptr(), x16.stride(0))
+    ok = self._ones_checked.get(key)
+    if ok is None:
+      ok = bool(self._bias_row_ok(self.F, x16.stride(0)) and float(x16[0, :self.F + 1][-1].item()) == 1.0
+                and float(x16[x16.shape[0] - 1, :self.F + 1][-1].item()) == 1.0) if x16.shape[0] else False
+      if len(self._ones_checked) > 64:
+        self._ones_checked.clear()
+      self._ones_checked[key] = ok
+    return ok
 
   def train_step_indices(self, table16, idx, mine=False, guid=None):
     """One optimisation step from guid index triplets [B,3] (device int32/int64): gather -> fwd -> loss -> bwd -> Adam."""
@@ -188,10 +221,13 @@ class TowerEngine:
     if x16 is None:
       x16 = self._ws[("x16", B)] = torch.empty((3 * B, self.F_pad), dtype=self.t16, device=self.device)
     ops.gather_rows(table16, idx, out=x16)
-    return self.train_step_rows(x16, B, mine=mine, guid=idx if guid is None else guid)
+    return self.train_step_rows(x16, B, mine=mine, guid=idx if guid is None else guid,
+                                input_ones=self._input_has_ones(table16))
 
-  def train_step_rows(self, x16, B, mine=False, guid=None):
+  def train_step_rows(self, x16, B, mine=False, guid=None, input_ones=None):
     R = 3 * B
+    if input_ones is None:
+      input_ones = self._input_has_ones(x16)
     D = self.dims[-1]
     e16 = None
     if mine:
@@ -206,24 +242,29 @@ class TowerEngine:
     # loss + backward through the output L2-norm and last leaky (gradients of the SUM of hinges; 1/B goes into Adam)
     ops.triplet_hinge(buf["e"], B, self.margin, neg_row=neg_row, grad_scale=1.0, rinv=buf["rinv"],
                       leaky_alpha=self.alpha, dz16=dz[self.L - 1], workspace=buf["G"], out=buf["loss"])
-    self.backward_rows(x16, R, buf)
+    self.backward_rows(x16, R, buf, input_ones)
     self.apply_gradients(B)
     return buf["loss"]["stats"]
 
-  def backward_rows(self, x16, R, buf):
+  def backward_rows(self, x16, R, buf, input_ones=False):
     dz = buf["dz"]
     for l in range(self.L - 1, -1, -1):
       K_in, N_out = self.dims[l], self.dims[l + 1]
       inp = x16 if l == 0 else buf["acts"][l - 1]
       s = buf["splits"][l]
-      # weight gradient: dW[in,out] = inp^T[in,R] . dz[R,out]   (both operands MN-major, K = R)
+      # weight gradient: dW[in,out] = inp^T[in,R] . dz[R,out]   (both operands MN-major, K = R).  With the ones column
+      # the GEMM has in+1 rows and its last row IS the bias gradient; [dW ; db] is one contiguous block of the flat buffer.
+      rows = buf["wrows"][l] if (l > 0 or input_ones) else K_in
+      o = int(self.offsets[2 * l])
+      gWb = self.g[o:o + rows * N_out]
       if s > 1:
-        used = ops.gemm16(inp, dz[l], K_in, N_out, R, 1, 1, EPI_STORE_F32, buf["partials"], num_splits=s,
-                          split_stride=K_in * N_out)
-        ops.sum_partials(buf["partials"], used, K_in * N_out, K_in * N_out, self.gW[l])
+        used = ops.gemm16(inp, dz[l], rows, N_out, R, 1, 1, EPI_STORE_F32, buf["partials"], num_splits=s,
+                          split_stride=rows * N_out, ld_out=N_out)
+        ops.sum_partials(buf["partials"], used, rows * N_out, rows * N_out, gWb)
       else:
-        ops.gemm16(inp, dz[l], K_in, N_out, R, 1, 1, EPI_STORE_F32, self.gW[l])
-      ops.colsum16(dz[l], R, N_out, self.gb[l], buf["colsum_ws"])
+        ops.gemm16(inp, dz[l], rows, N_out, R, 1, 1, EPI_STORE_F32, gWb, ld_out=N_out)
+      if rows == K_in:
+        ops.colsum16(dz[l], R, N_out, self.gb[l], buf["colsum_ws"])
       if l > 0:
         # data gradient + leaky' of the previous layer: dz[l-1] = (dz[l] . W_l^T) * leaky'(h_{l-1})
         ops.gemm16(dz[l], self.W16[l], R, K_in, N_out, 0, 0, EPI_MASK_LEAKY, dz[l - 1], alpha=self.alpha,

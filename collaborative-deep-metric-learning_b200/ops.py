@@ -165,6 +165,15 @@ def cast16(x, out16):
   return out16
 
 
+def fill_column16(X16, col, value):
+  """X16[:, col] = value for a 16-bit matrix whose pitch exceeds its logical width (padding columns)."""
+  if X16.dim() != 2 or X16.stride(1) != 1 or not (0 <= col < X16.stride(0)):
+    raise ValueError("fill_column16: column %d outside the row pitch" % col)
+  _count(1)
+  check(_lib.load().cdml_fill_column16(_ctx(X16), ptr(X16), X16.shape[0], X16.stride(0), int(col), float(value),
+                                       dtype16_of(X16), stream_ptr()))
+
+
 def mean_pair_dist(V, pairs):
   out = torch.empty((1,), dtype=torch.float32, device=V.device)
   pairs = pairs.to(torch.int64).contiguous()

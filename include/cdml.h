@@ -101,6 +101,12 @@ int cdml_adam_apply(cdml_ctx* ctx, float* w, float* m, float* v, const float* g,
 /* fp32 -> 16-bit cast of a flat buffer (initial shadow weights). */
 int cdml_cast16(cdml_ctx* ctx, const float* in, int64_t n, void* out16, int dtype16, void* stream);
 
+/* X16[r, col] = value for every row r (16-bit matrix, pitch ld elements).  Used to plant the column of ones that turns
+ * the bias gradient db = sum_rows dz (train.py:141) into one extra output row of the weight-gradient GEMM:
+ * [x | 1]^T . dz = [dW ; db]. */
+int cdml_fill_column16(cdml_ctx* ctx, void* X16, int64_t rows, int64_t ld, int64_t col, float value, int dtype16,
+                       void* stream);
+
 /* ---- row M: in-batch semi-hard negative mining (build-defined).  E16 16-bit [3B,ld] embeddings,
  *      E32 fp32 [3B,ld32] (for |a-p|^2), guid int64 [B,3].  neg_row int32 [B] out, d_an fp32 [B] out (nullable). */
 int cdml_mine_semihard(cdml_ctx* ctx, const void* E16, int64_t ld16, int dtype16, const float* E32, int64_t ld32,

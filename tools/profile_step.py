@@ -22,7 +22,7 @@ B, G = args.batch, args.guids
 table16 = torch.empty((G, eng.F_pad), dtype=torch.float16, device=dev)
 for s in range(0, G, 65536):
   rows = min(65536, G - s)
-  ops.rows_normalize_cast(torch.rand((rows, 1500), device=dev), 0, 1, 1e-12, ld_out=eng.F_pad, out16=table16[s:s + rows])
+  eng.prepare_table(torch.rand((rows, 1500), device=dev), out=table16[s:s + rows])
 idx = torch.randint(0, G, (B, 3), device=dev)
 records = []
 names = ["gather_rows", "gemm16", "sum_partials", "colsum16", "triplet_hinge", "adam_prepare", "adam_apply", "mine_semihard"]
