@@ -134,7 +134,7 @@ def workload_config(args, mine):
                       "feature table %d guids resident in HBM" % (args.batch, "on" if mine else "off", args.guids),
           "tower": DIMS, "batch_per_gpu": args.batch, "guids": args.guids, "mining": bool(mine), "margin": 0.8,
           "optimizer": "adam(tf1) lr=1e-3", "parallelism": "dp%d" % args.gpus,
-          "cuda_graph": bool(args.gpus == 1 and not getattr(args, "no_graph", False)),
+          "cuda_graph": bool(not getattr(args, "no_graph", False)),
           "l2_policy": "inputs_exceed_l2 (table+activations per step >> 126 MB)"}
 
 
@@ -210,8 +210,8 @@ def main():
       dist.barrier()
     torch.cuda.synchronize()
 
-  # Single GPU: the whole step is one CUDA-graph launch (the product's fast path); N>1 launches eagerly (NCCL inside).
-  replay = eng.capture_step(table16, B, mine=mine) if (world == 1 and not args.no_graph) else None
+  # The whole step is one CUDA-graph launch (the product's fast path); with N>1 the NCCL all-reduce is captured inside.
+  replay = eng.capture_step(table16, B, mine=mine) if not args.no_graph else None
 
   def step(i, idx_any):
     if replay is not None:
@@ -328,12 +328,6 @@ def main():
               "step_tensor_frac": (FLOP_PER_TRIPLET * value / world / 1e12) / pk["bf16_tflops_sustained"],
               "gemms": [{k: v for k, v in g.items() if k != "key"} for g in kern]}
 
-  if rank != 0:
-    if world > 1:
-      dist.barrier()
-      dist.destroy_process_group()
-    return
-
   line = {"metric": "train_triplets_per_sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": args.steps,
           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
           "vs_baseline": None, "dtype": "fp16 operands / fp32 accumulate (tcgen05 kind::f16), fp32 master weights",
@@ -342,39 +336,60 @@ def main():
           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "loss_last_step": loss_last,
           "tflops_per_gpu": FLOP_PER_TRIPLET * value / world / 1e12}
 
-  # ---- second BASELINE metric: exact KNN top-100 queries/sec on a 1M-item index (1 GPU; sharded run: tools/bench_knn.py)
+  # ---- second BASELINE metric: exact KNN top-100 queries/sec on a 1M-item index.  N>1: the index is row-sharded over
+  # the ranks (strong scaling: same 1M rows, same queries), per-shard top-k all-gathered over NCCL and merged on the GPU.
   if not args.no_knn:
-    del table16, idx_all, eng
+    from cdml_b200 import faiss_knn
+    del table16, idx_all, eng, replay
     torch.cuda.empty_cache()
     N, nq, k, d = args.knn_n, args.knn_queries, 100, 256
     gen.manual_seed(4)
-    X = torch.nn.functional.normalize(torch.randn((N, d), generator=gen, device=dev), dim=1)
-    index = ops.FlatIndex(X, "L2")
-    index.search(X[:nq], k)                                               # warm-up at full size (workspace, L2)
-    torch.cuda.synchronize()
+    X = torch.nn.functional.normalize(torch.randn((N, d), generator=gen, device=dev), dim=1)   # same on every rank
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    Q = X[:nq].clone()
+    index = ops.FlatIndex(X[lo:hi].contiguous(), "L2")
+    if world > 1:
+      del X
+    faiss_knn.sharded_search(index, Q, k, lo, "L2", pg)                   # warm-up at full size (workspace, L2, NCCL)
+    barrier()
     e0.record()
-    D, I = index.search(X[:nq], k)
+    D, I = faiss_knn.sharded_search(index, Q, k, lo, "L2", pg)
     e1.record()
-    torch.cuda.synchronize()
-    kms = e0.elapsed_time(e1)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kms = float(t.item())
     self_first = float((I[:, 0] == torch.arange(nq, device=dev)).float().mean().item())
-    Xh = X[:nq].cpu().pin_memory()
+    Xh = Q.cpu().pin_memory()
     Dh, Ih = torch.empty((nq, k)).pin_memory(), torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    barrier()
     t0 = time.time()
-    D2, I2 = index.search(Xh.to(dev, non_blocking=True), k)
+    D2, I2 = faiss_knn.sharded_search(index, Xh.to(dev, non_blocking=True), k, lo, "L2", pg)
     Dh.copy_(D2, non_blocking=True), Ih.copy_(I2, non_blocking=True)
-    torch.cuda.synchronize()
-    ke2e = nq / (time.time() - t0)
+    barrier()
+    t = torch.tensor([time.time() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ke2e = nq / float(t.item())
     st = index.last_stats()
     line["knn"] = {"metric": "knn_top100_queries_per_sec", "value": nq / (kms / 1e3), "unit": "queries/s",
-                   "config": {"workload": "configs[3]: exact flat L2 top-100, N=%d d=%d, %d queries (rows of the index)" % (N, d, nq)},
+                   "scaling": "strong",
+                   "config": {"workload": "configs[3]: exact flat L2 top-100, N=%d d=%d row-sharded over %d GPU(s), %d queries "
+                                          "(rows of the index)" % (N, d, world, nq)},
                    "ms": kms, "tflops": 2.0 * nq * N * d / kms / 1e9, "e2e": {"value": ke2e, "unit": "queries/s",
                    "h2d_bytes": nq * d * 4, "d2h_bytes": nq * k * 12},
-                   "candidates_per_query": st["candidates"] / nq, "fallback_queries": st["fallback_queries"],
+                   "candidates_per_query_rank0": st["candidates"] / nq, "fallback_queries_rank0": st["fallback_queries"],
                    "self_is_first_neighbour": self_first,
-                   "roofline": {"bound": "tensor", "achieved": 2.0 * nq * N * d / kms / 1e9, "peak": pk["bf16_tflops_sustained"],
-                                "unit": "TFLOP/s", "frac": 2.0 * nq * N * d / kms / 1e9 / pk["bf16_tflops_sustained"]}}
+                   "roofline": {"bound": "tensor", "achieved": 2.0 * nq * N * d / kms / 1e9 / world,
+                                "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s (per GPU)",
+                                "frac": 2.0 * nq * N * d / kms / 1e9 / world / pk["bf16_tflops_sustained"]}}
     index.close()
+  if rank != 0:
+    if world > 1:
+      dist.barrier()
+      dist.destroy_process_group()
+    return
   if not args.no_cpu and world == 1:
     line["cpu_baseline"] = cpu_train_baseline()
     if not args.no_knn:

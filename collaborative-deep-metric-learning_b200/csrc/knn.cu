@@ -61,6 +61,7 @@ struct EpiKnnGroupMax {
   const float* h;  // [Ns] ||x||^2/2 of the sampled rows (zeros for IP)
   float* gmax;     // [nq, ldg]
   int64_t ldg;
+  int wide;        // 0: one maximum per 32 sampled rows; 1: per 128 (4x less k-th selection work; needs Ns/128 >= 2k)
   // half norms of the warp's 128 columns (sample rows), once per column block; beyond N: +inf -> score -inf
   __device__ __forceinline__ void cols(int n0, const GemmShape& s, int c0, int /*c1*/, uint32_t stg) const {
     static_assert(BN == 256, "a warp owns 4 chunks (128 columns) of the tile");
@@ -95,8 +96,10 @@ struct EpiKnnGroupMax {
       if (cc + 2 < 4 && ok(cc + 2)) tmem_ld_32x32(taddr + (c0 + cc + 2) * 32, va);
       g[cc + 1] = ok(cc + 1) ? group(vb, cc + 1) : neg_inf();
     }
-    if (row < s.M)
-      *reinterpret_cast<float4*>(gmax + static_cast<int64_t>(row) * ldg + n0 / 32 + c0) = make_float4(g[0], g[1], g[2], g[3]);
+    if (row < s.M) {
+      if (wide) gmax[static_cast<int64_t>(row) * ldg + n0 / 128 + c0 / 4] = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+      else *reinterpret_cast<float4*>(gmax + static_cast<int64_t>(row) * ldg + n0 / 32 + c0) = make_float4(g[0], g[1], g[2], g[3]);
+    }
   }
 };
 
@@ -283,14 +286,17 @@ __device__ __forceinline__ int block_sum(int v, int* sh) {
   return t;
 }
 
-// k-th best sampled group score per query -> collection bound  thr = kth - slack(q)
+// k-th best sampled group score per query -> collection bound  thr = kth - slack(q).
+// Bitwise bisection over the order-preserving key, stopped after the top kSelectBits bits: the result is the true
+// k-th key rounded DOWN (a bound may always be lower), at 2^-12 relative precision -- far inside the slack.
+constexpr int kSelectBits = 20;
+template <int kPer>
 __global__ void __launch_bounds__(kRefineThreads)
 knn_kth_kernel(const float* __restrict__ gmax, int64_t ldg, int G, int k, const float* __restrict__ qss,
                float slack_scale, float slack_abs, float* __restrict__ thr) {
   __shared__ int sh[kRefineThreads / 32];
   const int q = blockIdx.x;
   const float* g = gmax + static_cast<int64_t>(q) * ldg;
-  constexpr int kPer = kMaxGroups / kRefineThreads;
   uint32_t keys[kPer];
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
@@ -298,7 +304,7 @@ knn_kth_kernel(const float* __restrict__ gmax, int64_t ldg, int G, int k, const 
     keys[i] = j < G ? f2key(g[j]) : 0u;
   }
   uint32_t T = 0;
-  for (int bit = 31; bit >= 0; --bit) {
+  for (int bit = 31; bit >= 32 - kSelectBits; --bit) {
     const uint32_t cand = T | (1u << bit);
     int c = 0;
 #pragma unroll
@@ -320,10 +326,9 @@ knn_refine_kernel(const float* __restrict__ Q, int64_t ldq, int d, const float* 
                   const int32_t* __restrict__ cnt, int cap, int k, int metric, float slack_scale, float slack_abs,
                   int64_t id_offset, float* __restrict__ D, int64_t* __restrict__ I, int64_t out_ld,
                   int32_t* __restrict__ overflow, int n_all) {
-  __shared__ uint32_t skey[kCandCap];
-  __shared__ int32_t sidx[kCandCap];
   __shared__ unsigned long long kept[kKeepCap];
   __shared__ int sh[kRefineThreads / 32];
+  __shared__ uint32_t shu[2 * (kRefineThreads / 32)];
   __shared__ int n_keep;
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
@@ -332,28 +337,51 @@ knn_refine_kernel(const float* __restrict__ Q, int64_t ldq, int d, const float* 
     if (tid == 0) overflow[q] = 1;
     return;
   }
-  for (int i = tid; i < n; i += kRefineThreads) {
-    skey[i] = f2key(cand_val[static_cast<int64_t>(q) * cap + i]);
-    sidx[i] = cand_idx[static_cast<int64_t>(q) * cap + i];
+  // the nominees stay in registers: kCandCap / kRefineThreads per thread
+  constexpr int kPer = kCandCap / kRefineThreads;
+  uint32_t keys[kPer];
+  int32_t idxs[kPer];
+  uint32_t kmax = 0u, kmin = 0xffffffffu;
+#pragma unroll
+  for (int t = 0; t < kPer; ++t) {
+    const int i = tid + t * kRefineThreads;
+    keys[t] = 0u, idxs[t] = 0;
+    if (i < n) {
+      keys[t] = f2key(cand_val[static_cast<int64_t>(q) * cap + i]);
+      idxs[t] = cand_idx[static_cast<int64_t>(q) * cap + i];
+      kmax = max(kmax, keys[t]), kmin = min(kmin, keys[t]);
+    }
   }
   if (tid == 0) n_keep = 0;
-  __syncthreads();
-  // k-th best approximate score among the nominees
+  // k-th best approximate score among the nominees: bitwise bisection, skipping the bits every key shares (nominees
+  // all lie between the collection bound and the best score: the top ~10 bits of the 20 examined are common)
   uint32_t T = 0;
   if (n > k) {
-    for (int bit = 31; bit >= 0; --bit) {
+    kmax = __reduce_max_sync(0xffffffffu, kmax), kmin = __reduce_min_sync(0xffffffffu, kmin);
+    if ((tid & 31) == 0) shu[tid >> 5] = kmax, shu[kRefineThreads / 32 + (tid >> 5)] = kmin;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kRefineThreads / 32; ++w) kmax = max(kmax, shu[w]), kmin = min(kmin, shu[kRefineThreads / 32 + w]);
+    const uint32_t diff = kmax ^ kmin;
+    const int top = diff == 0u ? -1 : 31 - __clz(diff);          // highest bit in which two keys differ
+    T = top >= 31 ? 0u : (kmax >> (top + 1)) << (top + 1);      // the shared prefix
+    for (int bit = top; bit >= 32 - kSelectBits; --bit) {       // k-th key rounded down: a prune bound may always be lower
       const uint32_t cand = T | (1u << bit);
       int c = 0;
-      for (int i = tid; i < n; i += kRefineThreads) c += skey[i] >= cand ? 1 : 0;
+#pragma unroll
+      for (int t = 0; t < kPer; ++t) c += keys[t] >= cand ? 1 : 0;   // empty slots hold key 0 < cand
       if (block_sum(c, sh) >= k) T = cand;
     }
+  } else {
+    __syncthreads();
   }
   const float slack = slack_scale * sqrtf(qss[q]) + slack_abs;
   const uint32_t keep_key = n > k ? f2key(key2f(T) - slack) : 0u;
-  for (int i = tid; i < n; i += kRefineThreads) {
-    if (skey[i] >= keep_key) {
+#pragma unroll
+  for (int t = 0; t < kPer; ++t) {
+    if (tid + t * kRefineThreads < n && keys[t] >= keep_key) {
       const int pos = atomicAdd(&n_keep, 1);
-      if (pos < kKeepCap) kept[pos] = static_cast<unsigned long long>(static_cast<uint32_t>(sidx[i]));
+      if (pos < kKeepCap) kept[pos] = static_cast<unsigned long long>(static_cast<uint32_t>(idxs[t]));
     }
   }
   if (n_all > 0) {
@@ -366,53 +394,86 @@ knn_refine_kernel(const float* __restrict__ Q, int64_t ldq, int d, const float* 
     if (tid == 0) overflow[q] = 1;
     return;
   }
-  // exact fp32 scores of the survivors: one warp per candidate
+  // exact fp32 scores of the survivors: each warp takes four candidates at a time so that their row fetches (1 KB each
+  // at d=256, scattered over the index) are all in flight together -- the re-rank is bound by HBM latency, not bytes
   const int warp = tid >> 5, lane = tid & 31;
   const float* qv = Q + static_cast<int64_t>(q) * ldq;
   const float qn = qss[q];
-  for (int i = warp; i < nk; i += kRefineThreads / 32) {
-    const uint32_t id = static_cast<uint32_t>(kept[i]);
-    const float* xv = X + static_cast<int64_t>(id) * ldx;
-    float dot = 0.f;
-    for (int j = lane; j < d; j += 32) dot = fmaf(qv[j], xv[j], dot);
+  const bool vec = (d & 3) == 0 && (ldx & 3) == 0 && (ldq & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Q)) & 15) == 0;
+  for (int i0 = warp * 4; i0 < nk; i0 += (kRefineThreads / 32) * 4) {
+    uint32_t id[4];
+    float dot[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    if (lane == 0) {
-      const float key = metric == 0 ? fmaxf(qn + xss[id] - 2.f * dot, 0.f) : -dot;
-      kept[i] = (static_cast<unsigned long long>(f2key(key)) << 32) | id;
-    }
-  }
-  int P = 1;
-  while (P < nk) P <<= 1;
-  if (P < 2) P = 2;
-  for (int i = nk + tid; i < P; i += kRefineThreads) kept[i] = ~0ull;
-  __syncthreads();
-  // bitonic sort ascending on (distance key, id)
-  for (int size = 2; size <= P; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = tid; t < (P >> 1); t += kRefineThreads) {
-        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
-        const int hi = lo + stride;
-        const bool up = (lo & size) == 0;
-        const unsigned long long a = kept[lo], b = kept[hi];
-        if ((a > b) == up) kept[lo] = b, kept[hi] = a;
+    for (int c = 0; c < 4; ++c) id[c] = static_cast<uint32_t>(kept[min(i0 + c, nk - 1)]);
+    if (vec) {
+      for (int j = lane * 4; j < d; j += 128) {
+        const float4 qq = __ldg(reinterpret_cast<const float4*>(qv + j));
+        float4 xx[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xx[c] = __ldg(reinterpret_cast<const float4*>(X + static_cast<int64_t>(id[c]) * ldx + j));
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dot[c] = fmaf(qq.x, xx[c].x, fmaf(qq.y, xx[c].y, fmaf(qq.z, xx[c].z, fmaf(qq.w, xx[c].w, dot[c]))));
       }
-      __syncthreads();
+    } else {
+      for (int j = lane; j < d; j += 32) {
+        const float qj = qv[j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dot[c] = fmaf(qj, X[static_cast<int64_t>(id[c]) * ldx + j], dot[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot[c] += __shfl_xor_sync(0xffffffffu, dot[c], o);
+    }
+    __syncwarp();
+    if (lane < 4 && i0 + lane < nk) {
+      const float dsel = lane == 0 ? dot[0] : lane == 1 ? dot[1] : lane == 2 ? dot[2] : dot[3];
+      const uint32_t isel = lane == 0 ? id[0] : lane == 1 ? id[1] : lane == 2 ? id[2] : id[3];
+      const float key = metric == 0 ? fmaxf(qn + xss[isel] - 2.f * dsel, 0.f) : -dsel;
+      kept[i0 + lane] = (static_cast<unsigned long long>(f2key(key)) << 32) | isel;
     }
   }
-  for (int i = tid; i < k; i += kRefineThreads) {
-    float dist;
-    int64_t id;
-    if (i < nk) {
-      const float key = key2f(static_cast<uint32_t>(kept[i] >> 32));
-      dist = metric == 0 ? key : -key;
-      id = static_cast<int64_t>(static_cast<uint32_t>(kept[i])) + id_offset;
-    } else {  // fewer than k database rows: faiss pads with inf / -1
-      dist = metric == 0 ? pos_inf() : neg_inf();
-      id = -1;
+  __syncthreads();
+  const auto emit = [&](int i, unsigned long long e) {
+    const float key = key2f(static_cast<uint32_t>(e >> 32));
+    D[static_cast<int64_t>(q) * out_ld + i] = metric == 0 ? key : -key;
+    I[static_cast<int64_t>(q) * out_ld + i] = static_cast<int64_t>(static_cast<uint32_t>(e)) + id_offset;
+  };
+  if (nk <= 2 * kRefineThreads) {
+    // few survivors (the usual ~1.2 k): rank sort -- every element counts the (distance,id) keys below it (they are
+    // distinct) and goes straight to its output slot; broadcast shared-memory reads, no barriers
+    for (int i = tid; i < nk; i += kRefineThreads) {
+      const unsigned long long e = kept[i];
+      int rank = 0;
+      for (int j = 0; j < nk; ++j) rank += kept[j] < e ? 1 : 0;
+      if (rank < k) emit(rank, e);
     }
-    D[static_cast<int64_t>(q) * out_ld + i] = dist;
-    I[static_cast<int64_t>(q) * out_ld + i] = id;
+  } else {
+    int P = 2;
+    while (P < nk) P <<= 1;
+    for (int i = nk + tid; i < P; i += kRefineThreads) kept[i] = ~0ull;
+    __syncthreads();
+    // bitonic sort ascending on (distance key, id)
+    for (int size = 2; size <= P; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = tid; t < (P >> 1); t += kRefineThreads) {
+          const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+          const int hi = lo + stride;
+          const bool up = (lo & size) == 0;
+          const unsigned long long a = kept[lo], b = kept[hi];
+          if ((a > b) == up) kept[lo] = b, kept[hi] = a;
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = tid; i < k && i < nk; i += kRefineThreads) emit(i, kept[i]);
+  }
+  for (int i = nk + tid; i < k; i += kRefineThreads) {   // fewer than k database rows: faiss pads with inf / -1
+    D[static_cast<int64_t>(q) * out_ld + i] = metric == 0 ? pos_inf() : neg_inf();
+    I[static_cast<int64_t>(q) * out_ld + i] = -1;
   }
 }
 
@@ -572,6 +633,10 @@ struct cdml_index {
   int32_t* log_count;  // [num_sms * 8] + 1 overflow word
   unsigned int log_cap;
   unsigned long long* fb_keys;
+  // pinned host mirrors of the per-query counters (one stream synchronisation per search, not per chunk)
+  int32_t *h_cnt, *h_ovf, *h_logovf;
+  float* h_qss;
+  int64_t h_cap;
   int64_t ldg;
   int64_t stats[2];
 };
@@ -582,6 +647,7 @@ static void index_free(cdml_index* ix) {
   cudaFree(ix->q16), cudaFree(ix->qss), cudaFree(ix->gmax), cudaFree(ix->thr), cudaFree(ix->cand_val);
   cudaFree(ix->cand_idx), cudaFree(ix->cnt), cudaFree(ix->overflow), cudaFree(ix->fb_keys);
   cudaFree(ix->log), cudaFree(ix->log_count);
+  cudaFreeHost(ix->h_cnt), cudaFreeHost(ix->h_ovf), cudaFreeHost(ix->h_qss), cudaFreeHost(ix->h_logovf);
   delete ix;
 }
 
@@ -694,7 +760,15 @@ int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, i
   const float rel = 1.5f * 0.0009765625f + 1.2e-7f * d;            // operand rounding + fp32 accumulation
   const float slack_scale = 2.f * rel * ix->xmaxnorm;               // times |q|
   const float slack_abs = 2.f * 1e-6f * (1.f + ix->xmaxnorm);       // fp16 subnormal floor
-  std::vector<int32_t> host_cnt, host_ovf;
+  if (ix->h_cap < nq) {
+    cudaFreeHost(ix->h_cnt), cudaFreeHost(ix->h_ovf), cudaFreeHost(ix->h_qss), cudaFreeHost(ix->h_logovf);
+    ix->h_cnt = ix->h_ovf = ix->h_logovf = nullptr, ix->h_qss = nullptr, ix->h_cap = 0;
+    CDML_CHECK_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ix->h_cnt), sizeof(int32_t) * nq));
+    CDML_CHECK_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ix->h_ovf), sizeof(int32_t) * nq));
+    CDML_CHECK_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ix->h_qss), sizeof(float) * nq));
+    CDML_CHECK_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ix->h_logovf), sizeof(int32_t) * (nq / chunk + 2)));
+    ix->h_cap = nq;
+  }
   for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
     const int64_t qc = std::min<int64_t>(chunk, nq - q0);
     const float* Qc = Q + q0 * ldq;
@@ -708,14 +782,20 @@ int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, i
     const bool tiny = ix->N <= kKeepCap;   // tiny database: exact re-rank of every row, no tensor-core scan
     if (!tiny) {
       if (ix->Ns > 0 && ix->Ns / 32 >= k) {
-        EpiKnnGroupMax<kBN> ea{ix->hs, ix->gmax, ix->ldg};
+        const int wide = (ix->Ns / 128 >= 2 * static_cast<int64_t>(k)) ? 1 : 0;
+        const int groups = wide ? static_cast<int>((ix->Ns + 255) / 256 * 2) : static_cast<int>(ix->Ns / 32);
+        EpiKnnGroupMax<kBN> ea{ix->hs, ix->gmax, ix->ldg, wide};
         if (resb_applicable(ix->dpad) && qc >= 8 * kBM)
           rc = launch_gemm_resb(ctx, ix->q16, ix->dpad, ix->xs16, ix->dpad, qc, ix->Ns, ix->dpad, CDML_F16, ea, st);
         else
           rc = launch_gemm<0, 0>(ctx, ix->q16, ix->dpad, ix->xs16, ix->dpad, qc, ix->Ns, ix->dpad, CDML_F16, 1, ea, st);
         if (rc < 0) return rc;
-        knn_kth_kernel<<<static_cast<int>(qc), kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, static_cast<int>(ix->Ns / 32), k,
-                                                                      ix->qss, slack_scale, slack_abs, ix->thr);
+        if (groups <= 4 * kRefineThreads)
+          knn_kth_kernel<4><<<static_cast<int>(qc), kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, k, ix->qss, slack_scale,
+                                                                          slack_abs, ix->thr);
+        else
+          knn_kth_kernel<kMaxGroups / kRefineThreads><<<static_cast<int>(qc), kRefineThreads, 0, st>>>(
+              ix->gmax, ix->ldg, groups, k, ix->qss, slack_scale, slack_abs, ix->thr);
       } else {
         fill_f32_kernel<<<64, 256, 0, st>>>(ix->thr, qc, -INFINITY);
       }
@@ -737,26 +817,24 @@ int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, i
       ix->stats[0] += ix->N * qc;
     }
     CDML_CHECK_CUDA(cudaGetLastError());
-    host_cnt.resize(qc), host_ovf.resize(qc);
-    CDML_CHECK_CUDA(cudaMemcpyAsync(host_cnt.data(), ix->cnt, sizeof(int32_t) * qc, cudaMemcpyDeviceToHost, st));
-    CDML_CHECK_CUDA(cudaMemcpyAsync(host_ovf.data(), ix->overflow, sizeof(int32_t) * qc, cudaMemcpyDeviceToHost, st));
-    int32_t log_ovf = 0;
-    CDML_CHECK_CUDA(cudaMemcpyAsync(&log_ovf, ix->log_count + ctx->num_sms * kKnnLogsPerCta, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CDML_CHECK_CUDA(cudaStreamSynchronize(st));
-    for (int64_t i = 0; i < qc; ++i) {
-      ix->stats[0] += host_cnt[i];
-      if (!host_ovf[i] && !log_ovf) continue;   // a full CTA log may have dropped nominees of any query
-      ix->stats[1] += 1;
-      if (ix->fb_keys == nullptr && dev_alloc(&ix->fb_keys, ix->N)) return -2;
-      float qn = 0.f;
-      CDML_CHECK_CUDA(cudaMemcpyAsync(&qn, ix->qss + i, sizeof(float), cudaMemcpyDeviceToHost, st));
-      CDML_CHECK_CUDA(cudaStreamSynchronize(st));
-      const int g2 = static_cast<int>(std::min<int64_t>((ix->N + 7) / 8, ctx->num_sms * 8));
-      knn_exact_keys_kernel<<<g2, 256, 0, st>>>(Qc + i * ldq, d, qn, ix->x32, ix->N, d, ix->xss, ix->metric, ix->fb_keys);
-      knn_exact_select_kernel<<<1, 1024, 0, st>>>(ix->fb_keys, ix->N, k, ix->metric, id_offset, D + (q0 + i) * k,
-                                                  I + (q0 + i) * k);
-      CDML_CHECK_CUDA(cudaGetLastError());
-    }
+    // counters of this chunk -> pinned host memory, stream-ordered before the next chunk reuses the workspace
+    CDML_CHECK_CUDA(cudaMemcpyAsync(ix->h_cnt + q0, ix->cnt, sizeof(int32_t) * qc, cudaMemcpyDeviceToHost, st));
+    CDML_CHECK_CUDA(cudaMemcpyAsync(ix->h_ovf + q0, ix->overflow, sizeof(int32_t) * qc, cudaMemcpyDeviceToHost, st));
+    CDML_CHECK_CUDA(cudaMemcpyAsync(ix->h_qss + q0, ix->qss, sizeof(float) * qc, cudaMemcpyDeviceToHost, st));
+    CDML_CHECK_CUDA(cudaMemcpyAsync(ix->h_logovf + q0 / chunk, ix->log_count + ctx->num_sms * kKnnLogsPerCta, sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, st));
+  }
+  CDML_CHECK_CUDA(cudaStreamSynchronize(st));
+  // rare: queries whose candidate list (or whose chunk's warp log) overflowed are redone exactly in fp32
+  for (int64_t i = 0; i < nq; ++i) {
+    ix->stats[0] += ix->N <= kKeepCap ? 0 : ix->h_cnt[i];
+    if (!ix->h_ovf[i] && !ix->h_logovf[i / chunk]) continue;   // a full warp log may have dropped nominees of any query
+    ix->stats[1] += 1;
+    if (ix->fb_keys == nullptr && dev_alloc(&ix->fb_keys, ix->N)) return -2;
+    const int g2 = static_cast<int>(std::min<int64_t>((ix->N + 7) / 8, ctx->num_sms * 8));
+    knn_exact_keys_kernel<<<g2, 256, 0, st>>>(Q + i * ldq, d, ix->h_qss[i], ix->x32, ix->N, d, ix->xss, ix->metric, ix->fb_keys);
+    knn_exact_select_kernel<<<1, 1024, 0, st>>>(ix->fb_keys, ix->N, k, ix->metric, id_offset, D + i * k, I + i * k);
+    CDML_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
 }

@@ -9,6 +9,7 @@ Forward (models.py:46-62 and `fully_connected` models.py:19-30), per row of the 
 Backward = the written-out autodiff of train.py:141-142 (see oracle/cdml_oracle.py::tower_backward).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -284,13 +285,14 @@ class TowerEngine:
 
   # ------------------------------------------------------------------ CUDA graph
   def capture_step(self, table16, B, mine=False):
-    """Capture one full optimisation step (gather -> fwd -> [mining] -> loss -> bwd -> Adam) in a CUDA graph and return
-    `replay(idx) -> stats`: `idx` [B,3] int64 (device or pinned host) is copied into the graph's static index buffer,
-    then ONE graph launch replaces the ~30 kernel launches of the step (the host launch phase, ~0.35 ms, is what
-    bounds small batches such as config 1's B=1024).  Single-GPU only: with N>1 ranks the step contains an NCCL
-    all-reduce and is launched eagerly."""
-    if self.world > 1:
-      raise RuntimeError("capture_step is single-GPU; data-parallel steps are launched eagerly")
+    """Capture one full optimisation step (gather -> fwd -> [mining] -> loss -> bwd -> [all-reduce] -> Adam) in a CUDA
+    graph and return `replay(idx) -> stats`: `idx` [B,3] int64 (device or pinned host) is copied into the graph's static
+    index buffer, then ONE graph launch replaces the ~30 kernel launches of the step (the host launch phase, ~0.35 ms,
+    is what bounds small batches such as config 1's B=1024).  With N>1 ranks the NCCL all-reduce of the flat gradient
+    buffer is captured inside the graph (every rank must call capture_step / replay the same number of times);
+    CDML_DDP_GRAPH=0 keeps data-parallel steps eager."""
+    if self.world > 1 and os.environ.get("CDML_DDP_GRAPH", "1") == "0":
+      raise RuntimeError("capture_step disabled for data-parallel runs (CDML_DDP_GRAPH=0)")
     static_idx = torch.zeros((B, 3), dtype=torch.int64, device=self.device)
     static_idx[:, 1], static_idx[:, 2] = 1 % table16.shape[0], 2 % table16.shape[0]
     snap = (self.w.clone(), self.m.clone(), self.v.clone(), self.step_counter.clone())   # warm-up must not train
@@ -301,9 +303,12 @@ class TowerEngine:
         self.train_step_indices(table16, static_idx, mine=mine)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    if self.world > 1:
+      torch.distributed.barrier(group=self.pg)
     graph = torch.cuda.CUDAGraph()
     launches0 = ops.launch_count()
-    with torch.cuda.graph(graph):
+    # thread_local: NCCL's watchdog thread may touch the CUDA API while this thread captures
+    with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.world > 1 else "global"):
       stats = self.train_step_indices(table16, static_idx, mine=mine)
     launches_per_step = ops.launch_count() - launches0
     ops._count(-launches_per_step)                     # nothing ran during capture

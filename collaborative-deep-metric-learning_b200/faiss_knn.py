@@ -48,6 +48,21 @@ def _device():
   return torch.device("cuda:%d" % torch.cuda.current_device())
 
 
+def sharded_search(index, xq, k, id_offset=0, metric="L2", process_group=None):
+  """Top-k of the (replicated) queries `xq` over a row-sharded index: this rank searches its own rows (global ids =
+  local row + id_offset), the per-shard [nq,k] results are all-gathered over NCCL and merged on the GPU by
+  cdml_knn_merge (ties -> lower id).  Device tensors in, device tensors out; identical on every rank."""
+  D, I = index.search(xq, k, id_offset=id_offset)
+  world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+  if world > 1:
+    Dg = torch.empty((world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
+    Ig = torch.empty((world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
+    torch.distributed.all_gather_into_tensor(Dg, D, group=process_group)
+    torch.distributed.all_gather_into_tensor(Ig, I, group=process_group)
+    D, I = ops.knn_merge(Dg, Ig, metric)
+  return D, I
+
+
 def calc_knn(embeddings, q_embeddings=None, nearest_num=51, l2_norm=True, M=80, efConstruction=64, efSearch=32,
              metric="L2", process_group=None):
   """Exact KNN of q_embeddings (default: the embeddings themselves) in embeddings.
@@ -74,13 +89,7 @@ def calc_knn(embeddings, q_embeddings=None, nearest_num=51, l2_norm=True, M=80, 
   index = ops.FlatIndex(xb, metric)
   print('create index time cost:', time.time() - begin)
   end = time.time()
-  D, I = index.search(xq, nearest_num, id_offset=lo)
-  if world > 1:
-    Dg = torch.empty((world,) + tuple(D.shape), dtype=D.dtype, device=dev)
-    Ig = torch.empty((world,) + tuple(I.shape), dtype=I.dtype, device=dev)
-    torch.distributed.all_gather_into_tensor(Dg, D, group=process_group)
-    torch.distributed.all_gather_into_tensor(Ig, I, group=process_group)
-    D, I = ops.knn_merge(Dg, Ig, metric)
+  D, I = sharded_search(index, xq, nearest_num, lo, metric, process_group)
   D, I = D.cpu().numpy(), I.cpu().numpy()
   index.close()
   print('whole set query time cost:', time.time() - end)
