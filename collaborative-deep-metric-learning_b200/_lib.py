@@ -37,6 +37,8 @@ _SIGNATURES = {
   "cdml_knn_index_build": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, POINTER(c_void_p)]),
   "cdml_knn_index_destroy": (c_int, [_P]),
   "cdml_knn_search": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, c_int64, _P]),
+  "cdml_knn_bounds": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P]),
+  "cdml_knn_search_bounded": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, c_int64, _P]),
   "cdml_knn_last_stats": (c_int, [_P, POINTER(c_int64)]),
   "cdml_knn_merge": (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P, _P]),
   "cdml_mean_pair_dist": (c_int, [_P, _P, c_int64, c_int, _P, c_int64, _P, _P]),

@@ -318,6 +318,16 @@ knn_kth_kernel(const float* __restrict__ gmax, int64_t ldg, int G, int k, const 
   }
 }
 
+// Collection bound from bounds agreed across index shards: thr = max(full, part) - slack(q)  (-inf when no shard had one)
+__global__ void knn_thr_combine_kernel(const float* __restrict__ full, const float* __restrict__ part,
+                                       const float* __restrict__ qss, int64_t n, float slack_scale, float slack_abs,
+                                       float* __restrict__ thr) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float b = fmaxf(full[i], part[i]);
+  thr[i] = b > neg_inf() ? b - (slack_scale * sqrtf(qss[i]) + slack_abs) : neg_inf();
+}
+
 // Per query: approximate prune -> exact fp32 re-rank -> (distance,id) sort -> top-k.
 __global__ void __launch_bounds__(kRefineThreads)
 knn_refine_kernel(const float* __restrict__ Q, int64_t ldq, int d, const float* __restrict__ qss,
@@ -744,9 +754,15 @@ static int ensure_workspace(cdml_index* ix, int64_t qc) {
   return 0;
 }
 
-int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k, float* D,
-                    int64_t* I, int64_t id_offset, void* stream) {
-  CDML_REQUIRE(ctx && ix && Q && D && I, "cdml_knn_search: NULL argument");
+// One implementation, three uses:
+//   search          (ext_full == nullptr, out_full == nullptr): bound pass + collect + refine, self-contained;
+//   bounds only     (out_full != nullptr): bound pass; writes the raw k_full-th / k_part-th best sampled scores per query;
+//   bounded search  (ext_full != nullptr): skips the bound pass, collects above max(ext_full, ext_part) - slack.
+static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k, float* D, int64_t* I,
+                   int64_t id_offset, void* stream, const float* ext_full, const float* ext_part, int k_part,
+                   float* out_full, float* out_part) {
+  const bool bounds_only = out_full != nullptr;
+  CDML_REQUIRE(ctx && ix && Q && (bounds_only || (D && I)), "cdml_knn_search: NULL argument");
   CDML_REQUIRE(nq >= 0 && ldq >= ix->d && k >= 1 && k <= 1024, "cdml_knn_search: bad arguments (k=%d, supported 1..1024)", k);
   CDML_REQUIRE(k <= kKeepCap / 2, "cdml_knn_search: k=%d exceeds the re-rank capacity %d", k, kKeepCap / 2);
   if (nq == 0) return 0;
@@ -780,8 +796,16 @@ int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, i
     CDML_CHECK_CUDA(cudaMemsetAsync(ix->overflow, 0, sizeof(int32_t) * qc, st));
     CDML_CHECK_CUDA(cudaMemsetAsync(ix->log_count, 0, sizeof(int32_t) * (ctx->num_sms * kKnnLogsPerCta + 1), st));
     const bool tiny = ix->N <= kKeepCap;   // tiny database: exact re-rank of every row, no tensor-core scan
+    if (bounds_only && (tiny || !(ix->Ns > 0 && ix->Ns / 32 >= k))) {   // no usable sample: no bound from this shard
+      fill_f32_kernel<<<64, 256, 0, st>>>(out_full + q0, qc, -INFINITY);
+      fill_f32_kernel<<<64, 256, 0, st>>>(out_part + q0, qc, -INFINITY);
+      continue;
+    }
     if (!tiny) {
-      if (ix->Ns > 0 && ix->Ns / 32 >= k) {
+      if (ext_full != nullptr) {
+        knn_thr_combine_kernel<<<static_cast<int>((qc + 255) / 256), 256, 0, st>>>(ext_full + q0, ext_part + q0, ix->qss, qc,
+                                                                                slack_scale, slack_abs, ix->thr);
+      } else if (ix->Ns > 0 && ix->Ns / 32 >= k) {
         const int wide = (ix->Ns / 128 >= 2 * static_cast<int64_t>(k)) ? 1 : 0;
         const int groups = wide ? static_cast<int>((ix->Ns + 255) / 256 * 2) : static_cast<int>(ix->Ns / 32);
         EpiKnnGroupMax<kBN> ea{ix->hs, ix->gmax, ix->ldg, wide};
@@ -790,12 +814,20 @@ int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, i
         else
           rc = launch_gemm<0, 0>(ctx, ix->q16, ix->dpad, ix->xs16, ix->dpad, qc, ix->Ns, ix->dpad, CDML_F16, 1, ea, st);
         if (rc < 0) return rc;
-        if (groups <= 4 * kRefineThreads)
-          knn_kth_kernel<4><<<static_cast<int>(qc), kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, k, ix->qss, slack_scale,
-                                                                          slack_abs, ix->thr);
-        else
-          knn_kth_kernel<kMaxGroups / kRefineThreads><<<static_cast<int>(qc), kRefineThreads, 0, st>>>(
-              ix->gmax, ix->ldg, groups, k, ix->qss, slack_scale, slack_abs, ix->thr);
+        auto kth = [&](int kk, float sc, float ab, float* out) {
+          if (groups <= 4 * kRefineThreads)
+            knn_kth_kernel<4><<<static_cast<int>(qc), kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, ix->qss, sc, ab, out);
+          else
+            knn_kth_kernel<kMaxGroups / kRefineThreads><<<static_cast<int>(qc), kRefineThreads, 0, st>>>(
+                ix->gmax, ix->ldg, groups, kk, ix->qss, sc, ab, out);
+        };
+        if (bounds_only) {
+          kth(k, 0.f, 0.f, out_full + q0);                       // raw scores: the caller combines them across shards
+          kth(std::max(1, std::min(k_part, k)), 0.f, 0.f, out_part + q0);
+          CDML_CHECK_CUDA(cudaGetLastError());
+          continue;
+        }
+        kth(k, slack_scale, slack_abs, ix->thr);
       } else {
         fill_f32_kernel<<<64, 256, 0, st>>>(ix->thr, qc, -INFINITY);
       }
@@ -824,6 +856,7 @@ int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, i
     CDML_CHECK_CUDA(cudaMemcpyAsync(ix->h_logovf + q0 / chunk, ix->log_count + ctx->num_sms * kKnnLogsPerCta, sizeof(int32_t),
                                     cudaMemcpyDeviceToHost, st));
   }
+  if (bounds_only) return 0;
   CDML_CHECK_CUDA(cudaStreamSynchronize(st));
   // rare: queries whose candidate list (or whose chunk's warp log) overflowed are redone exactly in fp32
   for (int64_t i = 0; i < nq; ++i) {
@@ -837,6 +870,25 @@ int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, i
     CDML_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
+}
+
+
+int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k, float* D,
+                    int64_t* I, int64_t id_offset, void* stream) {
+  return knn_run(ctx, ix, Q, nq, ldq, k, D, I, id_offset, stream, nullptr, nullptr, k, nullptr, nullptr);
+}
+
+int cdml_knn_bounds(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k_full, int k_part,
+                    float* bound_full, float* bound_part, void* stream) {
+  CDML_REQUIRE(bound_full && bound_part && k_part >= 1, "cdml_knn_bounds: NULL / bad argument");
+  return knn_run(ctx, ix, Q, nq, ldq, k_full, nullptr, nullptr, 0, stream, nullptr, nullptr, k_part, bound_full, bound_part);
+}
+
+int cdml_knn_search_bounded(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k,
+                            const float* bound_full, const float* bound_part, float* D, int64_t* I, int64_t id_offset,
+                            void* stream) {
+  CDML_REQUIRE(bound_full && bound_part, "cdml_knn_search_bounded: NULL bounds");
+  return knn_run(ctx, ix, Q, nq, ldq, k, D, I, id_offset, stream, bound_full, bound_part, k, nullptr, nullptr);
 }
 
 int cdml_knn_merge(cdml_ctx* ctx, const float* Dg, const int64_t* Ig, int G, int64_t nq, int k, int metric, float* D,

@@ -48,19 +48,38 @@ def _device():
   return torch.device("cuda:%d" % torch.cuda.current_device())
 
 
-def sharded_search(index, xq, k, id_offset=0, metric="L2", process_group=None):
-  """Top-k of the (replicated) queries `xq` over a row-sharded index: this rank searches its own rows (global ids =
-  local row + id_offset), the per-shard [nq,k] results are all-gathered over NCCL and merged on the GPU by
-  cdml_knn_merge (ties -> lower id).  Device tensors in, device tensors out; identical on every rank."""
-  D, I = index.search(xq, k, id_offset=id_offset)
+def sharded_search(index, xq, k, id_offset=0, metric="L2", process_group=None, merge_fn=None):
+  """Top-k of the (replicated) queries `xq` over a row-sharded index; device tensors in and out, identical on every rank.
+
+  1. bound pass on every shard, then two tiny NCCL all-reduces agree on one collection bound per query (MAX of the
+     shards' k-th best sampled score, MIN of their ceil(k/W)-th best): together the shards nominate about as many
+     candidates as one unsharded index would, instead of W times as many;
+  2. collect + exact re-rank on every shard -> local top-k with global ids (local row + id_offset);
+  3. NCCL all-to-all: rank r receives every shard's lists for ITS slice of the queries and merges them on the GPU
+     (cdml_knn_merge, ties -> lower id); one all-gather of the merged slices completes the result."""
   world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
-  if world > 1:
-    Dg = torch.empty((world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
-    Ig = torch.empty((world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
-    torch.distributed.all_gather_into_tensor(Dg, D, group=process_group)
-    torch.distributed.all_gather_into_tensor(Ig, I, group=process_group)
-    D, I = ops.knn_merge(Dg, Ig, metric)
-  return D, I
+  if world == 1:
+    return index.search(xq, k, id_offset=id_offset)
+  merge_fn = merge_fn or ops.knn_merge      # (tests drive this protocol over gloo with a CPU stand-in)
+  bf, bp = index.bounds(xq, k, -(-k // world))
+  torch.distributed.all_reduce(bf, op=torch.distributed.ReduceOp.MAX, group=process_group)
+  torch.distributed.all_reduce(bp, op=torch.distributed.ReduceOp.MIN, group=process_group)
+  D, I = index.search_bounded(xq, k, bf, bp, id_offset=id_offset)
+  nq = xq.shape[0]
+  if nq % world == 0 and nq >= world:
+    Dg, Ig = torch.empty_like(D), torch.empty_like(I)           # [W, nq/W, k]: every shard's lists for my query slice
+    torch.distributed.all_to_all_single(Dg, D, group=process_group)
+    torch.distributed.all_to_all_single(Ig, I, group=process_group)
+    Dm, Im = merge_fn(Dg.view(world, nq // world, k), Ig.view(world, nq // world, k), metric)
+    D, I = torch.empty_like(D), torch.empty_like(I)
+    torch.distributed.all_gather_into_tensor(D, Dm, group=process_group)
+    torch.distributed.all_gather_into_tensor(I, Im, group=process_group)
+    return D, I
+  Dg = torch.empty((world * nq, k), dtype=D.dtype, device=D.device)
+  Ig = torch.empty((world * nq, k), dtype=I.dtype, device=I.device)
+  torch.distributed.all_gather_into_tensor(Dg, D, group=process_group)
+  torch.distributed.all_gather_into_tensor(Ig, I, group=process_group)
+  return merge_fn(Dg.view(world, nq, k), Ig.view(world, nq, k), metric)
 
 
 def calc_knn(embeddings, q_embeddings=None, nearest_num=51, l2_norm=True, M=80, efConstruction=64, efSearch=32,

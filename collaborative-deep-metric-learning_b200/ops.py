@@ -219,6 +219,26 @@ class FlatIndex(object):
                                       int(id_offset), stream_ptr()))
     return D, I
 
+  def bounds(self, xq, k_full, k_part):
+    """Bound pass only: per query the raw k_full-th and k_part-th best sampled scores of this shard (device fp32 [nq])."""
+    nq = xq.shape[0]
+    bf = torch.empty((nq,), dtype=torch.float32, device=xq.device)
+    bp = torch.empty((nq,), dtype=torch.float32, device=xq.device)
+    _count(4 * ((nq + 32767) // 32768))
+    check(_lib.load().cdml_knn_bounds(_ctx(xq), self._h, ptr(xq), nq, _row_major_2d(xq, "xq"), int(k_full), int(k_part),
+                                      ptr(bf), ptr(bp), stream_ptr()))
+    return bf, bp
+
+  def search_bounded(self, xq, k, bound_full, bound_part, id_offset=0):
+    """Collect + refine above max(bound_full, bound_part) - slack (bounds agreed across shards by the caller)."""
+    nq = xq.shape[0]
+    D = torch.empty((nq, k), dtype=torch.float32, device=xq.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=xq.device)
+    _count(5 * ((nq + 32767) // 32768))
+    check(_lib.load().cdml_knn_search_bounded(_ctx(xq), self._h, ptr(xq), nq, _row_major_2d(xq, "xq"), k, ptr(bound_full),
+                                              ptr(bound_part), ptr(D), ptr(I), int(id_offset), stream_ptr()))
+    return D, I
+
   def last_stats(self):
     s = (ctypes.c_int64 * 2)()
     check(_lib.load().cdml_knn_last_stats(self._h, s))

@@ -124,6 +124,18 @@ int cdml_knn_index_build(cdml_ctx* ctx, const float* X, int64_t N, int d, int64_
 int cdml_knn_index_destroy(cdml_index* index);
 int cdml_knn_search(cdml_ctx* ctx, cdml_index* index, const float* Q, int64_t nq, int64_t ldq, int k, float* D,
                     int64_t* I, int64_t id_offset, void* stream);
+/* Row-sharded index, two-phase search (the exchange between the phases is the caller's: NCCL all-reduce MAX of bound_full
+ * and MIN of bound_part over the shards).  cdml_knn_bounds runs the bound pass only and writes, per query, the raw
+ * k_full-th and k_part-th best sampled scores of THIS shard (-inf when the shard has no usable sample).  Any shard has
+ * k_full rows above its bound_full, and every shard has k_part rows above the smallest bound_part, so with
+ * k_part = ceil(k / shards) both max_s(bound_full) and min_s(bound_part) are lower bounds of the global k-th best score.
+ * cdml_knn_search_bounded then collects only rows scoring above max(bound_full, bound_part) - slack: the shards together
+ * nominate about as many candidates as one unsharded index instead of `shards` times as many. */
+int cdml_knn_bounds(cdml_ctx* ctx, cdml_index* index, const float* Q, int64_t nq, int64_t ldq, int k_full, int k_part,
+                    float* bound_full, float* bound_part, void* stream);
+int cdml_knn_search_bounded(cdml_ctx* ctx, cdml_index* index, const float* Q, int64_t nq, int64_t ldq, int k,
+                            const float* bound_full, const float* bound_part, float* D, int64_t* I, int64_t id_offset,
+                            void* stream);
 /* Counters of the last search: stats[0] = candidates nominated, [1] = queries that overflowed to the exact fallback. */
 int cdml_knn_last_stats(cdml_index* index, int64_t* stats);
 /* Merge G per-shard results [G,nq,k] into the global top-k (ties -> lower id). */

@@ -342,6 +342,32 @@ def test_calc_knn_api_and_sharded_merge(cd, tmp_path):
   assert txt == "".join(O.format_knn_rows(0, D, I, dm))
 
 
+def test_sharded_two_phase_search_with_agreed_bounds(cd):
+  """Row-sharded index, bound exchange emulated on one GPU: per-shard cdml_knn_bounds, MAX / MIN across the shards (what
+  the NCCL all-reduces do), cdml_knn_search_bounded per shard (lists may be SHORTER than k: -1 / inf padded), merge."""
+  rng = np.random.RandomState(11)
+  N, nq, k, W = 40000, 512, 100, 4
+  X = O.knn_normalize(rng.standard_normal((N, 256)).astype(np.float32))
+  Q = X[rng.choice(N, nq, replace=False)]
+  Dw, Iw = O.flat_knn(X, Q, k=k, l2_norm=False)
+  xq = dev_t(cd, Q)
+  shards = [(s * N // W, (s + 1) * N // W) for s in range(W)]
+  idx = [cd.ops.FlatIndex(dev_t(cd, X[lo:hi]), "L2") for lo, hi in shards]
+  b = [ix.bounds(xq, k, -(-k // W)) for ix in idx]
+  bf = torch.stack([x[0] for x in b]).max(0).values
+  bp = torch.stack([x[1] for x in b]).min(0).values
+  assert torch.isfinite(bf).all() and torch.isfinite(bp).all()
+  parts = [ix.search_bounded(xq, k, bf, bp, id_offset=lo) for ix, (lo, hi) in zip(idx, shards)]
+  total = sum(ix.last_stats()["candidates"] for ix in idx)
+  single = cd.ops.FlatIndex(dev_t(cd, X), "L2")
+  single.search(xq, k)
+  assert total < 2.5 * single.last_stats()["candidates"]         # ~ one index's worth of nominees, not W times as many
+  assert any((p[1] < 0).any().item() for p in parts)             # some shard lists really are short (padding path taken)
+  Dm, Im = cd.ops.knn_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), "L2")
+  assert (Im >= 0).all().item()
+  assert_knn_matches(Dm.cpu().numpy(), Im.cpu().numpy(), Dw, Iw, 'L2', X, Q)
+
+
 def test_mean_dist_matches_oracle(cd, golden):
   from cdml_b200.evaluate import Evaluation
   ev = Evaluation(golden["gather_features"], golden["eval_cowatches"].tolist())

@@ -198,15 +198,35 @@ dist.all_reduce(flat)
 flat = flat.numpy() / (Bl * world)
 want = np.concatenate([np.concatenate([gW.ravel(), gb]) for gW, gb in full])
 assert np.allclose(flat, want, atol=1e-12), np.abs(flat - want).max()
-# --- row-sharded KNN: local top-k with id offset, all-gather, merge == global top-k
+# --- row-sharded KNN through the PRODUCT's sharded_search (bound exchange -> bounded search -> all-to-all -> merge ->
+#     all-gather), with a CPU stand-in for the device index / merge kernel built on the oracle
+from cdml_b200 import faiss_knn
+class ShardIndex:
+  def __init__(self, xb): self.xb = xb
+  def _scores(self, xq): return xq.numpy() @ self.xb.T - 0.5 * (self.xb ** 2).sum(1)[None, :]
+  def bounds(self, xq, k_full, k_part):
+    s = np.sort(self._scores(xq), axis=1)[:, ::-1]
+    pick = lambda kk: torch.tensor(np.ascontiguousarray(s[:, kk - 1] if kk <= s.shape[1] else np.full(len(s), -np.inf), dtype=np.float32))
+    return pick(k_full), pick(k_part)
+  def search_bounded(self, xq, k, bf, bp, id_offset=0):
+    s, thr = self._scores(xq), np.maximum(bf.numpy(), bp.numpy()) - 1e-5
+    D = np.full((len(s), k), np.inf, np.float32); I = np.full((len(s), k), -1, np.int64)
+    for i in range(len(s)):
+      rows = np.nonzero(s[i] > thr[i])[0]
+      if len(rows):
+        d, ids = O.flat_knn(self.xb[rows], xq.numpy()[i:i + 1], k=min(k, len(rows)), l2_norm=False)
+        D[i, :d.shape[1]], I[i, :d.shape[1]] = d[0], rows[ids[0]] + id_offset
+    return torch.tensor(D), torch.tensor(I)
+def cpu_merge(Dg, Ig, metric):
+  Dm, Im = O.knn_merge([d.numpy() for d in Dg], [i.numpy() for i in Ig], Dg.shape[2])
+  return torch.tensor(Dm), torch.tensor(Im)
 X = O.knn_normalize(np.random.RandomState(4).standard_normal((301, 16)).astype(np.float32))
 lo, hi = rank * 301 // world, (rank + 1) * 301 // world
-D, I = O.flat_knn(X[lo:hi], X, k=7, l2_norm=False)
-Dg = [torch.zeros(301, 7) for _ in range(world)]; Ig = [torch.zeros(301, 7, dtype=torch.int64) for _ in range(world)]
-dist.all_gather(Dg, torch.tensor(D)); dist.all_gather(Ig, torch.tensor(I + lo))
-Dm, Im = O.knn_merge([d.numpy() for d in Dg], [i.numpy() for i in Ig], 7)
 Dw, Iw = O.flat_knn(X, k=7, l2_norm=False)
-assert np.array_equal(Im, Iw) and np.allclose(Dm, Dw, atol=1e-6)
+for nq in (300, 301):      # divisible by the world size (all-to-all path) and not (all-gather fallback)
+  Dm, Im = faiss_knn.sharded_search(ShardIndex(X[lo:hi]), torch.tensor(X[:nq]), 7, lo, "L2", dist.group.WORLD, merge_fn=cpu_merge)
+  assert np.array_equal(Im.numpy(), Iw[:nq]) and np.allclose(Dm.numpy(), Dw[:nq], atol=1e-6), nq
+  assert (Im.numpy() >= 0).all()
 dist.barrier(); dist.destroy_process_group()
 print("rank %d ok" % rank)
 '''
