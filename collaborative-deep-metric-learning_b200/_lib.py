@@ -31,6 +31,10 @@ _SIGNATURES = {
                                  _P, _P, c_int64, c_int, _P, _P]),
   "cdml_adam_prepare": (c_int, [_P, _P, c_float, c_float, c_float, c_int, c_float, c_float, _P, _P]),
   "cdml_adam_apply": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, _P, c_int, _P]),
+  "cdml_opt_workspace_floats": (c_int64, []),
+  "cdml_opt_sumsq": (c_int, [_P, _P, _P, c_int64, c_float, c_float, _P, _P, _P]),
+  "cdml_opt_apply": (c_int, [_P, c_int, _P, _P, _P, _P, c_int64, _P, _P, c_float, c_float, c_float, c_float, c_float,
+                             c_float, c_float, c_float, c_float, _P, c_int, _P]),
   "cdml_cast16": (c_int, [_P, _P, c_int64, _P, c_int, _P]),
   "cdml_fill_column16": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_float, c_int, _P]),
   "cdml_mine_semihard": (c_int, [_P, _P, c_int64, c_int, _P, c_int64, _P, c_int64, c_int, c_float, _P, _P, _P]),

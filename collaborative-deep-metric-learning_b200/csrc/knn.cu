@@ -290,10 +290,11 @@ __device__ __forceinline__ int block_sum(int v, int* sh) {
 // Bitwise bisection over the order-preserving key, stopped after the top kSelectBits bits: the result is the true
 // k-th key rounded DOWN (a bound may always be lower), at 2^-12 relative precision -- far inside the slack.
 constexpr int kSelectBits = 20;
-template <int kPer>
+// Both selections of one launch share the loaded keys and the block reductions (the two counts travel in one int).
+template <int kPer, bool kDual>
 __global__ void __launch_bounds__(kRefineThreads)
-knn_kth_kernel(const float* __restrict__ gmax, int64_t ldg, int G, int k, const float* __restrict__ qss,
-               float slack_scale, float slack_abs, float* __restrict__ thr) {
+knn_kth_kernel(const float* __restrict__ gmax, int64_t ldg, int G, int k, int k2, const float* __restrict__ qss,
+               float slack_scale, float slack_abs, float* __restrict__ thr, float* __restrict__ thr2) {
   __shared__ int sh[kRefineThreads / 32];
   const int q = blockIdx.x;
   const float* g = gmax + static_cast<int64_t>(q) * ldg;
@@ -303,18 +304,20 @@ knn_kth_kernel(const float* __restrict__ gmax, int64_t ldg, int G, int k, const 
     const int j = threadIdx.x + i * kRefineThreads;
     keys[i] = j < G ? f2key(g[j]) : 0u;
   }
-  uint32_t T = 0;
+  uint32_t T = 0, T2 = 0;   // k-th and k2-th best key (k2 only when thr2 != nullptr); counts fit 16 bits (G <= 4096)
   for (int bit = 31; bit >= 32 - kSelectBits; --bit) {
-    const uint32_t cand = T | (1u << bit);
+    const uint32_t cand = T | (1u << bit), cand2 = T2 | (1u << bit);
     int c = 0;
 #pragma unroll
-    for (int i = 0; i < kPer; ++i) c += keys[i] >= cand ? 1 : 0;
-    if (block_sum(c, sh) >= k) T = cand;
+    for (int i = 0; i < kPer; ++i) c += (keys[i] >= cand ? 1 : 0) + (kDual && keys[i] >= cand2 ? 65536 : 0);
+    c = block_sum(c, sh);
+    if ((c & 0xffff) >= k) T = cand;
+    if (kDual && (c >> 16) >= k2) T2 = cand2;
   }
   if (threadIdx.x == 0) {
-    const float kth = key2f(T);
-    const bool finite = T > f2key(neg_inf());
-    thr[q] = finite ? kth - (slack_scale * sqrtf(qss[q]) + slack_abs) : neg_inf();
+    const float slack = slack_scale * sqrtf(qss[q]) + slack_abs;
+    thr[q] = T > f2key(neg_inf()) ? key2f(T) - slack : neg_inf();
+    if (kDual) thr2[q] = T2 > f2key(neg_inf()) ? key2f(T2) - slack : neg_inf();
   }
 }
 
@@ -814,20 +817,23 @@ static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, in
         else
           rc = launch_gemm<0, 0>(ctx, ix->q16, ix->dpad, ix->xs16, ix->dpad, qc, ix->Ns, ix->dpad, CDML_F16, 1, ea, st);
         if (rc < 0) return rc;
-        auto kth = [&](int kk, float sc, float ab, float* out) {
-          if (groups <= 4 * kRefineThreads)
-            knn_kth_kernel<4><<<static_cast<int>(qc), kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, ix->qss, sc, ab, out);
-          else
-            knn_kth_kernel<kMaxGroups / kRefineThreads><<<static_cast<int>(qc), kRefineThreads, 0, st>>>(
-                ix->gmax, ix->ldg, groups, kk, ix->qss, sc, ab, out);
+        auto kth = [&](int kk, int kk2, float sc, float ab, float* out, float* out2) {
+          const int grid = static_cast<int>(qc);
+          if (groups <= 4 * kRefineThreads) {
+            if (out2) knn_kth_kernel<4, true><<<grid, kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, sc, ab, out, out2);
+            else knn_kth_kernel<4, false><<<grid, kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, sc, ab, out, out2);
+          } else {
+            constexpr int kP = kMaxGroups / kRefineThreads;
+            if (out2) knn_kth_kernel<kP, true><<<grid, kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, sc, ab, out, out2);
+            else knn_kth_kernel<kP, false><<<grid, kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, sc, ab, out, out2);
+          }
         };
-        if (bounds_only) {
-          kth(k, 0.f, 0.f, out_full + q0);                       // raw scores: the caller combines them across shards
-          kth(std::max(1, std::min(k_part, k)), 0.f, 0.f, out_part + q0);
+        if (bounds_only) {   // raw scores: the caller combines them across shards
+          kth(k, std::max(1, std::min(k_part, k)), 0.f, 0.f, out_full + q0, out_part + q0);
           CDML_CHECK_CUDA(cudaGetLastError());
           continue;
         }
-        kth(k, slack_scale, slack_abs, ix->thr);
+        kth(k, k, slack_scale, slack_abs, ix->thr, nullptr);
       } else {
         fill_f32_kernel<<<64, 256, 0, st>>>(ix->thr, qc, -INFINITY);
       }

@@ -1,5 +1,6 @@
 // HBM-bound row kernels of the CDML hot path: gather, normalise+cast, hinge loss fwd/bwd, bias-gradient
 // column sums, split-K reduction, TF1 Adam, pair distances.  One warp per row wherever a row is the unit.
+#include <algorithm>
 #include "../../include/cdml.h"
 #include "ctx.cuh"
 
@@ -384,6 +385,85 @@ pair_dist_kernel(const float* __restrict__ V, int64_t ld, int D, const int64_t* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Gradient post-processing + the other optimizers of build_graph (train.py:115-146):
+//   g_eff = grad_scale * g + wd_reg * w                      (mean gradient + regularization_penalty * d reg / dw)
+//   clip_by_norm per variable (train.py:47-64):  g_eff *= clip / max(||g_eff||, clip)
+//   kind 0 Adam | 1 Momentum(0.9, nesterov) (train.py:115-116) | 2 LARS (tf.contrib.opt.LARSOptimizer, train.py:354)
+//        | 3 plain gradient descent
+// Norms come from opt_sumsq (fixed-order two-stage reduction -> deterministic).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSumsqBlocks = 592;   // 148 SMs x 4
+
+__global__ void __launch_bounds__(256)
+opt_sumsq_stage1_kernel(const float* __restrict__ g, const float* __restrict__ w, int64_t n, float gscale, float wd_reg,
+                        float* __restrict__ partial) {
+  __shared__ float sh[2][8];
+  float a = 0.f, b = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float wi = w[i];
+    const float ge = fmaf(wd_reg, wi, g[i] * gscale);
+    a = fmaf(ge, ge, a), b = fmaf(wi, wi, b);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o), b += __shfl_xor_sync(0xffffffffu, b, o);
+  if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = a, sh[1][threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ta = 0.f, tb = 0.f;
+    for (int i = 0; i < 8; ++i) ta += sh[0][i], tb += sh[1][i];
+    partial[2 * blockIdx.x] = ta, partial[2 * blockIdx.x + 1] = tb;
+  }
+}
+
+__global__ void opt_sumsq_stage2_kernel(const float* __restrict__ partial, int nblocks, float* __restrict__ out2) {
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int i = 0; i < nblocks; ++i) t += static_cast<double>(partial[2 * i + threadIdx.x]);
+    out2[threadIdx.x] = static_cast<float>(t);
+  }
+}
+
+template <int kBf16>
+__global__ void opt_apply_kernel(int kind, float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
+                                 const float* __restrict__ g, int64_t n, const float* __restrict__ scalars,
+                                 const float* __restrict__ norms, float beta1, float beta2, float eps, float gscale,
+                                 float wd_reg, float clip, float momentum, float lars_wd, float lars_eeta,
+                                 uint16_t* __restrict__ w16) {
+  const float lr_t = scalars[0], lr = scalars[1];
+  float coef = 1.f, trust = 1.f;
+  if (clip > 0.f) coef = clip / fmaxf(sqrtf(norms[0]), clip);
+  if (kind == 2) {
+    const float wn = sqrtf(norms[1]);
+    const float gn = sqrtf(norms[0]) * coef;          // norm of the (clipped) gradient handed to the optimizer
+    trust = (wn > 0.f && gn > 0.f) ? lars_eeta * wn / (gn + lars_wd * wn + eps) : 1.f;
+  }
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float wi = w[i];
+    const float gi = fmaf(wd_reg, wi, g[i] * gscale) * coef;
+    if (kind == 0) {
+      const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+      const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+      wi -= lr_t * mi / (sqrtf(vi) + eps);
+      m[i] = mi, v[i] = vi;
+    } else if (kind == 1) {                              // ApplyMomentum, use_nesterov
+      const float acc = momentum * m[i] + gi;
+      wi -= lr * gi + lr * momentum * acc;
+      m[i] = acc;
+    } else if (kind == 2) {                              // LARS: weight decay joins the gradient, plain momentum
+      const float acc = momentum * m[i] + (gi + lars_wd * wi);
+      wi -= lr * trust * acc;
+      m[i] = acc;
+    } else {
+      wi -= lr * gi;
+    }
+    w[i] = wi;
+    if (w16 != nullptr) w16[i] = static_cast<uint16_t>(pack2<kBf16>(wi, 0.f));
+  }
+}
+
 static inline int flat_grid(cdml_ctx* ctx, int64_t n, int threads) {
   const int64_t blocks = (n + threads - 1) / threads;
   const int64_t cap = static_cast<int64_t>(ctx->num_sms) * 8;
@@ -550,6 +630,39 @@ int cdml_adam_apply(cdml_ctx* ctx, float* w, float* m, float* v, const float* g,
   else
     adam_apply_kernel<0><<<grid, 256, 0, st>>>(w, m, v, g, n, scalars, beta1, beta2, eps, grad_scale,
                                                static_cast<uint16_t*>(w16));
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t cdml_opt_workspace_floats(void) { return 2 * kSumsqBlocks + 2; }
+
+int cdml_opt_sumsq(cdml_ctx* ctx, const float* g, const float* w, int64_t n, float grad_scale, float wd_reg,
+                   float* workspace, float* out2, void* stream) {
+  CDML_REQUIRE(ctx && g && w && workspace && out2 && n >= 0, "cdml_opt_sumsq: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, kSumsqBlocks)));
+  opt_sumsq_stage1_kernel<<<blocks, 256, 0, st>>>(g, w, n, grad_scale, wd_reg, workspace);
+  opt_sumsq_stage2_kernel<<<1, 32, 0, st>>>(workspace, blocks, out2);
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cdml_opt_apply(cdml_ctx* ctx, int kind, float* w, float* m, float* v, const float* g, int64_t n, const float* scalars,
+                   const float* norms, float beta1, float beta2, float eps, float grad_scale, float wd_reg, float clip_norm,
+                   float momentum, float lars_weight_decay, float lars_eeta, void* w16, int dtype16, void* stream) {
+  CDML_REQUIRE(ctx && w && g && scalars && kind >= 0 && kind <= 3, "cdml_opt_apply: bad argument");
+  CDML_REQUIRE(kind != 0 || (m && v), "cdml_opt_apply: Adam needs m and v");
+  CDML_REQUIRE((kind != 1 && kind != 2) || m, "cdml_opt_apply: momentum optimizers need the accumulator m");
+  CDML_REQUIRE((clip_norm <= 0.f && kind != 2) || norms, "cdml_opt_apply: clipping / LARS need the norms of cdml_opt_sumsq");
+  if (n == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = flat_grid(ctx, n, 256);
+  if (dtype16 == CDML_BF16)
+    opt_apply_kernel<1><<<grid, 256, 0, st>>>(kind, w, m, v, g, n, scalars, norms, beta1, beta2, eps, grad_scale, wd_reg,
+                                              clip_norm, momentum, lars_weight_decay, lars_eeta, static_cast<uint16_t*>(w16));
+  else
+    opt_apply_kernel<0><<<grid, 256, 0, st>>>(kind, w, m, v, g, n, scalars, norms, beta1, beta2, eps, grad_scale, wd_reg,
+                                              clip_norm, momentum, lars_weight_decay, lars_eeta, static_cast<uint16_t*>(w16));
   CDML_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

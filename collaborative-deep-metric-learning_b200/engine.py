@@ -35,7 +35,8 @@ class TowerEngine:
 
   def __init__(self, dims, device=None, dtype16=F16, seed=2, bias_init=0.0, base_lr=1e-3, margin=0.8,
                lr_decay_steps=1000000, lr_decay=0.96, beta1=0.9, beta2=0.999, eps=1e-8, alpha=LEAKY_ALPHA,
-               process_group=None, init_params=None):
+               process_group=None, init_params=None, optimizer="adam", clip_norm=0.0, reg_penalty=0.0, l2_penalty=1e-8,
+               momentum=0.9, lars_weight_decay=1e-4, lars_eeta=1e-3):
     if not torch.cuda.is_available():
       raise RuntimeError("TowerEngine needs a CUDA device (sm_100a); there is no CPU path")
     self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -52,6 +53,11 @@ class TowerEngine:
     self.margin = float(margin)
     self.base_lr, self.lr_decay_steps, self.lr_decay = float(base_lr), float(lr_decay_steps), float(lr_decay)
     self.beta1, self.beta2, self.eps = beta1, beta2, eps
+    # build_graph's gradient path (train.py:133-146): final_loss = reg_penalty * sum(l2_penalty * |W|^2 / 2) + loss, optional
+    # per-variable clip_by_norm, then the optimizer: adam | momentum (nesterov) | lars | sgd
+    self.opt_kind = {"adam": ops.OPT_ADAM, "momentum": ops.OPT_MOMENTUM, "lars": ops.OPT_LARS, "sgd": ops.OPT_SGD}[optimizer]
+    self.clip_norm, self.wd_reg = float(clip_norm), float(reg_penalty) * float(l2_penalty)
+    self.momentum, self.lars_wd, self.lars_eeta = float(momentum), float(lars_weight_decay), float(lars_eeta)
     self.pg = process_group
     self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
     self.F = self.dims[0]
@@ -80,6 +86,8 @@ class TowerEngine:
     self.W16 = [torch.zeros((self.dims[l], self.dims[l + 1]), dtype=self.t16, device=dev) for l in range(self.L)]
     self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)
     self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)
+    self.norms = torch.zeros((2 * self.L, 2), dtype=torch.float32, device=dev)       # per variable: {sum g_eff^2, sum w^2}
+    self.opt_ws = torch.empty((ops.opt_workspace_floats(),), dtype=torch.float32, device=dev)
     self._bufs = {}
     self._ws = {}
 
@@ -277,11 +285,27 @@ class TowerEngine:
     ops.adam_prepare(self.step_counter, self.scalars, self.base_lr, self.lr_decay_steps, self.lr_decay, True,
                      self.beta1, self.beta2)
     scale = 1.0 / (B_local * self.world)
+    plain_adam = self.opt_kind == ops.OPT_ADAM and self.clip_norm <= 0 and self.wd_reg == 0
     for l in range(self.L):
-      ops.adam_apply(self.W[l], self._view(self.m, 2 * l), self._view(self.v, 2 * l), self.gW[l], self.scalars,
-                     self.beta1, self.beta2, self.eps, scale, w16=self.W16[l])
-      ops.adam_apply(self.b[l], self._view(self.m, 2 * l + 1), self._view(self.v, 2 * l + 1), self.gb[l], self.scalars,
-                     self.beta1, self.beta2, self.eps, scale)
+      for i, (w, g, w16, wd) in enumerate(((self.W[l], self.gW[l], self.W16[l], self.wd_reg), (self.b[l], self.gb[l], None, 0.0))):
+        m, v = self._view(self.m, 2 * l + i), self._view(self.v, 2 * l + i)
+        if plain_adam:
+          ops.adam_apply(w, m, v, g, self.scalars, self.beta1, self.beta2, self.eps, scale, w16=w16)
+          continue
+        norms = None
+        if self.clip_norm > 0 or self.opt_kind == ops.OPT_LARS:
+          norms = ops.opt_sumsq(g, w, self.norms[2 * l + i], self.opt_ws, grad_scale=scale, wd_reg=wd)
+        ops.opt_apply(self.opt_kind, w, m, v, g, self.scalars, norms, self.beta1, self.beta2,
+                      0.0 if self.opt_kind == ops.OPT_LARS else self.eps, scale, wd, self.clip_norm, self.momentum,
+                      self.lars_wd, self.lars_eeta, w16=w16)
+
+  def reg_loss(self):
+    """sum_l l2_penalty * |W_l|^2 / 2 scaled by nothing (the summary `reg_loss`, train.py:133-136); host-side read."""
+    tot = 0.0
+    for l in range(self.L):
+      ops.opt_sumsq(self.gW[l], self.W[l], self.norms[2 * l], self.opt_ws)
+      tot += 0.5 * float(self.norms[2 * l][1].item())
+    return tot * (self.wd_reg if self.wd_reg else 0.0)
 
   # ------------------------------------------------------------------ CUDA graph
   def capture_step(self, table16, B, mine=False):

@@ -80,7 +80,8 @@ def compile_chain(out_node):
     raise NotImplementedError("all layers must share one leaky slope")
   return {"dims": [chain[0].width] + [f.attrs["output_size"] for f in fcs],
           "bias_init": [f.attrs["bias_init"] for f in fcs], "alpha": alphas.pop(),
-          "value": chain[0].attrs.get("value"), "names": [f.name for f in fcs]}
+          "value": chain[0].attrs.get("value"), "names": [f.name for f in fcs],
+          "l2_penalty": [f.attrs["l2_penalty"] for f in fcs]}
 
 
 class BaseModel(object):

@@ -159,6 +159,30 @@ def adam_apply(w, m, v, g, scalars, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale
                                     dtype16_of(w16) if w16 is not None else F16, stream_ptr()))
 
 
+OPT_ADAM, OPT_MOMENTUM, OPT_LARS, OPT_SGD = 0, 1, 2, 3
+
+
+def opt_workspace_floats():
+  return int(_lib.load().cdml_opt_workspace_floats())
+
+
+def opt_sumsq(g, w, out2, workspace, grad_scale=1.0, wd_reg=0.0):
+  """out2 = {sum (grad_scale*g + wd_reg*w)^2, sum w^2} of one variable (device fp32 [2])."""
+  _count(2)
+  check(_lib.load().cdml_opt_sumsq(_ctx(w), ptr(g), ptr(w), w.numel(), float(grad_scale), float(wd_reg), ptr(workspace),
+                                   ptr(out2), stream_ptr()))
+  return out2
+
+
+def opt_apply(kind, w, m, v, g, scalars, norms=None, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, wd_reg=0.0,
+              clip_norm=0.0, momentum=0.9, lars_weight_decay=1e-4, lars_eeta=1e-3, w16=None):
+  _count(1)
+  check(_lib.load().cdml_opt_apply(_ctx(w), int(kind), ptr(w), ptr(m), ptr(v), ptr(g), w.numel(), ptr(scalars), ptr(norms),
+                                   float(beta1), float(beta2), float(eps), float(grad_scale), float(wd_reg), float(clip_norm),
+                                   float(momentum), float(lars_weight_decay), float(lars_eeta), ptr(w16),
+                                   dtype16_of(w16) if w16 is not None else F16, stream_ptr()))
+
+
 def cast16(x, out16):
   _count(1)
   check(_lib.load().cdml_cast16(_ctx(x), ptr(x), x.numel(), ptr(out16), dtype16_of(out16), stream_ptr()))

@@ -27,7 +27,7 @@ if "train_dir" not in FLAGS:
   flags.DEFINE_string("train_dir", "training_dir/dataset/cdml_1", "training set root: *.train, features.npy, cowatches.eval/.test")
   flags.DEFINE_string("checkpoint_dir", "training_dir/checkpoints", "where model.ckpt-<step> and summaries go")
   flags.DEFINE_string("model", "VNet", "tower class name in models.py (the reference's default 'VedeNet' does not exist, SURVEY Q1)")
-  flags.DEFINE_string("optimizer", "AdamOptimizer", "AdamOptimizer (build_graph default, train.py:82); LARSOptimizer is SURVEY 8f")
+  flags.DEFINE_string("optimizer", "AdamOptimizer", "AdamOptimizer (build_graph default, train.py:82) | LARSOptimizer (main(), train.py:354) | MomentumOptimizer | GradientDescentOptimizer")
   flags.DEFINE_float("learning_rate", 1e-3, "base learning rate for Adam (main() hard-codes 1.0 for LARS, train.py:363)")
   flags.DEFINE_float("margin", 0.8, "hinge margin (train.py:364)")
   flags.DEFINE_integer("num_epochs", 8, "passes over each *.train file (train.py:359)")
@@ -43,11 +43,34 @@ class AdamOptimizer(object):
     self._lr, self.beta1, self.beta2, self.epsilon = learning_rate, beta1, beta2, epsilon
 
 
-class LARSOptimizer(object):
-  """tf.contrib.opt.LARSOptimizer (train.py:354) -- next on the scope list."""
+class MomentumOptimizer(object):
+  """tf.train.MomentumOptimizer; build_graph constructs it with momentum=0.9, use_nesterov=True (train.py:115-116)."""
+
+  def __init__(self, learning_rate, momentum=0.9, name="Momentum", use_nesterov=True):
+    if not use_nesterov:
+      raise NotImplementedError("build_graph only ever asks for the Nesterov form (train.py:116)")
+    self._learning_rate, self.momentum = learning_rate, momentum
+
+
+class GradientDescentOptimizer(object):
+  """tf.train.GradientDescentOptimizer."""
 
   def __init__(self, learning_rate):
-    raise NotImplementedError("LARSOptimizer is outside this round's hot-path scope; use AdamOptimizer")
+    self._learning_rate = learning_rate
+
+
+class LARSOptimizer(object):
+  """tf.contrib.opt.LARSOptimizer with its TF-1.13 defaults (the optimizer of the reference's main(), train.py:354)."""
+
+  def __init__(self, learning_rate, momentum=0.9, weight_decay=0.0001, eeta=0.001, epsilon=0.0):
+    self._learning_rate, self.momentum, self.weight_decay, self.eeta, self.epsilon = (
+        learning_rate, momentum, weight_decay, eeta, epsilon)
+    if epsilon != 0.0:
+      raise NotImplementedError("LARSOptimizer epsilon != 0 is not wired through")
+
+
+_OPTIMIZER_KINDS = {"AdamOptimizer": "adam", "MomentumOptimizer": "momentum", "LARSOptimizer": "lars",
+                    "GradientDescentOptimizer": "sgd"}
 
 
 class Graph(object):
@@ -91,20 +114,26 @@ def build_graph(input_batch, model, output_size=256, loss_fn=None, base_learning
   loss_fn = loss_fn or losses.HingeLoss()
   if not isinstance(loss_fn, losses.HingeLoss):
     raise NotImplementedError("only HingeLoss is fused into the B200 training step")
-  if optimizer_class.__name__ != "AdamOptimizer":
-    raise NotImplementedError("optimizer %s: only AdamOptimizer is built (LARS is SURVEY 8f rank 1)" % optimizer_class.__name__)
-  if clip_gradient_norm > 0:
-    raise NotImplementedError("per-variable clip_by_norm is off in the reference's Trainer (train.py:221); pass 0")
-  if regularization_penalty not in (0, 0.0):
-    raise NotImplementedError("regularization_penalty is 0 in the reference's Trainer (train.py:222); pass 0")
+  if optimizer_class.__name__ not in _OPTIMIZER_KINDS:
+    raise NotImplementedError("optimizer %s: built are %s" % (optimizer_class.__name__, sorted(_OPTIMIZER_KINDS)))
   result = model.create_model(input_batch, output_size)
   spec = models.compile_chain(result["l2_norm"])
-  opt = optimizer_class(base_learning_rate)
+  if optimizer_class.__name__ == "MomentumOptimizer":                       # train.py:115-118
+    opt = optimizer_class(base_learning_rate, momentum=0.9, name='Momentum', use_nesterov=True)
+  else:
+    opt = optimizer_class(base_learning_rate)
+  l2_penalties = set(spec["l2_penalty"])
+  if regularization_penalty and len(l2_penalties) != 1:
+    raise NotImplementedError("layers with different l2_penalty")
   engine = TowerEngine(spec["dims"], dtype16={"fp16": 0, "bf16": 1}[dtype16] if isinstance(dtype16, str) else dtype16,
                        seed=seed, bias_init=spec["bias_init"][0], base_lr=base_learning_rate, margin=margin,
                        lr_decay_steps=learning_rate_decay_examples, lr_decay=learning_rate_decay,
-                       beta1=opt.beta1, beta2=opt.beta2, eps=opt.epsilon, alpha=spec["alpha"],
-                       process_group=process_group, init_params=init_params)
+                       beta1=getattr(opt, "beta1", 0.9), beta2=getattr(opt, "beta2", 0.999), eps=getattr(opt, "epsilon", 1e-8),
+                       alpha=spec["alpha"], process_group=process_group, init_params=init_params,
+                       optimizer=_OPTIMIZER_KINDS[optimizer_class.__name__], clip_norm=max(float(clip_gradient_norm), 0.0),
+                       reg_penalty=float(regularization_penalty), l2_penalty=l2_penalties.pop(),
+                       momentum=getattr(opt, "momentum", 0.9), lars_weight_decay=getattr(opt, "weight_decay", 1e-4),
+                       lars_eeta=getattr(opt, "eeta", 1e-3))
   result = dict(result)
   result["__model__"] = model
   _DEFAULT_GRAPH = Graph(engine, input_batch, result, loss_fn)
@@ -273,7 +302,8 @@ def main(args):
     test_cowatches = load_cowatches(FLAGS.train_dir + "/cowatches.test")
     model = find_class_by_name(FLAGS.model, [models])()
     loss_fn = find_class_by_name("HingeLoss", [losses])()
-    optimizer_class = {"AdamOptimizer": AdamOptimizer, "LARSOptimizer": LARSOptimizer}[FLAGS.optimizer]
+    optimizer_class = {"AdamOptimizer": AdamOptimizer, "LARSOptimizer": LARSOptimizer, "MomentumOptimizer": MomentumOptimizer,
+                       "GradientDescentOptimizer": GradientDescentOptimizer}[FLAGS.optimizer]
     trainer = Trainer(pipe=pipe, num_epochs=FLAGS.num_epochs, batch_size=FLAGS.batch_size, model=model, loss_fn=loss_fn,
                       learning_rate=FLAGS.learning_rate, margin=FLAGS.margin, checkpoint_dir=FLAGS.checkpoint_dir,
                       optimizer_class=optimizer_class, config=None, eval_cowatches=eval_cowatches,

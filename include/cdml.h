@@ -98,6 +98,21 @@ int cdml_adam_prepare(cdml_ctx* ctx, int64_t* step_counter, float base_lr, float
                       int staircase, float beta1, float beta2, float* scalars, void* stream);
 int cdml_adam_apply(cdml_ctx* ctx, float* w, float* m, float* v, const float* g, int64_t n, const float* scalars,
                     float beta1, float beta2, float eps, float grad_scale, void* w16, int dtype16, void* stream);
+/* ---- the rest of build_graph's gradient path (train.py:133-146) and its other optimizers.
+ *      g_eff = grad_scale*g + wd_reg*w  (wd_reg = regularization_penalty * l2_penalty of slim.l2_regularizer, weights only);
+ *      per-variable tf.clip_by_norm (train.py:47-64): g_eff *= clip_norm / max(||g_eff||, clip_norm) when clip_norm > 0;
+ *      kind 0 Adam, 1 MomentumOptimizer(momentum, use_nesterov=True) (train.py:115-116),
+ *           2 tf.contrib.opt.LARSOptimizer (train.py:354: trust = eeta*||w|| / (||g|| + wd*||w|| + eps) when both norms > 0,
+ *             g += wd*w, acc = momentum*acc + g, w -= lr*trust*acc), 3 GradientDescent.
+ *      cdml_opt_sumsq writes out2 = {sum g_eff^2, sum w^2} for one variable (deterministic two-stage reduction;
+ *      workspace fp32 [cdml_opt_workspace_floats()]); cdml_opt_apply reads them as `norms` (needed for clipping and
+ *      LARS, NULL otherwise).  scalars = cdml_adam_prepare's output ([0] bias-corrected Adam step size, [1] decayed lr). */
+int64_t cdml_opt_workspace_floats(void);
+int cdml_opt_sumsq(cdml_ctx* ctx, const float* g, const float* w, int64_t n, float grad_scale, float wd_reg,
+                   float* workspace, float* out2, void* stream);
+int cdml_opt_apply(cdml_ctx* ctx, int kind, float* w, float* m, float* v, const float* g, int64_t n, const float* scalars,
+                   const float* norms, float beta1, float beta2, float eps, float grad_scale, float wd_reg, float clip_norm,
+                   float momentum, float lars_weight_decay, float lars_eeta, void* w16, int dtype16, void* stream);
 /* fp32 -> 16-bit cast of a flat buffer (initial shadow weights). */
 int cdml_cast16(cdml_ctx* ctx, const float* in, int64_t n, void* out16, int dtype16, void* stream);
 

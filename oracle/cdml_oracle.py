@@ -233,16 +233,45 @@ def adam_step_tf1(w, m, v, g, lr, t, beta1=0.9, beta2=0.999, eps=1e-8):
   return w, m, v
 
 
-class OracleTrainer:
-  """train.build_graph + Trainer._build_model constants (train.py:74-146, 210-222)
-  for Adam: clip off, reg penalty 0, lr decay 0.96 per 1e6 steps (staircase)."""
+def clip_by_norm(g, clip):
+  """tf.clip_by_norm(t, clip) = t * clip / max(||t||_2, clip), applied per variable (train.py:47-64)."""
+  n = float(np.sqrt(np.sum(np.asarray(g, np.float64) ** 2)))
+  return g * (clip / max(n, clip))
 
-  def __init__(self, params, lr=1e-3, margin=0.8, decay_steps=1000000, decay=0.96, dtype=np.float64):
+
+def momentum_step_tf1(w, acc, g, lr, momentum=0.9, nesterov=True):
+  """tf.train.MomentumOptimizer as build_graph constructs it (train.py:115-116; TF1 ApplyMomentum):
+  acc <- momentum*acc + g ; nesterov: w <- w - lr*g - lr*momentum*acc ; plain: w <- w - lr*acc."""
+  acc = momentum * acc + g
+  w = w - lr * g - lr * momentum * acc if nesterov else w - lr * acc
+  return w, acc
+
+
+def lars_step_tf1(w, acc, g, lr, momentum=0.9, weight_decay=1e-4, eeta=1e-3, epsilon=0.0):
+  """tf.contrib.opt.LARSOptimizer (TF 1.13 defaults; the optimizer of main(), train.py:354), restated from its published
+  compute_lr / _apply_dense:  trust = eeta*|w| / (|g| + wd*|w| + eps) if |w| > 0 and |g| > 0 else 1 ;
+  g <- g + wd*w ; acc <- momentum*acc + g ; w <- w - (lr*trust)*acc   (use_nesterov=False)."""
+  wn = float(np.sqrt(np.sum(np.asarray(w, np.float64) ** 2)))
+  gn = float(np.sqrt(np.sum(np.asarray(g, np.float64) ** 2)))
+  trust = eeta * wn / (gn + weight_decay * wn + epsilon) if (wn > 0 and gn > 0) else 1.0
+  g = g + weight_decay * w
+  acc = momentum * acc + g
+  return w - (lr * trust) * acc, acc
+
+
+class OracleTrainer:
+  """train.build_graph (train.py:74-146): final_loss = regularization_penalty * sum_l l2_penalty*|W_l|^2/2 + hinge loss,
+  compute_gradients, optional per-variable clip_by_norm, apply_gradients with the staircase-decayed learning rate.
+  Defaults = Trainer._build_model's constants (train.py:210-222): Adam, clip off, reg penalty 0, decay 0.96 / 1e6 steps."""
+
+  def __init__(self, params, lr=1e-3, margin=0.8, decay_steps=1000000, decay=0.96, dtype=np.float64, optimizer="adam",
+               clip_norm=0.0, reg_penalty=0.0, l2_penalty=1e-8):
     self.dtype = dtype
     self.params = [(np.asarray(W, dtype).copy(), np.asarray(b, dtype).copy()) for W, b in params]
     self.m = [(np.zeros_like(W), np.zeros_like(b)) for W, b in self.params]
     self.v = [(np.zeros_like(W), np.zeros_like(b)) for W, b in self.params]
     self.lr, self.margin, self.decay_steps, self.decay = lr, margin, decay_steps, decay
+    self.optimizer, self.clip_norm, self.reg_penalty, self.l2_penalty = optimizer, clip_norm, reg_penalty, l2_penalty
     self.global_step = 0
 
   def loss_and_grads(self, x_rows):
@@ -252,13 +281,33 @@ class OracleTrainer:
     dE = hinge_loss_grad(E, self.margin, self.dtype).reshape(-1, E.shape[-1])
     return fwd, loss, tower_backward(fwd, self.params, dE, dtype=self.dtype)
 
+  def reg_loss(self):
+    """slim.l2_regularizer(l2_penalty)(W) = l2_penalty * sum(W^2) / 2, weights only (models.py:28)."""
+    return float(sum(self.l2_penalty * np.sum(np.asarray(W, np.float64) ** 2) / 2 for W, _ in self.params))
+
+  def _apply(self, w, m, v, g, lr, t):
+    if self.clip_norm > 0:
+      g = clip_by_norm(g, self.clip_norm)
+    if self.optimizer == "adam":
+      return adam_step_tf1(w, m, v, g, lr, t)
+    if self.optimizer == "momentum":
+      w2, m2 = momentum_step_tf1(w, m, g, lr)
+      return w2, m2, v
+    if self.optimizer == "lars":
+      w2, m2 = lars_step_tf1(w, m, g, lr)
+      return w2, m2, v
+    if self.optimizer == "sgd":
+      return w - lr * g, m, v
+    raise ValueError(self.optimizer)
+
   def step(self, x_rows):
     fwd, loss, grads = self.loss_and_grads(x_rows)
     lr = exponential_decay(self.lr, self.global_step, self.decay_steps, self.decay)
     t = self.global_step + 1
     for li, ((W, b), (gW, gb)) in enumerate(zip(self.params, grads)):
-      W2, mW, vW = adam_step_tf1(W, self.m[li][0], self.v[li][0], gW, lr, t)
-      b2, mb, vb = adam_step_tf1(b, self.m[li][1], self.v[li][1], gb, lr, t)
+      gW = gW + self.reg_penalty * self.l2_penalty * W          # d(reg_penalty * l2_penalty*|W|^2/2)/dW
+      W2, mW, vW = self._apply(W, self.m[li][0], self.v[li][0], gW, lr, t)
+      b2, mb, vb = self._apply(b, self.m[li][1], self.v[li][1], gb, lr, t)
       self.params[li], self.m[li], self.v[li] = (W2, b2), (mW, mb), (vW, vb)
     self.global_step = t
     return float(loss["hinge_loss"]), fwd, loss

@@ -175,6 +175,69 @@ def test_training_step_gradients_loss_and_adam(cd):
     assert np.abs(b - tr.params[l][1]).max() < 2.5e-2
 
 
+@pytest.mark.parametrize("kind,clip,wd", [("adam", 1.0, 1e-3), ("momentum", 0.0, 0.0), ("momentum", 0.7, 1e-3), ("lars", 0.0, 0.0),
+                                          ("lars", 0.5, 1e-3), ("sgd", 2.0, 0.0)])
+def test_optimizer_kernels_match_oracle_on_identical_gradients(cd, kind, clip, wd):
+  """cdml_opt_sumsq + cdml_opt_apply against the oracle's statements of clip_by_norm / regularizer / Momentum / LARS /
+  Adam, fed the SAME gradients (fp32 kernels vs float64 oracle: 1e-5 relative)."""
+  rng = np.random.RandomState(9)
+  n, B = 100003, 64.0
+  w = rng.standard_normal(n).astype(np.float32) * 0.05
+  kinds = {"adam": cd.ops.OPT_ADAM, "momentum": cd.ops.OPT_MOMENTUM, "lars": cd.ops.OPT_LARS, "sgd": cd.ops.OPT_SGD}
+  wd_t, md, vd = dev_t(cd, w), torch.zeros(n, device=cd.dev), torch.zeros(n, device=cd.dev)
+  w16 = torch.zeros(n, dtype=torch.float16, device=cd.dev)
+  wo, mo, vo = w.astype(np.float64), np.zeros(n), np.zeros(n)
+  step = torch.zeros(1, dtype=torch.int64, device=cd.dev)
+  scalars = torch.zeros(4, device=cd.dev)
+  norms = torch.zeros(2, device=cd.dev)
+  ws = torch.empty(cd.ops.opt_workspace_floats(), device=cd.dev)
+  lr = 0.05 if kind != "lars" else 1.0
+  for t in range(1, 5):
+    gsum = (rng.standard_normal(n) * (3.0 if t % 2 else 0.01)).astype(np.float32) * B      # SUM gradient; 1/B folded in
+    cd.ops.adam_prepare(step, scalars, lr, 2, 0.5, True)                                    # lr halves every 2 steps
+    nz = cd.ops.opt_sumsq(dev_t(cd, gsum), wd_t, norms, ws, grad_scale=1 / B, wd_reg=wd) if (clip > 0 or kind == "lars") else None
+    cd.ops.opt_apply(kinds[kind], wd_t, md, vd, dev_t(cd, gsum), scalars, nz, eps=0.0 if kind == "lars" else 1e-8,
+                     grad_scale=1 / B, wd_reg=wd, clip_norm=clip, w16=w16)
+    g = gsum.astype(np.float64) / B + wd * wo
+    if clip > 0:
+      g = O.clip_by_norm(g, clip)
+    lr_t = O.exponential_decay(lr, t - 1, 2, 0.5)
+    if kind == "adam":
+      wo, mo, vo = O.adam_step_tf1(wo, mo, vo, g, lr_t, t)
+    elif kind == "momentum":
+      wo, mo = O.momentum_step_tf1(wo, mo, g, lr_t)
+    elif kind == "lars":
+      wo, mo = O.lars_step_tf1(wo, mo, g, lr_t)
+    else:
+      wo = wo - lr_t * g
+    got = wd_t.cpu().numpy()
+    assert np.abs(got - wo).max() < 1e-5 * max(1.0, np.abs(wo).max()), (kind, t, np.abs(got - wo).max())
+  assert np.abs(w16.float().cpu().numpy() - got).max() < 1e-3            # 16-bit shadow weights follow
+
+
+@pytest.mark.parametrize("optimizer_name,lr", [("LARSOptimizer", 1.0), ("MomentumOptimizer", 0.05)])
+def test_build_graph_with_reference_defaults_clip_and_regularizer(cd, optimizer_name, lr):
+  """build_graph with ITS OWN defaults (clip_gradient_norm=1.0, regularization_penalty=1; train.py:83-84) and the
+  optimizer of main() (LARS, train.py:354) tracks the oracle: loss curve within 1e-3, same weight travel."""
+  G, F, B = 1500, 1500, 256
+  feats = O.synth_features(G, F, 0)
+  params = O.init_tower([F, 5000, 256], seed=2)
+  g = cd.train.build_graph(cd.models.placeholder(F), cd.models.VNet(), base_learning_rate=lr, margin=0.8,
+                           optimizer_class=getattr(cd.train, optimizer_name), init_params=params)
+  eng = g.engine
+  kind = {"LARSOptimizer": "lars", "MomentumOptimizer": "momentum"}[optimizer_name]
+  tr = O.OracleTrainer(params, lr=lr, margin=0.8, decay_steps=100000, optimizer=kind, clip_norm=1.0, reg_penalty=1.0, l2_penalty=1e-8)
+  table16 = eng.prepare_table(dev_t(cd, feats))
+  lg, lc = [], []
+  for t in range(6):
+    trip = O.synth_triplets(B, G, 70 + t)
+    lg.append(float(eng.train_step_indices(table16, dev_t(cd, trip))[0].item()))
+    lc.append(tr.step(O.flatten_triplets(O.gather_rows(feats, trip)))[0])
+  assert np.max(np.abs(np.array(lg) / np.array(lc) - 1)) < 1e-3, (lg, lc)
+  for l, (W, b) in enumerate(eng.get_params()):
+    assert _grad_rel(W - params[l][0], tr.params[l][0] - params[l][0]) < 0.2, l    # 16-bit gradient noise (1-2 %), compounded by momentum
+
+
 def test_cuda_graph_step_equals_eager_step(cd):
   G, F, B = 1500, 1500, 256
   dims = [F, 5000, 256]

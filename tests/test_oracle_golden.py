@@ -115,6 +115,45 @@ def test_tf1_adam_first_step_closed_form_and_schedule():
   assert abs(O.exponential_decay(0.01, 2500000, 1000000, 0.96) - 0.01 * 0.96 ** 2) < 1e-15
 
 
+def test_clip_momentum_lars_and_regularizer_statements():
+  """The rest of build_graph's gradient path (train.py:47-64, :115-118, :133-146, :354), pinned to closed forms and to
+  torch's independent SGD-with-Nesterov implementation (TF and torch share that formulation)."""
+  rng = np.random.RandomState(3)
+  w, g = rng.standard_normal((7, 5)), rng.standard_normal((7, 5))
+  # clip_by_norm: untouched below the threshold, rescaled to exactly the threshold above it
+  assert np.array_equal(O.clip_by_norm(g, 100.0), g)
+  assert abs(np.linalg.norm(O.clip_by_norm(g, 1.0)) - 1.0) < 1e-12
+  # Nesterov momentum vs torch.optim.SGD(momentum=0.9, nesterov=True)
+  wt = torch.tensor(w.copy(), requires_grad=True)
+  opt = torch.optim.SGD([wt], lr=0.1, momentum=0.9, nesterov=True)
+  wn, acc = w.copy(), np.zeros_like(w)
+  for i in range(4):
+    wt.grad = torch.tensor(g * (i + 1))
+    opt.step()
+    wn, acc = O.momentum_step_tf1(wn, acc, g * (i + 1), 0.1)
+  assert np.abs(wn - wt.detach().numpy()).max() < 1e-12
+  # LARS first step (acc = 0): w1 = w - lr * eeta*|w|/(|g| + wd*|w|) * (g + wd*w); zero gradient -> trust ratio 1
+  w1, acc1 = O.lars_step_tf1(w, np.zeros_like(w), g, lr=1.0)
+  wn_, gn_ = np.linalg.norm(w), np.linalg.norm(g)
+  assert np.allclose(w1, w - 1e-3 * wn_ / (gn_ + 1e-4 * wn_) * (g + 1e-4 * w), rtol=1e-12)
+  w2, _ = O.lars_step_tf1(w, np.zeros_like(w), np.zeros_like(w), lr=0.5)
+  assert np.allclose(w2, w - 0.5 * 1e-4 * w)
+  # regularizer: d(reg_penalty * reg_loss)/dW by finite differences, and its use in step()
+  params = O.init_tower([6, 8, 4], seed=2, dtype=np.float64)
+  tr = O.OracleTrainer(params, optimizer="sgd", lr=0.5, reg_penalty=3.0, l2_penalty=1e-2)
+  W0 = tr.params[0][0]
+  base = tr.reg_loss()
+  W0[1, 2] += 1e-6
+  fd = (tr.reg_loss() - base) / 1e-6
+  W0[1, 2] -= 1e-6
+  assert abs(fd - 1e-2 * W0[1, 2]) < 1e-7
+  x = np.random.RandomState(5).random_sample((12, 6))
+  grads = tr.loss_and_grads(x)[2]
+  want = W0 - 0.5 * (grads[0][0] + 3.0 * 1e-2 * W0)
+  tr.step(x)
+  assert np.allclose(tr.params[0][0], want, rtol=1e-12)
+
+
 def test_flat_knn_against_independent_brute_force_and_merge():
   rng = np.random.RandomState(4)
   X = rng.standard_normal((600, 32)).astype(np.float32)
