@@ -476,3 +476,75 @@ def test_semihard_mining_matches_oracle_up_to_fp16_selection_noise(cd):
   t16 = eng.prepare_table(dev_t(cd, feats))
   s = eng.train_step_indices(t16, dev_t(cd, trip), mine=True).cpu().numpy()
   assert np.isfinite(s).all() and s[3] <= B
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes, through size-independent properties (the oracle only spot-checks a few rows there)
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_size_knn_1m_index_properties_and_oracle_spot_check(cd):
+  """configs[3]: N = 1M x 256, top-100.  Self is the first neighbour at distance ~0, rows ascending, 0 <= D <= 4,
+  ids unique and in range; 24 random queries are compared with the float32 oracle over the whole index."""
+  N, d, nq, k = 1000000, 256, 16384, 100
+  gen = torch.Generator(device=cd.dev)
+  gen.manual_seed(4)
+  X = torch.nn.functional.normalize(torch.randn((N, d), generator=gen, device=cd.dev), dim=1)
+  index = cd.ops.FlatIndex(X, "L2")
+  qrows = torch.randperm(N, generator=gen, device=cd.dev)[:nq]
+  D, I = index.search(X[qrows].contiguous(), k)
+  st = index.last_stats()
+  assert st["fallback_queries"] == 0
+  assert bool((I[:, 0] == qrows).all().item())
+  assert float(D[:, 0].abs().max().item()) < 1e-5
+  assert bool((D[:, 1:] >= D[:, :-1]).all().item())
+  assert float(D.min().item()) >= 0.0 and float(D.max().item()) <= 4.0
+  assert int(I.min().item()) >= 0 and int(I.max().item()) < N
+  srt = torch.sort(I, dim=1).values
+  assert bool((srt[:, 1:] != srt[:, :-1]).all().item())
+  Xh = X.cpu().numpy()
+  pick = np.random.RandomState(0).choice(nq, 24, replace=False)
+  Qh = Xh[qrows.cpu().numpy()[pick]]
+  Dw, Iw = O.flat_knn(Xh, Qh, k=k, l2_norm=False)
+  assert_knn_matches(D[pick].cpu().numpy(), I[pick].cpu().numpy(), Dw, Iw, "L2", Xh, Qh)
+  index.close()
+
+
+def test_full_size_training_step_batch_65536_properties(cd):
+  """configs[1]: batch 65536 with in-batch mining on a 200k-guid table.  Gather bit-exact against torch indexing, unit-norm
+  embeddings, loss consistent with its own per-triplet outputs, mined negatives valid (guid not in {a,p}, farther than
+  the positive), every rank-free invariant of the step."""
+  G, F, B = 200000, 1500, 65536
+  dims = [F, 5000, 256]
+  eng = cd.engine.TowerEngine(dims, device=cd.dev, base_lr=1e-3, margin=0.8, seed=2)
+  gen = torch.Generator(device=cd.dev)
+  gen.manual_seed(7)
+  table16 = torch.empty((G, eng.F_pad), dtype=torch.float16, device=cd.dev)
+  for s in range(0, G, 50000):
+    eng.prepare_table(torch.rand((50000, F), generator=gen, device=cd.dev), out=table16[s:s + 50000])
+  idx = torch.randint(0, G, (B, 3), generator=gen, device=cd.dev)
+  idx[:, 1] = (idx[:, 0] + 1 + idx[:, 1] % (G - 1)) % G
+  idx[:, 2] = (idx[:, 1] + 1 + idx[:, 2] % (G - 2)) % G
+  clash = idx[:, 2] == idx[:, 0]
+  idx[:, 2][clash] = (idx[:, 2][clash] + 1) % G
+  x16 = cd.ops.gather_rows(table16, idx)
+  assert torch.equal(x16, table16[idx.reshape(-1)])                                     # bit-exact row gather at full size
+  w0 = eng.w.clone()
+  stats = eng.train_step_rows(x16, B, mine=True, guid=idx)
+  buf = eng._buffers(3 * B, True)
+  e = buf["e"]
+  assert float((e.norm(dim=1) - 1).abs().max().item()) < 1e-3
+  s = stats.cpu().numpy()
+  pos, neg, hin = (buf["loss"][k_] for k_ in ("pos_dist", "neg_dist", "hinge_dist"))
+  assert abs(s[0] - float(hin.double().mean().item())) < 1e-5 and abs(s[1] - float(pos.double().mean().item())) < 1e-5
+  assert bool(torch.allclose(hin, torch.clamp(pos - neg + 0.8, min=0), atol=1e-6))
+  assert 0.0 <= s[0] <= 0.8 + 4.0
+  # mining: recompute with the ops-level call on the same embeddings
+  e16 = eng._ws[("e16", 3 * B)]
+  neg_row, d_an = cd.ops.mine_semihard(e16, e, idx, B, 0.8, want_dist=True)
+  flat = idx.reshape(-1)
+  g_neg = flat[neg_row.long()]
+  assert bool(((g_neg != idx[:, 0]) & (g_neg != idx[:, 1])).all().item())
+  assert bool((neg_row.long() % 3 != 0).all().item())                                    # candidates are positives / negatives, never anchors
+  mined = neg_row.long() != 3 * torch.arange(B, device=cd.dev) + 2
+  assert float(mined.float().mean().item()) > 0.9
+  assert bool((d_an[mined] > pos[mined] - 2e-2).all().item())                            # d(a,n) > d(a,p) up to the fp16 selection noise
+  assert bool(torch.isfinite(eng.w).all().item()) and float((eng.w - w0).abs().max().item()) <= 1.01e-3   # one Adam step
