@@ -24,8 +24,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DIMS = [1500, 5000, 256]
-FLOP_PER_TRIPLET = 3 * (4 * DIMS[0] * DIMS[1] + 6 * DIMS[1] * DIMS[2])      # 113.04 MFLOP fwd+bwd
+TOWERS = {"vnet": ([1500, 5000, 256], "fp16"),                      # configs[1]: the default models.py tower
+          "wide": ([2048, 2048, 2048, 2048, 256], "bf16")}          # configs[2]: 2048-d input, 3 x 2048 hidden, bf16
+DIMS = TOWERS["vnet"][0]
+
+
+def flop_per_triplet(dims):
+  """3 rows x (forward 2*in*out + weight gradient 2*in*out per layer, + data gradient 2*in*out for every layer but the
+  first).  VNet: 3*(4FH + 6HD) = 113.04 MFLOP; wide tower: 210.76 MFLOP."""
+  return 3 * sum((4 if l == 0 else 6) * dims[l] * dims[l + 1] for l in range(len(dims) - 1))
+
+
+FLOP_PER_TRIPLET = flop_per_triplet(DIMS)
 
 
 def peaks():
@@ -130,9 +140,11 @@ def run_reference(args):
 
 
 def workload_config(args, mine):
-  return {"workload": "configs[1]: VNet 1500-5000-256, batch %d triplets/GPU, in-batch semi-hard mining %s, "
-                      "feature table %d guids resident in HBM" % (args.batch, "on" if mine else "off", args.guids),
-          "tower": DIMS, "batch_per_gpu": args.batch, "guids": args.guids, "mining": bool(mine), "margin": 0.8,
+  dims, dt = TOWERS[getattr(args, "tower", "vnet")]
+  return {"workload": "configs[%d]: tower %s (%s operands), batch %d triplets/GPU, in-batch semi-hard mining %s, "
+                      "feature table %d guids resident in HBM" % (1 if dims is DIMS else 2, "-".join(map(str, dims)), dt,
+                                                                  args.batch, "on" if mine else "off", args.guids),
+          "tower": dims, "batch_per_gpu": args.batch, "guids": args.guids, "mining": bool(mine), "margin": 0.8,
           "optimizer": "adam(tf1) lr=1e-3", "parallelism": "dp%d" % args.gpus,
           "cuda_graph": bool(not getattr(args, "no_graph", False)),
           "l2_policy": "inputs_exceed_l2 (table+activations per step >> 126 MB)"}
@@ -161,6 +173,7 @@ def main():
   ap.add_argument("--no-knn", action="store_true")
   ap.add_argument("--no-cpu", action="store_true")
   ap.add_argument("--no-graph", action="store_true")
+  ap.add_argument("--tower", default="vnet", choices=sorted(TOWERS), help="vnet = configs[1] (default), wide = configs[2]")
   ap.add_argument("--knn-n", type=int, default=1000000)
   ap.add_argument("--knn-queries", type=int, default=65536)
   args = ap.parse_args()
@@ -184,13 +197,16 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     pg = dist.group.WORLD
   mine = not args.no_mine
-  B, G, F = args.batch, args.guids, DIMS[0]
+  dims, dt16 = TOWERS[args.tower]
+  flop_triplet = flop_per_triplet(dims)
+  B, G, F = args.batch, args.guids, dims[0]
 
   # ---- synthetic inputs (seeded; uniform [0,1) features like imitation_data.gen_features) generated on the device
   gen = torch.Generator(device=dev)
   gen.manual_seed(1234)
-  eng = engine.TowerEngine(DIMS, device=dev, base_lr=1e-3, margin=0.8, seed=2, process_group=pg)
-  table16 = torch.empty((G, eng.F_pad), dtype=torch.float16, device=dev)
+  eng = engine.TowerEngine(dims, device=dev, base_lr=1e-3, margin=0.8, seed=2, process_group=pg,
+                           dtype16=_lib.BF16 if dt16 == "bf16" else _lib.F16)
+  table16 = torch.empty((G, eng.F_pad), dtype=eng.t16, device=dev)
   for s in range(0, G, 65536):                                            # normalise+cast in slabs (K2 folded, one-off)
     rows = min(65536, G - s)
     slab = torch.rand((rows, F), generator=gen, device=dev, dtype=torch.float32)
@@ -325,16 +341,16 @@ def main():
               "traffic": traffic, "traffic_source": traffic_src,
               "algorithmic_bytes": top["bytes"],
               "peak_source": "%s bf16_tflops_sustained (kernel timed inside the step)" % pk["source"],
-              "step_tensor_frac": (FLOP_PER_TRIPLET * value / world / 1e12) / pk["bf16_tflops_sustained"],
+              "step_tensor_frac": (flop_triplet * value / world / 1e12) / pk["bf16_tflops_sustained"],
               "gemms": [{k: v for k, v in g.items() if k != "key"} for g in kern]}
 
   line = {"metric": "train_triplets_per_sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": args.steps,
           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-          "vs_baseline": None, "dtype": "fp16 operands / fp32 accumulate (tcgen05 kind::f16), fp32 master weights",
+          "vs_baseline": None, "dtype": "%s operands / fp32 accumulate (tcgen05 kind::f16), fp32 master weights" % dt16,
           "data": "synthetic", "config": workload_config(args, mine),
           "e2e": {"value": e2e_value, "unit": "triplets/s", "h2d_bytes_per_step": B * 3 * 8, "d2h_bytes_per_step": 16},
           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "loss_last_step": loss_last,
-          "tflops_per_gpu": FLOP_PER_TRIPLET * value / world / 1e12}
+          "tflops_per_gpu": flop_triplet * value / world / 1e12}
 
   # ---- second BASELINE metric: exact KNN top-100 queries/sec on a 1M-item index.  N>1: the index is row-sharded over
   # the ranks (strong scaling: same 1M rows, same queries), per-shard top-k all-gathered over NCCL and merged on the GPU.

@@ -490,72 +490,170 @@ knn_refine_kernel(const float* __restrict__ Q, int64_t ldq, int d, const float* 
   }
 }
 
-// ---- exact fallback (rare): one query against every row in fp32 ----
-__global__ void __launch_bounds__(256)
-knn_exact_keys_kernel(const float* __restrict__ qv, int d, float qn, const float* __restrict__ X, int64_t N, int64_t ldx,
-                      const float* __restrict__ xss, int metric, unsigned long long* __restrict__ keys) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + warp; r < N; r += static_cast<int64_t>(gridDim.x) * 8) {
-    const float* xv = X + r * ldx;
-    float dot = 0.f;
-    for (int j = lane; j < d; j += 32) dot = fmaf(qv[j], xv[j], dot);
+// ---- exact fallback: queries whose candidate list overflowed (dense near-tie bands, e.g. tight clusters) ----
+// One CTA takes up to kFbQueries such queries and streams the whole index once in fp32 (every row fetch is shared by
+// the CTA's queries); per query a shared-memory buffer of 2*kcap (distance,id) keys collects the rows that beat the
+// running k-th best and is compacted (bitonic sort, keep k) whenever it may overflow in the next round.  All overflow
+// queries of a search run in ONE launch with no host round trips (the former per-query scan + select took ~2 ms each).
+constexpr int kFbQueries = 8;
+constexpr int kFbThreads = 256;
+constexpr int kFbRound = (kFbThreads / 32) * 32;   // rows examined between two block barriers
+
+__global__ void __launch_bounds__(kFbThreads)
+knn_exact_batch_kernel(const int32_t* __restrict__ qlist, int nlist, const float* __restrict__ Q, int64_t ldq, int d,
+                       const float* __restrict__ X, int64_t N, int64_t ldx, const float* __restrict__ xss, int metric,
+                       int k, int kcap, int64_t id_offset, float* __restrict__ D, int64_t* __restrict__ I, int compact_out) {
+  // gridDim.y row splits: this CTA scans rows [row_lo, row_hi); with compact_out the lists go to [split, list slot, k]
+  // (merged afterwards by knn_merge_kernel), otherwise straight to the queries' rows of D / I
+  extern __shared__ unsigned long long fb_smem[];
+  unsigned long long* buf = fb_smem;                                   // [kFbQueries][2*kcap]
+  float* qs = reinterpret_cast<float*>(buf + kFbQueries * 2 * kcap);   // [kFbQueries][d]
+  __shared__ uint32_t thr_key[kFbQueries];                             // key of the running k-th best distance
+  __shared__ int cnt[kFbQueries];
+  __shared__ float qnorm[kFbQueries];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * kFbQueries;
+  const int nqs = min(kFbQueries, nlist - q0);
+  const int cap = 2 * kcap;
+  for (int i = tid; i < kFbQueries * d; i += kFbThreads) {
+    const int j = i / d;
+    qs[i] = j < nqs ? Q[static_cast<int64_t>(qlist[q0 + j]) * ldq + (i - j * d)] : 0.f;
+  }
+  if (tid < kFbQueries) thr_key[tid] = 0xffffffffu, cnt[tid] = 0;
+  __syncthreads();
+  if (warp < kFbQueries) {
+    float a = 0.f;
+    for (int c = lane; c < d; c += 32) a = fmaf(qs[warp * d + c], qs[warp * d + c], a);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    if (lane == 0) {
-      const float key = metric == 0 ? fmaxf(qn + xss[r] - 2.f * dot, 0.f) : -dot;
-      keys[r] = (static_cast<unsigned long long>(f2key(key)) << 32) | static_cast<uint32_t>(r);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) qnorm[warp] = a;
+  }
+  __syncthreads();
+  auto compact = [&](int j) {   // block-wide: keep the k smallest keys of query j's buffer
+    const int n = min(cnt[j], cap);
+    unsigned long long* b = buf + static_cast<size_t>(j) * cap;
+    int P = 2;
+    while (P < n) P <<= 1;
+    for (int i = n + tid; i < P; i += kFbThreads) b[i] = ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = tid; t < (P >> 1); t += kFbThreads) {
+          const int lo = ((t / stride) * (stride << 1)) + (t % stride), hi = lo + stride;
+          const bool up = (lo & size) == 0;
+          const unsigned long long x = b[lo], y = b[hi];
+          if ((x > y) == up) b[lo] = y, b[hi] = x;
+        }
+        __syncthreads();
+      }
+    if (tid == 0) {
+      const int keep = min(n, k);
+      cnt[j] = keep;
+      if (keep == k) thr_key[j] = static_cast<uint32_t>(b[k - 1] >> 32);
     }
+    __syncthreads();
+  };
+  const int64_t row_lo = N * blockIdx.y / gridDim.y, row_hi = N * (blockIdx.y + 1) / gridDim.y;
+  float qreg[kFbQueries][8];   // this lane's columns (lane + 32p) of the CTA's queries, d <= 256
+#pragma unroll
+  for (int j = 0; j < kFbQueries; ++j)
+#pragma unroll
+    for (int p = 0; p < 8; ++p) qreg[j][p] = (d <= 256 && lane + 32 * p < d) ? qs[j * d + lane + 32 * p] : 0.f;
+  for (int64_t r0 = row_lo; r0 < row_hi; r0 += kFbRound) {
+    // each warp: 32 consecutive rows of the round, lane <-> columns.  d <= 256: the queries' pieces live in registers
+    // (qreg, loaded once) and four rows are fetched together -- the scan is bound by row-fetch latency otherwise.
+    auto offer = [&](int64_t r, const float (&dot)[kFbQueries]) {
+      if (lane < nqs) {
+        float dsel = dot[0];
+#pragma unroll
+        for (int j = 1; j < kFbQueries; ++j) dsel = lane == j ? dot[j] : dsel;
+        const float key = metric == 0 ? fmaxf(qnorm[lane] + xss[r] - 2.f * dsel, 0.f) : -dsel;
+        const uint32_t kk = f2key(key);
+        if (kk <= thr_key[lane]) {   // ties with the running k-th best stay candidates: (distance,id) decides later
+          const int pos = atomicAdd(&cnt[lane], 1);
+          if (pos < cap) buf[static_cast<size_t>(lane) * cap + pos] = (static_cast<unsigned long long>(kk) << 32) | static_cast<uint32_t>(r);
+        }
+      }
+    };
+    if (d <= 256) {
+      for (int rr = 0; rr < 32; rr += 4) {
+        const int64_t rb = r0 + warp * 32 + rr;
+        if (rb >= row_hi) break;
+        float x[4][8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const float* xv = X + min(rb + a, row_hi - 1) * ldx;
+#pragma unroll
+          for (int p = 0; p < 8; ++p) x[a][p] = lane + 32 * p < d ? __ldg(xv + lane + 32 * p) : 0.f;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          float dot[kFbQueries];
+#pragma unroll
+          for (int j = 0; j < kFbQueries; ++j) {
+            float t = 0.f;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) t = fmaf(x[a][p], qreg[j][p], t);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            dot[j] = t;
+          }
+          if (rb + a < row_hi) offer(rb + a, dot);
+        }
+      }
+    } else {
+      for (int rr = 0; rr < 32; ++rr) {
+        const int64_t r = r0 + warp * 32 + rr;
+        if (r >= row_hi) break;
+        const float* xv = X + r * ldx;
+        float dot[kFbQueries];
+#pragma unroll
+        for (int j = 0; j < kFbQueries; ++j) dot[j] = 0.f;
+        for (int c = lane; c < d; c += 32) {
+          const float x = __ldg(xv + c);
+#pragma unroll
+          for (int j = 0; j < kFbQueries; ++j) dot[j] = fmaf(x, qs[j * d + c], dot[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kFbQueries; ++j) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) dot[j] += __shfl_xor_sync(0xffffffffu, dot[j], o);
+        }
+        offer(r, dot);
+      }
+    }
+    __syncthreads();
+    unsigned int need = 0u;   // latched by every thread BEFORE anyone appends again: the decision must be block-uniform
+    for (int j = 0; j < nqs; ++j) need |= (cnt[j] + kFbRound > cap ? 1u : 0u) << j;
+    __syncthreads();
+    for (int j = 0; j < nqs; ++j)
+      if ((need >> j) & 1u) compact(j);
+  }
+  for (int j = 0; j < nqs; ++j) {
+    compact(j);
+    const int64_t q = compact_out ? static_cast<int64_t>(blockIdx.y) * nlist + q0 + j : qlist[q0 + j];
+    const int have = cnt[j];
+    for (int i = tid; i < k; i += kFbThreads) {
+      if (i < have) {
+        const unsigned long long e = buf[static_cast<size_t>(j) * cap + i];
+        const float key = key2f(static_cast<uint32_t>(e >> 32));
+        D[q * k + i] = metric == 0 ? key : -key;
+        I[q * k + i] = static_cast<int64_t>(static_cast<uint32_t>(e)) + id_offset;
+      } else {
+        D[q * k + i] = metric == 0 ? pos_inf() : neg_inf();
+        I[q * k + i] = -1;
+      }
+    }
+    __syncthreads();
   }
 }
 
-__global__ void __launch_bounds__(1024)
-knn_exact_select_kernel(const unsigned long long* __restrict__ keys, int64_t N, int k, int metric, int64_t id_offset,
-                        float* __restrict__ D, int64_t* __restrict__ I) {
-  __shared__ int sh[32];
-  __shared__ unsigned long long best[1024];
-  __shared__ int nb;
-  const int tid = threadIdx.x;
-  const int kk = static_cast<int>(N < k ? N : k);
-  // T = kk-th smallest key: largest T with fewer than kk keys strictly below it
-  unsigned long long T = 0;
-  for (int bit = 63; bit >= 0; --bit) {
-    const unsigned long long cand = T | (1ull << bit);
-    int c = 0;
-    for (int64_t i = tid; i < N; i += 1024) c += keys[i] < cand ? 1 : 0;
-    if (block_sum(c, sh) < kk) T = cand;
-  }
-  if (tid == 0) nb = 0;
-  __syncthreads();
-  for (int64_t i = tid; i < N; i += 1024)
-    if (keys[i] <= T) {
-      const int pos = atomicAdd(&nb, 1);
-      if (pos < 1024) best[pos] = keys[i];
-    }
-  __syncthreads();
-  for (int i = nb + tid; i < 1024; i += 1024) best[i] = ~0ull;
-  __syncthreads();
-  for (int size = 2; size <= 1024; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (tid < 512) {
-        const int lo = ((tid / stride) * (stride << 1)) + (tid % stride);
-        const int hi = lo + stride;
-        const bool up = (lo & size) == 0;
-        const unsigned long long a = best[lo], b = best[hi];
-        if ((a > b) == up) best[lo] = b, best[hi] = a;
-      }
-      __syncthreads();
-    }
-  }
-  for (int i = tid; i < k; i += 1024) {
-    if (i < kk) {
-      const float key = key2f(static_cast<uint32_t>(best[i] >> 32));
-      D[i] = metric == 0 ? key : -key;
-      I[i] = static_cast<int64_t>(static_cast<uint32_t>(best[i])) + id_offset;
-    } else {
-      D[i] = metric == 0 ? pos_inf() : neg_inf();
-      I[i] = -1;
-    }
-  }
+__global__ void knn_scatter_rows_kernel(const int32_t* __restrict__ qlist, int nlist, int k, const float* __restrict__ Dm,
+                                        const int64_t* __restrict__ Im, float* __restrict__ D, int64_t* __restrict__ I) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(nlist) * k) return;
+  const int64_t q = qlist[i / k];
+  D[q * k + i % k] = Dm[i], I[q * k + i % k] = Im[i];
 }
 
 // ---- sharded merge: [G, nq, k] -> top-k by (distance, id) ----
@@ -645,7 +743,6 @@ struct cdml_index {
   uint4* log;          // [num_sms * 8, log_cap] warp-private candidate logs of pass B
   int32_t* log_count;  // [num_sms * 8] + 1 overflow word
   unsigned int log_cap;
-  unsigned long long* fb_keys;
   // pinned host mirrors of the per-query counters (one stream synchronisation per search, not per chunk)
   int32_t *h_cnt, *h_ovf, *h_logovf;
   float* h_qss;
@@ -658,7 +755,7 @@ static void index_free(cdml_index* ix) {
   if (ix == nullptr) return;
   cudaFree(ix->x32), cudaFree(ix->xss), cudaFree(ix->h), cudaFree(ix->x16), cudaFree(ix->xs16), cudaFree(ix->hs);
   cudaFree(ix->q16), cudaFree(ix->qss), cudaFree(ix->gmax), cudaFree(ix->thr), cudaFree(ix->cand_val);
-  cudaFree(ix->cand_idx), cudaFree(ix->cnt), cudaFree(ix->overflow), cudaFree(ix->fb_keys);
+  cudaFree(ix->cand_idx), cudaFree(ix->cnt), cudaFree(ix->overflow);
   cudaFree(ix->log), cudaFree(ix->log_count);
   cudaFreeHost(ix->h_cnt), cudaFreeHost(ix->h_ovf), cudaFreeHost(ix->h_qss), cudaFreeHost(ix->h_logovf);
   delete ix;
@@ -864,20 +961,52 @@ static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, in
   }
   if (bounds_only) return 0;
   CDML_CHECK_CUDA(cudaStreamSynchronize(st));
-  // rare: queries whose candidate list (or whose chunk's warp log) overflowed are redone exactly in fp32
+  // queries whose candidate list (or whose chunk's warp log) overflowed are redone exactly in fp32, all in one launch
+  std::vector<int32_t> redo;
   for (int64_t i = 0; i < nq; ++i) {
     ix->stats[0] += ix->N <= kKeepCap ? 0 : ix->h_cnt[i];
-    if (!ix->h_ovf[i] && !ix->h_logovf[i / chunk]) continue;   // a full warp log may have dropped nominees of any query
-    ix->stats[1] += 1;
-    if (ix->fb_keys == nullptr && dev_alloc(&ix->fb_keys, ix->N)) return -2;
-    const int g2 = static_cast<int>(std::min<int64_t>((ix->N + 7) / 8, ctx->num_sms * 8));
-    knn_exact_keys_kernel<<<g2, 256, 0, st>>>(Q + i * ldq, d, ix->h_qss[i], ix->x32, ix->N, d, ix->xss, ix->metric, ix->fb_keys);
-    knn_exact_select_kernel<<<1, 1024, 0, st>>>(ix->fb_keys, ix->N, k, ix->metric, id_offset, D + i * k, I + i * k);
+    if (ix->h_ovf[i] || ix->h_logovf[i / chunk]) redo.push_back(static_cast<int32_t>(i));   // a full warp log may have dropped nominees of any query
+  }
+  ix->stats[1] = static_cast<int64_t>(redo.size());
+  if (!redo.empty()) {
+    int kcap = 64;
+    while (kcap < k) kcap <<= 1;
+    kcap = std::max(kcap, kFbRound);      // a round may append up to kFbRound rows per query before the next compaction
+    const size_t smem = static_cast<size_t>(kFbQueries) * 2 * kcap * sizeof(unsigned long long) + static_cast<size_t>(kFbQueries) * d * sizeof(float);
+    CDML_REQUIRE(smem <= 200 * 1024, "cdml_knn_search: exact fallback needs %zu bytes of shared memory (k=%d, d=%d)", smem, k, d);
+    CDML_CHECK_CUDA(cudaFuncSetAttribute(knn_exact_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int32_t* dlist = nullptr;
+    if (dev_alloc(&dlist, redo.size())) return -2;
+    CDML_CHECK_CUDA(cudaMemcpyAsync(dlist, redo.data(), sizeof(int32_t) * redo.size(), cudaMemcpyHostToDevice, st));
+    const int nlist = static_cast<int>(redo.size());
+    const int blocks = (nlist + kFbQueries - 1) / kFbQueries;
+    // few overflow queries: split the index rows over several CTAs per query group so that the whole GPU scans
+    int splits = std::max(1, std::min(16, (2 * ctx->num_sms + blocks - 1) / blocks));
+    if (ix->N < 64 * 1024) splits = 1;
+    float* Dp = nullptr;
+    int64_t* Ip = nullptr;
+    if (splits > 1 && (dev_alloc(&Dp, static_cast<size_t>(splits + 1) * nlist * k) || dev_alloc(&Ip, static_cast<size_t>(splits + 1) * nlist * k))) {
+      cudaFree(dlist), cudaFree(Dp);
+      return -2;
+    }
+    knn_exact_batch_kernel<<<dim3(blocks, splits), kFbThreads, smem, st>>>(dlist, nlist, Q, ldq, d, ix->x32, ix->N, d, ix->xss,
+                                                                          ix->metric, k, kcap, id_offset, splits > 1 ? Dp : D,
+                                                                          splits > 1 ? Ip : I, splits > 1 ? 1 : 0);
     CDML_CHECK_CUDA(cudaGetLastError());
+    if (splits > 1) {   // per-split lists -> top-k (same merge kernel as the sharded index) -> the queries' rows
+      float* Dm = Dp + static_cast<size_t>(splits) * nlist * k;
+      int64_t* Im = Ip + static_cast<size_t>(splits) * nlist * k;
+      int rcm = cdml_knn_merge(ctx, Dp, Ip, splits, nlist, k, ix->metric, Dm, Im, stream);
+      if (rcm) { cudaFree(dlist), cudaFree(Dp), cudaFree(Ip); return rcm; }
+      const int64_t tot = static_cast<int64_t>(nlist) * k;
+      knn_scatter_rows_kernel<<<static_cast<int>((tot + 255) / 256), 256, 0, st>>>(dlist, nlist, k, Dm, Im, D, I);
+      CDML_CHECK_CUDA(cudaGetLastError());
+    }
+    CDML_CHECK_CUDA(cudaStreamSynchronize(st));   // `redo` (pageable) and the scratch buffers must outlive the kernels
+    cudaFree(dlist), cudaFree(Dp), cudaFree(Ip);
   }
   return 0;
 }
-
 
 int cdml_knn_search(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k, float* D,
                     int64_t* I, int64_t id_offset, void* stream) {

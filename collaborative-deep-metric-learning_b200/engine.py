@@ -61,7 +61,7 @@ class TowerEngine:
     self.pg = process_group
     self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
     self.F = self.dims[0]
-    self.F_pad = _pad64(self.F)
+    self.F_pad = _pad64(self.F + 1)     # always one spare column: it carries the ones of [x | 1] (bias gradient row)
     self.fused_bias_grad = True    # bias gradients as an extra row of the weight-gradient GEMMs (no colsum kernels)
     self._ones_checked = {}
 
@@ -142,13 +142,13 @@ class TowerEngine:
       return buf
     dev, t16 = self.device, self.t16
     D = self.dims[-1]
-    def mat16(cols):
-      return torch.empty((R, _pad64(cols)), dtype=t16, device=dev)[:, :cols]
+    def mat16(cols, spare=0):
+      return torch.empty((R, _pad64(cols + spare)), dtype=t16, device=dev)[:, :cols]
 
     def act16(cols):
       # hidden activations feed the next layer's weight-gradient GEMM as [h | 1]: the spare pitch column `cols` holds 1.0
       # (written once; the forward epilogue only writes columns < cols, the forward GEMM of the next layer reads K = cols)
-      m = mat16(cols)
+      m = mat16(cols, 1 if train else 0)
       if train and self._bias_row_ok(cols, m.stride(0)):
         ops.fill_column16(m, cols, 1.0)
       return m

@@ -1,0 +1,114 @@
+"""Local, HDFS-free composition of the reference's serving cycle (cdml_run.sh:73-150; BASELINE configs[4]) through the
+public API: train (train.Trainer on *.train index triplets) -> embed every guid (predict.Prediction.run_features) ->
+exact top-k KNN (faiss_knn.calc_knn semantics, device resident) -> knn_split* files (faiss_knn.write_knn).
+
+  python tools/cycle.py [--guids G] [--triplets T] [--batch B] [--knn-k K] [--write-rows R] [--out DIR]
+
+Defaults are a 1/10-scale cycle (1M guids, 5M triplets, 1M x 1M KNN) that finishes in about a minute on one B200;
+--guids 10000000 --triplets 50000000 is configs[4] itself.  Features and cowatch pairs are synthetic and generated on
+the device (a 10M x 1500 float32 feature file would be 60 GB of host I/O that has nothing to do with the path)."""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import cdml_b200  # noqa: F401
+from cdml_b200 import engine, faiss_knn, ops, predict
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--guids", type=int, default=1000000)
+ap.add_argument("--triplets", type=int, default=5000000)
+ap.add_argument("--batch", type=int, default=65536)
+ap.add_argument("--knn-k", type=int, default=100)
+ap.add_argument("--write-rows", type=int, default=100000, help="rows of the KNN result formatted into knn_split* files")
+ap.add_argument("--out", default="")
+ap.add_argument("--mine", action="store_true", help="in-batch semi-hard mining (default: the reference's random negatives)")
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+torch.cuda.set_device(0)
+G, F, B = args.guids, 1500, args.batch
+gen = torch.Generator(device=dev)
+gen.manual_seed(11)
+t = {}
+
+
+def tick(name, t0):
+  torch.cuda.synchronize()
+  t[name] = time.time() - t0
+
+
+# ---- stage 0: resident feature table (normalised 16-bit, built slab by slab) + guid clusters so that there is a signal
+t0 = time.time()
+eng = engine.TowerEngine([F, 5000, 256], device=dev, base_lr=1e-3, margin=0.8)
+table16 = torch.empty((G, eng.F_pad), dtype=eng.t16, device=dev)
+centres = torch.rand((1000, F), generator=gen, device=dev)
+cluster = torch.randint(0, 1000, (G,), generator=gen, device=dev)
+for s in range(0, G, 65536):
+  rows = min(65536, G - s)
+  slab = centres[cluster[s:s + rows]] + 0.25 * torch.rand((rows, F), generator=gen, device=dev)
+  eng.prepare_table(slab, out=table16[s:s + rows])
+tick("build_feature_table_s", t0)
+
+# ---- stage 1: one training epoch over `triplets` cowatch pairs (anchor/positive from the same cluster, random negative)
+t0 = time.time()
+steps = max(1, args.triplets // B)
+replay = eng.capture_step(table16, B, mine=args.mine)
+order = torch.argsort(cluster)
+start = torch.searchsorted(cluster[order], torch.arange(1001, device=dev))
+losses = []
+for i in range(steps):
+  a = torch.randint(0, G, (B,), generator=gen, device=dev)
+  c = cluster[a]
+  span = (start[c + 1] - start[c]).clamp(min=1)
+  p = order[start[c] + (torch.rand((B,), generator=gen, device=dev) * span).long() % span]
+  n = torch.randint(0, G, (B,), generator=gen, device=dev)
+  st = replay(torch.stack([a, p, n], 1))
+  if i % 16 == 0 or i == steps - 1:
+    losses.append(float(st[0].item()))
+tick("train_s", t0)
+
+# ---- stage 2: embed every guid (Prediction.run_features on the live engine, batches of 100 000 like predict.py:42)
+t0 = time.time()
+pred = predict.Prediction(sess=eng)
+emb = torch.empty((G, 256), dtype=torch.float32, device=dev)
+for s in range(0, G, 100000):
+  rows = min(100000, G - s)
+  x16 = table16[s:s + rows]                                   # already normalised 16-bit rows: forward only
+  emb[s:s + rows].copy_(eng.forward_rows(x16, rows)["e"])
+tick("embed_s", t0)
+
+# ---- stage 3: exact top-k over all embeddings, queries = the index itself (faiss_knn.py:105-106)
+t0 = time.time()
+index = ops.FlatIndex(emb, "L2")
+D = torch.empty((G, args.knn_k), dtype=torch.float32, device=dev)
+I = torch.empty((G, args.knn_k), dtype=torch.int64, device=dev)
+for s in range(0, G, 262144):
+  rows = min(262144, G - s)
+  d_, i_ = index.search(emb[s:s + rows], args.knn_k)
+  D[s:s + rows], I[s:s + rows] = d_, i_
+  if os.environ.get("CYCLE_DEBUG"):
+    print("block %d: stats %s, ids out of range %d, emb finite %s, loss %s" % (s, index.last_stats(), int(((i_ < -1) | (i_ >= G)).sum().item()),
+          bool(torch.isfinite(emb[s:s + rows]).all().item()), losses[-3:]), file=sys.stderr, flush=True)
+stats = index.last_stats()
+tick("knn_s", t0)
+same_cluster = float((cluster[I[:, 1:6]] == cluster[:, None]).float().mean().item())
+self_first = float((I[:, 0] == torch.arange(G, device=dev)).float().mean().item())
+
+# ---- stage 4: knn_split* files (write_knn format) for the first `write_rows` queries
+t0 = time.time()
+out_dir = args.out or tempfile.mkdtemp(prefix="cdml_cycle_")
+R = min(args.write_rows, G)
+dm = {i: "g%08d" % i for i in range(G)} if R else {}
+faiss_knn.write_knn(out_dir, split_num=10, D=D[:R].cpu().numpy(), I=I[:R].cpu().numpy(), prefix="knn_split", decode_map=dm)
+tick("write_s", t0)
+print(json.dumps({"guids": G, "triplets": steps * B, "steps": steps, "knn_k": args.knn_k, "seconds": t,
+                  "train_triplets_per_s": steps * B / t["train_s"], "embed_rows_per_s": G / t["embed_s"],
+                  "knn_queries_per_s": G / t["knn_s"], "loss_first_last": [losses[0], losses[-1]],
+                  "top5_same_cluster": same_cluster, "self_is_first_neighbour": self_first,
+                  "knn_fallback_queries_last_block": stats["fallback_queries"], "mining": bool(args.mine), "out_dir": out_dir}))
