@@ -327,7 +327,7 @@ def main():
   top = kern[0]
   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), if present
   traffic, traffic_src = None, None
-  prof = os.path.join(ROOT, "profiles", "r01_ncu_step_gemms_final_summary.json")
+  prof = os.path.join(ROOT, "profiles", "r01_ncu_step_gemms_v2_summary.json")
   if os.path.exists(prof) and args.batch == 65536:
     want = {(0, 1, 1): "EpiStore16", (0, 1, 2): "EpiL2Norm", (1, 1, 0): "EpiStoreF32", (0, 0, 3): "EpiMaskLeaky",
             (0, 0, 99): "EpiMine"}.get(top["key"])
@@ -335,7 +335,7 @@ def main():
     if cands:
       best = max(cands, key=lambda k: k["duration_ms"])
       traffic = (best["dram_read_GB"] + best["dram_write_GB"]) * 1e9
-      traffic_src = "profiles/r01_ncu_step_gemms_final_summary.json: " + best["kernel"]
+      traffic_src = "profiles/r01_ncu_step_gemms_v2_summary.json: " + best["kernel"]
   roofline = {"bound": "tensor", "kernel": "cdml gemm tcgen05 " + top["gemm"], "achieved": top["tflops"],
               "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": top["tflops"] / pk["bf16_tflops_sustained"],
               "traffic": traffic, "traffic_source": traffic_src,
