@@ -464,6 +464,63 @@ __global__ void opt_apply_kernel(int kind, float* __restrict__ w, float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fusion towers (models.py:65-157): 256-wide elementwise joins of 16-bit activations and the output L2-norm of a
+// tensor that is not a GEMM output.  op: 0 a*b | 1 a+b | 2 a*b+a+b | 3 a*leaky'(b) | 4 a*b+a | 6 (a*b+a)*leaky'(c)
+// | 7 a*b*leaky'(c);  leaky'(t) = t > 0 ? 1 : alpha.  fp32 math, 16-bit in / out.
+// ------------------------------------------------------------------------------------------------
+template <int kBf16>
+__global__ void ew16_kernel(int op, const uint16_t* __restrict__ a, int64_t lda, const uint16_t* __restrict__ b,
+                            int64_t ldb, const uint16_t* __restrict__ c, int64_t ldc, uint16_t* __restrict__ out,
+                            int64_t ldo, int64_t rows, int cols, float alpha) {
+  const int cols2 = cols >> 1;   // cols is even (checked by the host)
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows * cols2;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols2;
+    const int j = static_cast<int>(i - r * cols2) * 2;
+    const float2 x = unpack2<kBf16>(*reinterpret_cast<const uint32_t*>(a + r * lda + j));
+    const float2 y = unpack2<kBf16>(*reinterpret_cast<const uint32_t*>(b + r * ldb + j));
+    float2 z = make_float2(0.f, 0.f);
+    if (op >= 6) z = unpack2<kBf16>(*reinterpret_cast<const uint32_t*>(c + r * ldc + j));
+    float2 o;
+    switch (op) {
+      case 0: o = make_float2(x.x * y.x, x.y * y.y); break;
+      case 1: o = make_float2(x.x + y.x, x.y + y.y); break;
+      case 2: o = make_float2(fmaf(x.x, y.x, x.x + y.x), fmaf(x.y, y.y, x.y + y.y)); break;
+      case 3: o = make_float2(x.x * (y.x > 0.f ? 1.f : alpha), x.y * (y.y > 0.f ? 1.f : alpha)); break;
+      case 4: o = make_float2(fmaf(x.x, y.x, x.x), fmaf(x.y, y.y, x.y)); break;
+      case 6: o = make_float2(fmaf(x.x, y.x, x.x) * (z.x > 0.f ? 1.f : alpha), fmaf(x.y, y.y, x.y) * (z.y > 0.f ? 1.f : alpha)); break;
+      default: o = make_float2(x.x * y.x * (z.x > 0.f ? 1.f : alpha), x.y * y.y * (z.y > 0.f ? 1.f : alpha)); break;
+    }
+    *reinterpret_cast<uint32_t*>(out + r * ldo + j) = pack2<kBf16>(o.x, o.y);
+  }
+}
+
+// e = y * rsqrt(max(sum y^2, eps)) for 16-bit rows y (tf.nn.l2_normalize, models.py:90/:121/:156): fp32 e, rinv, 16-bit e.
+template <int kBf16>
+__global__ void __launch_bounds__(kRowThreads)
+rows_l2norm16_kernel(const uint16_t* __restrict__ y, int64_t n, int D, int64_t ld_y, float eps, float* __restrict__ e,
+                     int64_t ld_e, float* __restrict__ rinv, uint16_t* __restrict__ e16, int64_t ld_e16) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + warp; r < n;
+       r += static_cast<int64_t>(gridDim.x) * kWarpsPerBlock) {
+    const uint16_t* yr = y + r * ld_y;
+    float ss = 0.f;
+    for (int j = 2 * lane; j < D; j += 64) {
+      const float2 v = unpack2<kBf16>(*reinterpret_cast<const uint32_t*>(yr + j));
+      ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
+    }
+    ss = warp_sum(ss);
+    const float s = rsqrtf(fmaxf(ss, eps));
+    if (lane == 0 && rinv != nullptr) rinv[r] = s;
+    for (int j = 2 * lane; j < D; j += 64) {
+      const float2 v = unpack2<kBf16>(*reinterpret_cast<const uint32_t*>(yr + j));
+      *reinterpret_cast<float2*>(e + r * ld_e + j) = make_float2(v.x * s, v.y * s);
+      if (e16 != nullptr) *reinterpret_cast<uint32_t*>(e16 + r * ld_e16 + j) = pack2<kBf16>(v.x * s, v.y * s);
+    }
+  }
+}
+
 static inline int flat_grid(cdml_ctx* ctx, int64_t n, int threads) {
   const int64_t blocks = (n + threads - 1) / threads;
   const int64_t cap = static_cast<int64_t>(ctx->num_sms) * 8;
@@ -663,6 +720,42 @@ int cdml_opt_apply(cdml_ctx* ctx, int kind, float* w, float* m, float* v, const 
   else
     opt_apply_kernel<0><<<grid, 256, 0, st>>>(kind, w, m, v, g, n, scalars, norms, beta1, beta2, eps, grad_scale, wd_reg,
                                               clip_norm, momentum, lars_weight_decay, lars_eeta, static_cast<uint16_t*>(w16));
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cdml_ew16(cdml_ctx* ctx, int op, const void* a, int64_t lda, const void* b, int64_t ldb, const void* c, int64_t ldc,
+              void* out, int64_t ldo, int64_t rows, int cols, float alpha, int dtype16, void* stream) {
+  CDML_REQUIRE(ctx && a && b && out && rows >= 0 && cols > 0 && cols % 2 == 0, "cdml_ew16: bad argument");
+  CDML_REQUIRE(op == 0 || op == 1 || op == 2 || op == 3 || op == 4 || op == 6 || op == 7, "cdml_ew16: unknown op %d", op);
+  CDML_REQUIRE(op < 6 || c != nullptr, "cdml_ew16: op %d needs the third operand", op);
+  CDML_REQUIRE(lda % 2 == 0 && ldb % 2 == 0 && ldo % 2 == 0 && (c == nullptr || ldc % 2 == 0), "cdml_ew16: odd row pitch");
+  if (rows == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = flat_grid(ctx, rows * (cols / 2), 256);
+  if (dtype16 == CDML_BF16)
+    ew16_kernel<1><<<grid, 256, 0, st>>>(op, static_cast<const uint16_t*>(a), lda, static_cast<const uint16_t*>(b), ldb,
+                                         static_cast<const uint16_t*>(c), ldc, static_cast<uint16_t*>(out), ldo, rows, cols, alpha);
+  else
+    ew16_kernel<0><<<grid, 256, 0, st>>>(op, static_cast<const uint16_t*>(a), lda, static_cast<const uint16_t*>(b), ldb,
+                                         static_cast<const uint16_t*>(c), ldc, static_cast<uint16_t*>(out), ldo, rows, cols, alpha);
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cdml_rows_l2norm16(cdml_ctx* ctx, const void* y16, int64_t n, int D, int64_t ld_y, float eps, int dtype16, float* e,
+                       int64_t ld_e, float* rinv, void* e16, int64_t ld_e16, void* stream) {
+  CDML_REQUIRE(ctx && y16 && e && n >= 0 && D > 0 && D % 2 == 0 && ld_y % 2 == 0 && ld_e % 2 == 0 && ld_e16 % 2 == 0,
+               "cdml_rows_l2norm16: bad argument");
+  if (n == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = row_grid(ctx, n);
+  if (dtype16 == CDML_BF16)
+    rows_l2norm16_kernel<1><<<grid, kRowThreads, 0, st>>>(static_cast<const uint16_t*>(y16), n, D, ld_y, eps, e, ld_e, rinv,
+                                                          static_cast<uint16_t*>(e16), ld_e16);
+  else
+    rows_l2norm16_kernel<0><<<grid, kRowThreads, 0, st>>>(static_cast<const uint16_t*>(y16), n, D, ld_y, eps, e, ld_e, rinv,
+                                                          static_cast<uint16_t*>(e16), ld_e16);
   CDML_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

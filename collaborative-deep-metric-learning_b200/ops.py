@@ -183,6 +183,29 @@ def opt_apply(kind, w, m, v, g, scalars, norms=None, beta1=0.9, beta2=0.999, eps
                                    dtype16_of(w16) if w16 is not None else F16, stream_ptr()))
 
 
+EW_MUL, EW_ADD, EW_MUL_ADD_BOTH, EW_MASK, EW_MUL_ADD, EW_MUL_ADD_MASK, EW_MUL_MASK = 0, 1, 2, 3, 4, 6, 7
+
+
+def ew16(op, a, b, out, c=None, alpha=0.2):
+  """Elementwise join of 16-bit [rows, cols] matrices (cdml_ew16); `out` may alias an input."""
+  rows, cols = out.shape
+  _count(1)
+  check(_lib.load().cdml_ew16(_ctx(out), int(op), ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(c),
+                              c.stride(0) if c is not None else 0, ptr(out), out.stride(0), rows, cols, float(alpha),
+                              dtype16_of(out), stream_ptr()))
+  return out
+
+
+def rows_l2norm16(y16, e, rinv=None, e16=None, eps=1e-12):
+  """tf.nn.l2_normalize of 16-bit rows -> fp32 e (+ rinv, + 16-bit copy)."""
+  n, D = y16.shape
+  _count(1)
+  check(_lib.load().cdml_rows_l2norm16(_ctx(y16), ptr(y16), n, D, y16.stride(0), float(eps), dtype16_of(y16), ptr(e),
+                                       e.stride(0), ptr(rinv), ptr(e16), e16.stride(0) if e16 is not None else 0,
+                                       stream_ptr()))
+  return e
+
+
 def cast16(x, out16):
   _count(1)
   check(_lib.load().cdml_cast16(_ctx(x), ptr(x), x.numel(), ptr(out16), dtype16_of(out16), stream_ptr()))
