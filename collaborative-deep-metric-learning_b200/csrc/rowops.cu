@@ -466,33 +466,58 @@ __global__ void opt_apply_kernel(int kind, float* __restrict__ w, float* __restr
 
 // ------------------------------------------------------------------------------------------------
 // Fusion towers (models.py:65-157): 256-wide elementwise joins of 16-bit activations and the output L2-norm of a
-// tensor that is not a GEMM output.  op: 0 a*b | 1 a+b | 2 a*b+a+b | 3 a*leaky'(b) | 4 a*b+a | 6 (a*b+a)*leaky'(c)
+// tensor that is not a GEMM output.  op: 0 a*b | 1 a+b | 2 a*b+a+b | 3 a*leaky'(b) | 4 a*b+a | 5 a*b+c | 6 (a*b+a)*leaky'(c)
 // | 7 a*b*leaky'(c);  leaky'(t) = t > 0 ? 1 : alpha.  fp32 math, 16-bit in / out.
 // ------------------------------------------------------------------------------------------------
-template <int kBf16>
-__global__ void ew16_kernel(int op, const uint16_t* __restrict__ a, int64_t lda, const uint16_t* __restrict__ b,
-                            int64_t ldb, const uint16_t* __restrict__ c, int64_t ldc, uint16_t* __restrict__ out,
-                            int64_t ldo, int64_t rows, int cols, float alpha) {
-  const int cols2 = cols >> 1;   // cols is even (checked by the host)
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows * cols2;
+template <int kOp>
+__device__ __forceinline__ float ew_apply(float x, float y, float z, float alpha) {
+  if constexpr (kOp == 0) return x * y;
+  else if constexpr (kOp == 1) return x + y;
+  else if constexpr (kOp == 2) return fmaf(x, y, x + y);
+  else if constexpr (kOp == 3) return x * (y > 0.f ? 1.f : alpha);
+  else if constexpr (kOp == 4) return fmaf(x, y, x);
+  else if constexpr (kOp == 5) return fmaf(x, y, z);
+  else if constexpr (kOp == 6) return fmaf(x, y, x) * (z > 0.f ? 1.f : alpha);
+  else return x * y * (z > 0.f ? 1.f : alpha);
+}
+
+// kVec = 8: one 16-byte piece per operand per thread (cols, pitches multiples of 8, 16-byte aligned bases); kVec = 2 otherwise.
+template <int kBf16, int kOp, int kVec>
+__global__ void __launch_bounds__(256)
+ew16_kernel(const uint16_t* __restrict__ a, int64_t lda, const uint16_t* __restrict__ b, int64_t ldb,
+            const uint16_t* __restrict__ c, int64_t ldc, uint16_t* __restrict__ out, int64_t ldo, int64_t rows, int cols,
+            float alpha) {
+  constexpr int kWords = kVec / 2;
+  const int per_row = cols / kVec;
+  const int64_t total = rows * per_row;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / cols2;
-    const int j = static_cast<int>(i - r * cols2) * 2;
-    const float2 x = unpack2<kBf16>(*reinterpret_cast<const uint32_t*>(a + r * lda + j));
-    const float2 y = unpack2<kBf16>(*reinterpret_cast<const uint32_t*>(b + r * ldb + j));
-    float2 z = make_float2(0.f, 0.f);
-    if (op >= 6) z = unpack2<kBf16>(*reinterpret_cast<const uint32_t*>(c + r * ldc + j));
-    float2 o;
-    switch (op) {
-      case 0: o = make_float2(x.x * y.x, x.y * y.y); break;
-      case 1: o = make_float2(x.x + y.x, x.y + y.y); break;
-      case 2: o = make_float2(fmaf(x.x, y.x, x.x + y.x), fmaf(x.y, y.y, x.y + y.y)); break;
-      case 3: o = make_float2(x.x * (y.x > 0.f ? 1.f : alpha), x.y * (y.y > 0.f ? 1.f : alpha)); break;
-      case 4: o = make_float2(fmaf(x.x, y.x, x.x), fmaf(x.y, y.y, x.y)); break;
-      case 6: o = make_float2(fmaf(x.x, y.x, x.x) * (z.x > 0.f ? 1.f : alpha), fmaf(x.y, y.y, x.y) * (z.y > 0.f ? 1.f : alpha)); break;
-      default: o = make_float2(x.x * y.x * (z.x > 0.f ? 1.f : alpha), x.y * y.y * (z.y > 0.f ? 1.f : alpha)); break;
+    const int64_t r = i / per_row;
+    const int j = static_cast<int>(i - r * per_row) * kVec;
+    uint32_t xa[kWords], xb[kWords], xc[kWords], xo[kWords];
+    if constexpr (kVec == 8) {
+      const uint4 va = *reinterpret_cast<const uint4*>(a + r * lda + j);
+      const uint4 vb = *reinterpret_cast<const uint4*>(b + r * ldb + j);
+      xa[0] = va.x, xa[1] = va.y, xa[2] = va.z, xa[3] = va.w;
+      xb[0] = vb.x, xb[1] = vb.y, xb[2] = vb.z, xb[3] = vb.w;
+      if constexpr (kOp >= 5) {
+        const uint4 vc = *reinterpret_cast<const uint4*>(c + r * ldc + j);
+        xc[0] = vc.x, xc[1] = vc.y, xc[2] = vc.z, xc[3] = vc.w;
+      }
+    } else {
+      xa[0] = *reinterpret_cast<const uint32_t*>(a + r * lda + j);
+      xb[0] = *reinterpret_cast<const uint32_t*>(b + r * ldb + j);
+      if constexpr (kOp >= 5) xc[0] = *reinterpret_cast<const uint32_t*>(c + r * ldc + j);
     }
-    *reinterpret_cast<uint32_t*>(out + r * ldo + j) = pack2<kBf16>(o.x, o.y);
+#pragma unroll
+    for (int w = 0; w < kWords; ++w) {
+      const float2 x = unpack2<kBf16>(xa[w]), y = unpack2<kBf16>(xb[w]);
+      float2 z = make_float2(0.f, 0.f);
+      if constexpr (kOp >= 5) z = unpack2<kBf16>(xc[w]);
+      xo[w] = pack2<kBf16>(ew_apply<kOp>(x.x, y.x, z.x, alpha), ew_apply<kOp>(x.y, y.y, z.y, alpha));
+    }
+    if constexpr (kVec == 8) *reinterpret_cast<uint4*>(out + r * ldo + j) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+    else *reinterpret_cast<uint32_t*>(out + r * ldo + j) = xo[0];
   }
 }
 
@@ -727,18 +752,38 @@ int cdml_opt_apply(cdml_ctx* ctx, int kind, float* w, float* m, float* v, const 
 int cdml_ew16(cdml_ctx* ctx, int op, const void* a, int64_t lda, const void* b, int64_t ldb, const void* c, int64_t ldc,
               void* out, int64_t ldo, int64_t rows, int cols, float alpha, int dtype16, void* stream) {
   CDML_REQUIRE(ctx && a && b && out && rows >= 0 && cols > 0 && cols % 2 == 0, "cdml_ew16: bad argument");
-  CDML_REQUIRE(op == 0 || op == 1 || op == 2 || op == 3 || op == 4 || op == 6 || op == 7, "cdml_ew16: unknown op %d", op);
-  CDML_REQUIRE(op < 6 || c != nullptr, "cdml_ew16: op %d needs the third operand", op);
+  CDML_REQUIRE(op >= 0 && op <= 7, "cdml_ew16: unknown op %d", op);
+  CDML_REQUIRE(op < 5 || c != nullptr, "cdml_ew16: op %d needs the third operand", op);
   CDML_REQUIRE(lda % 2 == 0 && ldb % 2 == 0 && ldo % 2 == 0 && (c == nullptr || ldc % 2 == 0), "cdml_ew16: odd row pitch");
   if (rows == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = flat_grid(ctx, rows * (cols / 2), 256);
-  if (dtype16 == CDML_BF16)
-    ew16_kernel<1><<<grid, 256, 0, st>>>(op, static_cast<const uint16_t*>(a), lda, static_cast<const uint16_t*>(b), ldb,
-                                         static_cast<const uint16_t*>(c), ldc, static_cast<uint16_t*>(out), ldo, rows, cols, alpha);
-  else
-    ew16_kernel<0><<<grid, 256, 0, st>>>(op, static_cast<const uint16_t*>(a), lda, static_cast<const uint16_t*>(b), ldb,
-                                         static_cast<const uint16_t*>(c), ldc, static_cast<uint16_t*>(out), ldo, rows, cols, alpha);
+  const uint16_t* pa = static_cast<const uint16_t*>(a);
+  const uint16_t* pb = static_cast<const uint16_t*>(b);
+  const uint16_t* pc = static_cast<const uint16_t*>(c);
+  uint16_t* po = static_cast<uint16_t*>(out);
+  const bool vec = cols % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0 && (c == nullptr || ldc % 8 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                     reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const int grid = flat_grid(ctx, rows * (cols / (vec ? 8 : 2)), 256);
+#define CDML_EW_LAUNCH(BF, OP)                                                                                       \
+  do {                                                                                                               \
+    if (vec) ew16_kernel<BF, OP, 8><<<grid, 256, 0, st>>>(pa, lda, pb, ldb, pc, ldc, po, ldo, rows, cols, alpha);       \
+    else ew16_kernel<BF, OP, 2><<<grid, 256, 0, st>>>(pa, lda, pb, ldb, pc, ldc, po, ldo, rows, cols, alpha);           \
+  } while (0)
+#define CDML_EW_OPS(BF)                                                                                              \
+  switch (op) {                                                                                                      \
+    case 0: CDML_EW_LAUNCH(BF, 0); break;                                                                            \
+    case 1: CDML_EW_LAUNCH(BF, 1); break;                                                                            \
+    case 2: CDML_EW_LAUNCH(BF, 2); break;                                                                            \
+    case 3: CDML_EW_LAUNCH(BF, 3); break;                                                                            \
+    case 4: CDML_EW_LAUNCH(BF, 4); break;                                                                            \
+    case 5: CDML_EW_LAUNCH(BF, 5); break;                                                                            \
+    case 6: CDML_EW_LAUNCH(BF, 6); break;                                                                            \
+    default: CDML_EW_LAUNCH(BF, 7); break;                                                                           \
+  }
+  if (dtype16 == CDML_BF16) { CDML_EW_OPS(1) } else { CDML_EW_OPS(0) }
+#undef CDML_EW_OPS
+#undef CDML_EW_LAUNCH
   CDML_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

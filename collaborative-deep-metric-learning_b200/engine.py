@@ -36,7 +36,9 @@ class TowerEngine:
   def __init__(self, dims, device=None, dtype16=F16, seed=2, bias_init=0.0, base_lr=1e-3, margin=0.8,
                lr_decay_steps=1000000, lr_decay=0.96, beta1=0.9, beta2=0.999, eps=1e-8, alpha=LEAKY_ALPHA,
                process_group=None, init_params=None, optimizer="adam", clip_norm=0.0, reg_penalty=0.0, l2_penalty=1e-8,
-               momentum=0.9, lars_weight_decay=1e-4, lars_eeta=1e-3):
+               momentum=0.9, lars_weight_decay=1e-4, lars_eeta=1e-3, layer_shapes=None):
+    """`layer_shapes` ([(in,out)] per fully_connected layer; `bias_init` may then be a list): parameter layout of a tower
+    that is not a plain chain (fusion.GraphEngine); default = consecutive `dims`."""
     if not torch.cuda.is_available():
       raise RuntimeError("TowerEngine needs a CUDA device (sm_100a); there is no CPU path")
     self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -46,7 +48,11 @@ class TowerEngine:
     for d in self.dims[1:]:
       if d % 8:
         raise ValueError("layer widths must be multiples of 8 (16-byte row pitch for TMA); got %d" % d)
-    self.L = len(self.dims) - 1
+    self.shapes = [(int(a), int(b)) for a, b in (layer_shapes if layer_shapes is not None else zip(self.dims[:-1], self.dims[1:]))]
+    for _, d in self.shapes:
+      if d % 8:
+        raise ValueError("layer widths must be multiples of 8 (16-byte row pitch for TMA); got %d" % d)
+    self.L = len(self.shapes)
     self.dtype16 = dtype16
     self.t16 = ops.TORCH16[dtype16]
     self.alpha = float(alpha)
@@ -67,7 +73,7 @@ class TowerEngine:
 
     # ---- flat fp32 parameter / gradient / Adam buffers; per-tensor views ----
     sizes = []
-    for fi, fo in zip(self.dims[:-1], self.dims[1:]):
+    for fi, fo in self.shapes:
       sizes += [fi * fo, fo]
     self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     # keep every tensor 16-byte aligned inside the flat buffer
@@ -79,11 +85,11 @@ class TowerEngine:
     self.v = torch.zeros(total, dtype=torch.float32, device=dev)
     self.g = torch.zeros(total, dtype=torch.float32, device=dev)
     self.sizes = sizes
-    self.W = [self._view(self.w, 2 * l).view(self.dims[l], self.dims[l + 1]) for l in range(self.L)]
+    self.W = [self._view(self.w, 2 * l).view(*self.shapes[l]) for l in range(self.L)]
     self.b = [self._view(self.w, 2 * l + 1) for l in range(self.L)]
-    self.gW = [self._view(self.g, 2 * l).view(self.dims[l], self.dims[l + 1]) for l in range(self.L)]
+    self.gW = [self._view(self.g, 2 * l).view(*self.shapes[l]) for l in range(self.L)]
     self.gb = [self._view(self.g, 2 * l + 1) for l in range(self.L)]
-    self.W16 = [torch.zeros((self.dims[l], self.dims[l + 1]), dtype=self.t16, device=dev) for l in range(self.L)]
+    self.W16 = [torch.zeros(self.shapes[l], dtype=self.t16, device=dev) for l in range(self.L)]
     self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)
     self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)
     self.norms = torch.zeros((2 * self.L, 2), dtype=torch.float32, device=dev)       # per variable: {sum g_eff^2, sum w^2}
@@ -94,10 +100,10 @@ class TowerEngine:
     if init_params is None:
       rng = np.random.RandomState(seed)
       init_params = []
-      for fi, fo in zip(self.dims[:-1], self.dims[1:]):
+      biases = list(bias_init) if isinstance(bias_init, (list, tuple)) else [bias_init] * self.L
+      for (fi, fo), b0 in zip(self.shapes, biases):
         lim = math.sqrt(6.0 / (fi + fo))  # slim xavier_initializer (uniform)
-        init_params.append((rng.uniform(-lim, lim, size=(fi, fo)).astype(np.float32),
-                            np.full((fo,), bias_init, np.float32)))
+        init_params.append((rng.uniform(-lim, lim, size=(fi, fo)).astype(np.float32), np.full((fo,), b0, np.float32)))
     self.load_params(init_params)
 
   # ------------------------------------------------------------------ parameters
@@ -210,6 +216,9 @@ class TowerEngine:
       ops.fill_column16(x16, self.F, 1.0)     # the ones column of [x | 1] (first padding column; never read by the forward GEMM)
     return x16
 
+  def _table_rows(self, table16):
+    return table16.shape[0]
+
   def _input_has_ones(self, x16):
     """First use of an input matrix: does its padding column F hold the ones `prepare_table` plants?  (One 2-byte
     read per distinct buffer; a table built by other means silently falls back to the column-sum kernel.)"""
@@ -260,24 +269,28 @@ class TowerEngine:
     for l in range(self.L - 1, -1, -1):
       K_in, N_out = self.dims[l], self.dims[l + 1]
       inp = x16 if l == 0 else buf["acts"][l - 1]
-      s = buf["splits"][l]
-      # weight gradient: dW[in,out] = inp^T[in,R] . dz[R,out]   (both operands MN-major, K = R).  With the ones column
-      # the GEMM has in+1 rows and its last row IS the bias gradient; [dW ; db] is one contiguous block of the flat buffer.
-      rows = buf["wrows"][l] if (l > 0 or input_ones) else K_in
-      o = int(self.offsets[2 * l])
-      gWb = self.g[o:o + rows * N_out]
-      if s > 1:
-        used = ops.gemm16(inp, dz[l], rows, N_out, R, 1, 1, EPI_STORE_F32, buf["partials"], num_splits=s,
-                          split_stride=rows * N_out, ld_out=N_out)
-        ops.sum_partials(buf["partials"], used, rows * N_out, rows * N_out, gWb)
-      else:
-        ops.gemm16(inp, dz[l], rows, N_out, R, 1, 1, EPI_STORE_F32, gWb, ld_out=N_out)
-      if rows == K_in:
-        ops.colsum16(dz[l], R, N_out, self.gb[l], buf["colsum_ws"])
+      self._weight_gradient(l, inp, dz[l], R, buf, with_bias_row=(l > 0 or input_ones))
       if l > 0:
         # data gradient + leaky' of the previous layer: dz[l-1] = (dz[l] . W_l^T) * leaky'(h_{l-1})
         ops.gemm16(dz[l], self.W16[l], R, K_in, N_out, 0, 0, EPI_MASK_LEAKY, dz[l - 1], alpha=self.alpha,
                    aux1=buf["acts"][l - 1])
+
+  def _weight_gradient(self, l, inp, dz, R, buf, with_bias_row):
+    """dW[in,out] = inp^T[in,R] . dz[R,out]   (both operands MN-major, K = R).  With the ones column the GEMM has in+1
+    rows and its last row IS the bias gradient; [dW ; db] is one contiguous block of the flat buffer."""
+    K_in, N_out = self.shapes[l]
+    s = buf["splits"][l]
+    rows = buf["wrows"][l] if with_bias_row else K_in
+    o = int(self.offsets[2 * l])
+    gWb = self.g[o:o + rows * N_out]
+    if s > 1:
+      used = ops.gemm16(inp, dz, rows, N_out, R, 1, 1, EPI_STORE_F32, buf["partials"], num_splits=s,
+                        split_stride=rows * N_out, ld_out=N_out)
+      ops.sum_partials(buf["partials"], used, rows * N_out, rows * N_out, gWb)
+    else:
+      ops.gemm16(inp, dz, rows, N_out, R, 1, 1, EPI_STORE_F32, gWb, ld_out=N_out)
+    if rows == K_in:
+      ops.colsum16(dz, R, N_out, self.gb[l], buf["colsum_ws"])
 
   def apply_gradients(self, B_local):
     if self.world > 1:
@@ -319,7 +332,7 @@ class TowerEngine:
       raise RuntimeError("capture_step disabled for data-parallel runs (CDML_DDP_GRAPH=0)")
     # warm-up triplets with distinct guids per row: a degenerate batch (one guid everywhere) drives the mining
     # epilogue through its re-scan on every chunk (measured 21 ms per scan instead of 2)
-    G = table16.shape[0]
+    G = self._table_rows(table16)
     ar = torch.arange(B, dtype=torch.int64, device=self.device)
     static_idx = torch.stack([(3 * ar) % G, (3 * ar + 1) % G, (3 * ar + 2) % G], dim=1).contiguous()
     snap = (self.w.clone(), self.m.clone(), self.v.clone(), self.step_counter.clone())   # warm-up must not train

@@ -183,7 +183,7 @@ def opt_apply(kind, w, m, v, g, scalars, norms=None, beta1=0.9, beta2=0.999, eps
                                    dtype16_of(w16) if w16 is not None else F16, stream_ptr()))
 
 
-EW_MUL, EW_ADD, EW_MUL_ADD_BOTH, EW_MASK, EW_MUL_ADD, EW_MUL_ADD_MASK, EW_MUL_MASK = 0, 1, 2, 3, 4, 6, 7
+EW_MUL, EW_ADD, EW_MUL_ADD_BOTH, EW_MASK, EW_MUL_ADD, EW_FMA, EW_MUL_ADD_MASK, EW_MUL_MASK = 0, 1, 2, 3, 4, 5, 6, 7
 
 
 def ew16(op, a, b, out, c=None, alpha=0.2):

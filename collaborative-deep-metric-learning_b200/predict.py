@@ -43,7 +43,11 @@ def load_engine(ckpt, device=None):
   if not os.path.exists(path):
     raise IOError("Prediction __init__ Cannot find %s" % ckpt)
   z = np.load(path, allow_pickle=False)
-  eng = TowerEngine([int(d) for d in z["dims"]], device=device)
+  if "spec" in z.files:       # a fusion tower (fusion.GraphEngine)
+    from .fusion import GraphEngine
+    eng = GraphEngine(json.loads(str(z["spec"])), feature_size=int(z["dims"][0]), device=device)
+  else:
+    eng = TowerEngine([int(d) for d in z["dims"]], device=device)
   eng.load_state_dict({"w": z["w"], "m": z["m"], "v": z["v"], "step": int(z["step"])})
   return eng
 

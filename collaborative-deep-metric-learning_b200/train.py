@@ -17,6 +17,7 @@ from absl import app, flags
 
 from . import inputs, losses, models
 from .engine import TowerEngine
+from .fusion import GraphEngine
 from .evaluate import Evaluation
 from .online_data import feature_size, load_cowatches
 from .predict import Prediction
@@ -117,7 +118,14 @@ def build_graph(input_batch, model, output_size=256, loss_fn=None, base_learning
   if optimizer_class.__name__ not in _OPTIMIZER_KINDS:
     raise NotImplementedError("optimizer %s: built are %s" % (optimizer_class.__name__, sorted(_OPTIMIZER_KINDS)))
   result = model.create_model(input_batch, output_size)
-  spec = models.compile_chain(result["l2_norm"])
+  graph = None
+  try:
+    spec = models.compile_chain(result["l2_norm"])
+  except NotImplementedError:
+    # not a plain fully_connected chain: the visual+doc fusion towers (models.py:65-243) run on fusion.GraphEngine
+    graph = models.compile_graph(result["l2_norm"])
+    fcs = [e for e in graph["spec"] if e["op"] == "fc"]
+    spec = {"l2_penalty": [e["l2_penalty"] for e in fcs], "alpha": fcs[0]["alpha"]}
   if optimizer_class.__name__ == "MomentumOptimizer":                       # train.py:115-118
     opt = optimizer_class(base_learning_rate, momentum=0.9, name='Momentum', use_nesterov=True)
   else:
@@ -125,8 +133,12 @@ def build_graph(input_batch, model, output_size=256, loss_fn=None, base_learning
   l2_penalties = set(spec["l2_penalty"])
   if regularization_penalty and len(l2_penalties) != 1:
     raise NotImplementedError("layers with different l2_penalty")
-  engine = TowerEngine(spec["dims"], dtype16={"fp16": 0, "bf16": 1}[dtype16] if isinstance(dtype16, str) else dtype16,
-                       seed=seed, bias_init=spec["bias_init"][0], base_lr=base_learning_rate, margin=margin,
+  common = dict(dtype16={"fp16": 0, "bf16": 1}[dtype16] if isinstance(dtype16, str) else dtype16, seed=seed)
+  if graph is not None:
+    make = lambda **kw: GraphEngine(graph["spec"], feature_size=graph["F"], **common, **kw)
+  else:
+    make = lambda **kw: TowerEngine(spec["dims"], bias_init=spec["bias_init"][0], **common, **kw)
+  engine = make(base_lr=base_learning_rate, margin=margin,
                        lr_decay_steps=learning_rate_decay_examples, lr_decay=learning_rate_decay,
                        beta1=getattr(opt, "beta1", 0.9), beta2=getattr(opt, "beta2", 0.999), eps=getattr(opt, "epsilon", 1e-8),
                        alpha=spec["alpha"], process_group=process_group, init_params=init_params,
@@ -151,9 +163,12 @@ def save_checkpoint(engine, checkpoint_dir, step, model_name):
   prefix = os.path.join(checkpoint_dir, "model.ckpt-%d" % step)
   sd = engine.state_dict()
   names = {}
+  scopes = getattr(engine, "names", None)        # fusion towers name their layers (models.py:82-88)
   for l, (W, b) in enumerate(engine.get_params()):
-    scope = "fully_connected" if l == 0 else "fully_connected_%d" % l   # slim auto scopes (SURVEY 8a notes)
+    scope = scopes[l] if scopes else ("fully_connected" if l == 0 else "fully_connected_%d" % l)   # slim auto scopes
     names[scope + "/weights"], names[scope + "/biases"] = W, b
+  if "spec" in sd:
+    names["spec"] = np.asarray(sd["spec"])
   np.savez(prefix + ".npz", dims=np.asarray(sd["dims"]), w=sd["w"], m=sd["m"], v=sd["v"], step=sd["step"],
            model=model_name, **names)
   with open(os.path.join(checkpoint_dir, "checkpoint"), "w") as f:

@@ -115,8 +115,8 @@ int cdml_opt_apply(cdml_ctx* ctx, int kind, float* w, float* m, float* v, const 
                    float momentum, float lars_weight_decay, float lars_eeta, void* w16, int dtype16, void* stream);
 /* ---- fusion towers (models.py:65-157): elementwise joins of 16-bit [rows, cols] activations (tf.multiply, the residual
  *      adds and their backward forms) and tf.nn.l2_normalize of a tensor that is not a GEMM output.
- *      op: 0 a*b | 1 a+b | 2 a*b+a+b | 3 a*leaky'(b) | 4 a*b+a | 6 (a*b+a)*leaky'(c) | 7 a*b*leaky'(c),
- *      leaky'(t) = t > 0 ? 1 : alpha; c may be NULL for ops < 6; cols and all pitches even. */
+ *      op: 0 a*b | 1 a+b | 2 a*b+a+b | 3 a*leaky'(b) | 4 a*b+a | 5 a*b+c | 6 (a*b+a)*leaky'(c) |
+ *      7 a*b*leaky'(c), leaky'(t) = t > 0 ? 1 : alpha; c may be NULL for ops < 5; cols and all pitches even. */
 int cdml_ew16(cdml_ctx* ctx, int op, const void* a, int64_t lda, const void* b, int64_t ldb, const void* c, int64_t ldc,
               void* out, int64_t ldo, int64_t rows, int cols, float alpha, int dtype16, void* stream);
 int cdml_rows_l2norm16(cdml_ctx* ctx, const void* y16, int64_t n, int D, int64_t ld_y, float eps, int dtype16, float* e,

@@ -213,6 +213,138 @@ def tower_grads_emulated16(x, params, margin, kind="fp16", alpha: float = LEAKY_
 
 
 # --------------------------------------------------------------------------- #
+# fusion towers (models.py:65-243) as a small op list                           #
+# --------------------------------------------------------------------------- #
+def fusion_spec(name, feature_size=1628, visual=1500):
+  """Op list of the reference's fusion towers, restated from models.py: MultiplyNet :65-91, MlpNet :93-122,
+  ResNet :125-157, ResNetV2 :205-243.  Entries: input(lo,hi) = l2-normalised column slice (models.py:80-81, :85-86),
+  fc(src,out,bias_init) = fully_connected (models.py:19-30), mul / add over earlier entries, l2norm = model output."""
+  fc = lambda src, out, name: {"op": "fc", "src": src, "out": out, "bias_init": 0.1, "alpha": LEAKY_ALPHA, "name": name}
+  vin = {"op": "input", "lo": 0, "hi": visual, "eps": L2_EPS}
+  din = {"op": "input", "lo": visual, "hi": feature_size, "eps": L2_EPS}
+  if name == "ResNetV2":
+    spec = [vin, fc(0, 5000, "layer_visual_1_1"), fc(1, 256, "layer_visual_1_2"), fc(0, 256, "layer_visual_2_1"),
+            din, fc(4, 400, "layer_doc_1_1"), fc(5, 256, "layer_doc_1_2"), fc(4, 256, "layer_doc_2_1"),
+            {"op": "mul", "src": [2, 6]}, {"op": "mul", "src": [2, 7]}, {"op": "mul", "src": [3, 6]},
+            {"op": "mul", "src": [3, 7]}, {"op": "add", "src": [8, 9, 10, 11, 2, 3, 6, 7]},
+            fc(12, 256, "layer_fusion_1"), {"op": "add", "src": [12, 13]}, fc(14, 256, "layer_fusion_2"),
+            {"op": "add", "src": [14, 15]}, {"op": "l2norm", "src": 16, "eps": L2_EPS}]
+    return spec
+  spec = [vin, fc(0, 5000, "layer_visual_1"), fc(1, 256, "layer_visual_2"),
+          din, fc(3, 400, "layer_doc_1"), fc(4, 256, "layer_doc_2"), {"op": "mul", "src": [2, 5]}]
+  if name == "MultiplyNet":
+    spec += [{"op": "l2norm", "src": 6, "eps": L2_EPS}]
+  elif name == "MlpNet":
+    spec += [fc(6, 600, "layer_fusion_1"), fc(7, 256, "layer_fusion_2"), {"op": "l2norm", "src": 8, "eps": L2_EPS}]
+  elif name == "ResNet":
+    spec += [{"op": "add", "src": [6, 2, 5]}, fc(7, 256, "layer_fusion_1"), {"op": "add", "src": [7, 8]},
+             fc(9, 256, "layer_fusion_2"), {"op": "add", "src": [9, 10]}, {"op": "l2norm", "src": 11, "eps": L2_EPS}]
+  else:
+    raise ValueError(name)
+  return spec
+
+
+def graph_widths(spec):
+  w = []
+  for e in spec:
+    if e["op"] == "input":
+      w.append(e["hi"] - e["lo"])
+    elif e["op"] == "fc":
+      w.append(e["out"])
+    elif e["op"] in ("mul", "add"):
+      w.append(w[e["src"][0]])
+    else:
+      w.append(w[e["src"]])
+  return w
+
+
+def init_graph(spec, seed: int = 2, dtype=np.float32):
+  """Xavier-uniform weights / constant biases for every fc entry, in list order (= TF variable creation order)."""
+  rng = np.random.RandomState(seed)
+  w = graph_widths(spec)
+  return [(xavier_uniform(rng, w[e["src"]], e["out"], dtype), np.full((e["out"],), e["bias_init"], dtype))
+          for e in spec if e["op"] == "fc"]
+
+
+def graph_forward(x, spec, params, dtype=np.float64, rnd=None):
+  """Forward of an op list.  `rnd` (test infrastructure): rounding applied wherever the kernels store a 16-bit value
+  (normalised inputs, shadow weights, every intermediate); None = exact arithmetic."""
+  r = rnd or (lambda a: a)
+  x = np.asarray(x, dtype)
+  vals, li, out = [], 0, None
+  for e in spec:
+    if e["op"] == "input":
+      vals.append(r(l2_normalize(x[:, e["lo"]:e["hi"]], e.get("eps", L2_EPS))))
+    elif e["op"] == "fc":
+      W, b = params[li]
+      li += 1
+      vals.append(r(fully_connected(vals[e["src"]], r(np.asarray(W, dtype)), np.asarray(b, dtype), e.get("alpha", LEAKY_ALPHA))))
+    elif e["op"] == "mul":
+      vals.append(r(vals[e["src"][0]] * vals[e["src"][1]]))
+    elif e["op"] == "add":
+      acc = vals[e["src"][0]]
+      for s in e["src"][1:]:
+        acc = r(acc + vals[s])
+      vals.append(acc)
+    else:
+      y = vals[e["src"]]
+      rinv = 1.0 / np.sqrt(np.maximum(np.sum(y * y, -1, keepdims=True), e.get("eps", L2_EPS)))
+      vals.append(y * rinv)
+      out = {"values": vals, "rinv": rinv[:, 0], "l2_norm": vals[-1]}
+  return out
+
+
+def graph_backward(fwd, spec, params, dE, dtype=np.float64, rnd=None):
+  """Reverse sweep of the op list: [(dW, db)] per fc entry, from dL/d(l2_norm) [R,D].
+  l2norm: dy = (g - e (e.g)) rinv ; fc: dz = dh leaky'(h), dW = in^T dz, db = sum dz, d_in = dz W^T ;
+  mul: da = g b, db = g a ; add: every term receives g.  Nothing flows into the inputs."""
+  r = rnd or (lambda a: a)
+  vals = fwd["values"]
+  g = [None] * len(spec)
+
+  def acc(i, t):
+    g[i] = t if g[i] is None else r(g[i] + t)
+
+  fc_ids = [i for i, e in enumerate(spec) if e["op"] == "fc"]
+  grads = [None] * len(fc_ids)
+  e_out = fwd["l2_norm"]
+  d = np.asarray(dE, dtype)
+  acc(spec[-1]["src"], r((d - e_out * np.sum(e_out * d, -1, keepdims=True)) * fwd["rinv"][:, None]))
+  for i in range(len(spec) - 2, -1, -1):
+    e = spec[i]
+    if e["op"] == "input" or g[i] is None:
+      continue
+    if e["op"] == "fc":
+      li = fc_ids.index(i)
+      dz = r(g[i] * np.where(vals[i] > 0, 1.0, e.get("alpha", LEAKY_ALPHA)))
+      grads[li] = (vals[e["src"]].T @ dz, np.sum(dz, 0))
+      if spec[e["src"]]["op"] != "input":
+        acc(e["src"], r(dz @ r(np.asarray(params[li][0], dtype)).T))
+    elif e["op"] == "mul":
+      a, b = e["src"]
+      acc(a, r(g[i] * vals[b]))
+      acc(b, r(g[i] * vals[a]))
+    else:
+      for s in e["src"]:
+        acc(s, g[i])
+  return grads
+
+
+def graph_grads_emulated16(x, spec, params, margin, kind="fp16"):
+  """PRECISION MODEL of the fusion-tower step (test infrastructure), the counterpart of tower_grads_emulated16:
+  gradients of the SUM of hinges flow backwards in 16 bits, the 1/B is applied to the fp32 weight gradients."""
+  rnd = lambda a: round16(a, kind)
+  fwd = graph_forward(x, spec, params, np.float64, rnd)
+  e = fwd["l2_norm"]
+  E = e.reshape(-1, 3, e.shape[-1])
+  B = E.shape[0]
+  loss = hinge_loss(E, margin)
+  g = hinge_loss_grad(E, margin).reshape(-1, e.shape[-1]) * B
+  grads = graph_backward(fwd, spec, params, g, np.float64, rnd)
+  return {"l2_norm": e, "loss": loss, "grads": [(gw / B, gb / B) for gw, gb in grads]}
+
+
+# --------------------------------------------------------------------------- #
 # optimizer (train.py:82,108-113,146) -- TF1 AdamOptimizer                      #
 # --------------------------------------------------------------------------- #
 def exponential_decay(base_lr, global_step, decay_steps, decay_rate, staircase=True):
@@ -265,8 +397,9 @@ class OracleTrainer:
   Defaults = Trainer._build_model's constants (train.py:210-222): Adam, clip off, reg penalty 0, decay 0.96 / 1e6 steps."""
 
   def __init__(self, params, lr=1e-3, margin=0.8, decay_steps=1000000, decay=0.96, dtype=np.float64, optimizer="adam",
-               clip_norm=0.0, reg_penalty=0.0, l2_penalty=1e-8):
+               clip_norm=0.0, reg_penalty=0.0, l2_penalty=1e-8, spec=None):
     self.dtype = dtype
+    self.spec = spec            # op list of a fusion tower (fusion_spec); None = the fully_connected chain
     self.params = [(np.asarray(W, dtype).copy(), np.asarray(b, dtype).copy()) for W, b in params]
     self.m = [(np.zeros_like(W), np.zeros_like(b)) for W, b in self.params]
     self.v = [(np.zeros_like(W), np.zeros_like(b)) for W, b in self.params]
@@ -275,10 +408,15 @@ class OracleTrainer:
     self.global_step = 0
 
   def loss_and_grads(self, x_rows):
-    fwd = tower_forward(x_rows, self.params, dtype=self.dtype)
+    if self.spec is not None:
+      fwd = graph_forward(x_rows, self.spec, self.params, dtype=self.dtype)
+    else:
+      fwd = tower_forward(x_rows, self.params, dtype=self.dtype)
     E = fwd["l2_norm"].reshape(-1, 3, fwd["l2_norm"].shape[-1])
     loss = hinge_loss(E, self.margin, self.dtype)
     dE = hinge_loss_grad(E, self.margin, self.dtype).reshape(-1, E.shape[-1])
+    if self.spec is not None:
+      return fwd, loss, graph_backward(fwd, self.spec, self.params, dE, dtype=self.dtype)
     return fwd, loss, tower_backward(fwd, self.params, dE, dtype=self.dtype)
 
   def reg_loss(self):

@@ -548,3 +548,126 @@ def test_full_size_training_step_batch_65536_properties(cd):
   assert float(mined.float().mean().item()) > 0.9
   assert bool((d_an[mined] > pos[mined] - 2e-2).all().item())                            # d(a,n) > d(a,p) up to the fp16 selection noise
   assert bool(torch.isfinite(eng.w).all().item()) and float((eng.w - w0).abs().max().item()) <= 1.01e-3   # one Adam step
+
+
+# ---------------------------------------------------------------- fusion towers (models.py:65-243)
+def _fusion_engine(cd, name, **kw):
+  model = getattr(cd.models, name)()
+  g = cd.models.compile_graph(model.create_model(cd.models.placeholder(1628))["l2_norm"])
+  from cdml_b200 import fusion
+  spec = O.fusion_spec(name)
+  params = O.init_graph(spec, seed=2)
+  return fusion.GraphEngine(g["spec"], feature_size=1628, device=cd.dev, init_params=params, **kw), spec, params
+
+
+def test_ew16_and_rows_l2norm16_kernels(cd):
+  """cdml_ew16 (all eight joins, vector and 2-element paths, aliased output) and cdml_rows_l2norm16 against numpy."""
+  rng = np.random.RandomState(5)
+  for rows, cols, pitch in ((515, 256, 320), (33, 10, 14)):
+    a, b, c = (rng.standard_normal((rows, cols)).astype(np.float16) for _ in range(3))
+    def dev(m):
+      t = torch.zeros((rows, pitch), dtype=torch.float16, device=cd.dev)[:, :cols]
+      t.copy_(torch.as_tensor(m))
+      return t
+    A, Bm, C = a.astype(np.float64), b.astype(np.float64), c.astype(np.float64)
+    lk = lambda t: np.where(t > 0, 1.0, 0.2)
+    want = {cd.ops.EW_MUL: A * Bm, cd.ops.EW_ADD: A + Bm, cd.ops.EW_MUL_ADD_BOTH: A * Bm + A + Bm, cd.ops.EW_MASK: A * lk(Bm),
+            cd.ops.EW_MUL_ADD: A * Bm + A, cd.ops.EW_FMA: A * Bm + C, cd.ops.EW_MUL_ADD_MASK: (A * Bm + A) * lk(C),
+            cd.ops.EW_MUL_MASK: A * Bm * lk(C)}
+    for op, w in want.items():
+      out = cd.ops.ew16(op, dev(a), dev(b), dev(np.zeros_like(a)), c=dev(c), alpha=0.2)
+      assert np.array_equal(out.cpu().numpy(), w.astype(np.float16)), op     # fp32 math, one rounding: bit-exact
+    x = dev(a)
+    cd.ops.ew16(cd.ops.EW_ADD, x, dev(b), x)                                 # out aliases an input
+    assert np.array_equal(x.cpu().numpy(), (A + Bm).astype(np.float16))
+  y = (rng.standard_normal((300, 256)) * 3).astype(np.float16)
+  y[7] = 0
+  e = torch.empty((300, 256), dtype=torch.float32, device=cd.dev)
+  rinv = torch.empty((300,), dtype=torch.float32, device=cd.dev)
+  e16 = torch.empty((300, 256), dtype=torch.float16, device=cd.dev)
+  cd.ops.rows_l2norm16(dev_t(cd, y), e, rinv=rinv, e16=e16)
+  want = O.l2_normalize(y.astype(np.float64))
+  assert np.allclose(e.cpu().numpy(), want, atol=1e-6) and np.all(e.cpu().numpy()[7] == 0)
+  assert np.allclose(e16.cpu().numpy().astype(np.float64), want, atol=1e-3)
+  assert np.allclose(rinv.cpu().numpy()[:7], 1 / np.linalg.norm(y[:7].astype(np.float64), axis=1), rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["MultiplyNet", "MlpNet", "ResNet", "ResNetV2"])
+def test_fusion_tower_embeddings_within_1e3(cd, name):
+  eng, spec, params = _fusion_engine(cd, name)
+  feats = O.synth_features(3 * 130, 1628, 11)
+  e = eng.embed(dev_t(cd, feats)).cpu().numpy()
+  want = O.graph_forward(feats, spec, params)["l2_norm"]
+  assert e.shape == (390, 256) and np.allclose(np.linalg.norm(e, axis=1), 1.0, atol=1e-5)
+  assert rel_rows(e, want).max() < 1e-3                          # fp16 operands, fp32 accumulate: stated tolerance 1e-3
+
+
+@pytest.mark.parametrize("name", ["MultiplyNet", "MlpNet", "ResNet", "ResNetV2"])
+def test_fusion_tower_training_step_gradients_and_loss(cd, name):
+  G, B = 2000, 384
+  eng, spec, params = _fusion_engine(cd, name, base_lr=1e-3, margin=0.8)
+  feats = O.synth_features(G, 1628, 0)
+  trip = O.synth_triplets(B, G, 1)
+  tables = eng.prepare_table(dev_t(cd, feats))
+  x = O.flatten_triplets(O.gather_rows(feats, trip))
+  tr = O.OracleTrainer(params, lr=1e-3, margin=0.8, spec=spec)
+  _, loss0, grads = tr.loss_and_grads(x)
+  s = eng.train_step_indices(tables, dev_t(cd, trip)).cpu().numpy()
+  assert abs(s[0] / loss0["hinge_loss"] - 1) < 1e-3
+  assert abs(s[1] / loss0["pos_dist"].mean() - 1) < 1e-3 and abs(s[2] / loss0["neg_dist"].mean() - 1) < 1e-3
+  # same two gates as the chain tower: tight against the 16-bit precision model, 4e-2 against float64
+  model = O.graph_grads_emulated16(x, spec, params, 0.8, "fp16")
+  for l in range(eng.L):
+    gW, gb = eng.gW[l].cpu().numpy() / B, eng.gb[l].cpu().numpy() / B
+    assert _grad_rel(gW, model["grads"][l][0]) < 1e-2 and _grad_rel(gb, model["grads"][l][1]) < 1e-2, (name, l)
+    assert _grad_rel(gW, grads[l][0]) < 4e-2 and _grad_rel(gb, grads[l][1]) < 4e-2, (name, l)
+
+
+def test_resnet_lars_training_as_main_runs_it_and_checkpoint_roundtrip(cd, tmp_path):
+  """train.py main(): ResNet + tf.contrib.opt.LARSOptimizer, lr 1.0, margin 0.8 (train.py:354-364) through build_graph;
+  loss curve against the oracle, CUDA-graph replay == eager, checkpoint -> predict.load_engine -> same embeddings."""
+  G, B = 1500, 256
+  spec = O.fusion_spec("ResNet")
+  params = O.init_graph(spec, seed=2)
+  feats = O.synth_features(G, 1628, 0)
+  def build():
+    return cd.train.build_graph(cd.models.placeholder(1628), cd.models.ResNet(), base_learning_rate=1.0, margin=0.8,
+                                learning_rate_decay_examples=1000000, optimizer_class=cd.train.LARSOptimizer,
+                                clip_gradient_norm=0, regularization_penalty=0, init_params=params).engine
+  eng, eng2 = build(), build()
+  tables = eng.prepare_table(dev_t(cd, feats))
+  replay = eng2.capture_step(tables, B)
+  tr = O.OracleTrainer(params, lr=1.0, margin=0.8, optimizer="lars", spec=spec)
+  lg, lr_, lc = [], [], []
+  for t in range(1, 7):
+    trip = O.synth_triplets(B, G, t)
+    lg.append(float(eng.train_step_indices(tables, dev_t(cd, trip))[0].item()))
+    lr_.append(float(replay(dev_t(cd, trip))[0].item()))
+    lc.append(tr.step(O.flatten_triplets(O.gather_rows(feats, trip)))[0])
+  assert np.max(np.abs(np.array(lg) / np.array(lc) - 1)) < 2e-3, (lg, lc)
+  assert np.allclose(lg, lr_, rtol=1e-6)
+  for (W, b), (W2, b2), (Wo, bo) in zip(eng.get_params(), eng2.get_params(), tr.params):
+    assert np.array_equal(W, W2) and np.array_equal(b, b2)
+    assert _grad_rel(W, Wo) < 1e-3
+  prefix = cd.train.save_checkpoint(eng, str(tmp_path), 6, "ResNet")
+  z = np.load(prefix + ".npz")
+  assert "layer_visual_1/weights" in z.files and "layer_fusion_2/biases" in z.files
+  eng3 = cd.predict.load_engine(prefix)
+  q = dev_t(cd, feats[:300])
+  assert np.array_equal(eng3.embed(q).cpu().numpy(), eng.embed(q).cpu().numpy())
+
+
+def test_fusion_tower_mined_step_matches_oracle_selection(cd):
+  """ResNet step with in-batch semi-hard mining: the loss of the mined step equals the hinge of the oracle's selection on
+  the oracle's embeddings (mining is tower-independent: it sees only E and the guids)."""
+  eng, spec, params = _fusion_engine(cd, "ResNet", base_lr=1e-3, margin=0.8)
+  G, B = 3000, 512
+  feats = O.synth_features(G, 1628, 0)
+  trip = O.synth_triplets(B, G, 3)
+  tables = eng.prepare_table(dev_t(cd, feats))
+  s = eng.train_step_indices(tables, dev_t(cd, trip), mine=True).cpu().numpy()
+  E = O.graph_forward(O.flatten_triplets(O.gather_rows(feats, trip)), spec, params)["l2_norm"]
+  rows, _ = O.mine_semihard(E, trip, 0.8)
+  a, p, n = E[0::3], E[1::3], E[np.asarray(rows)]
+  want = np.maximum(((a - p) ** 2).sum(-1) - ((a - n) ** 2).sum(-1) + 0.8, 0).mean()
+  assert np.isfinite(s).all() and abs(s[0] / want - 1) < 1e-2       # a few fp16-ranked selections may differ (near ties)

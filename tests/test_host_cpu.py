@@ -65,8 +65,8 @@ def test_model_plugin_interface(lib):
   assert wide["dims"] == [2048, 2048, 2048, 2048, 256]
   with pytest.raises(StopIteration):
     utils.find_class_by_name("VedeNet", [models])            # the reference's broken default
-  with pytest.raises(NotImplementedError):
-    models.ResNet().create_model(models.placeholder(1628))
+  with pytest.raises(NotImplementedError):                   # a fusion tower is a graph, not a chain
+    models.compile_chain(models.ResNet().create_model(models.placeholder(1628))["l2_norm"])
   with pytest.raises(NotImplementedError):                   # topology outside the hot path
     models.compile_chain(models.fully_connected(models.placeholder(8), 4))
 
@@ -241,3 +241,24 @@ def test_two_rank_protocol_over_gloo(tmp_path):
   outs = [p.communicate(timeout=240)[0] for p in procs]
   for r, (p, o) in enumerate(zip(procs, outs)):
     assert p.returncode == 0 and ("rank %d ok" % r) in o, o
+
+
+def test_fusion_towers_compile_to_the_oracle_op_lists():
+  """The product's recorder (models.MultiplyNet / MlpNet / ResNet / ResNetV2 -> compile_graph) must produce the op list
+  the oracle restates from models.py:65-243; DenseNet is not constructible in the reference and says so."""
+  import cdml_b200  # noqa: F401
+  from cdml_b200 import models
+  from oracle import cdml_oracle as O
+  keys = {"input": ("lo", "hi"), "fc": ("src", "out", "bias_init", "alpha", "name"), "mul": ("src",), "add": ("src",),
+          "l2norm": ("src",)}
+  for name in ("MultiplyNet", "MlpNet", "ResNet", "ResNetV2"):
+    g = models.compile_graph(getattr(models, name)().create_model(models.placeholder(1628))["l2_norm"])
+    want = O.fusion_spec(name)
+    assert g["F"] == 1628 and g["D"] == 256 and len(g["spec"]) == len(want)
+    for got, w in zip(g["spec"], want):
+      assert got["op"] == w["op"] and all(got[k] == w[k] for k in keys[w["op"]]), (name, got, w)
+  with pytest.raises(NotImplementedError):
+    models.DenseNet().create_model(models.placeholder(1628))
+  # a plain chain still compiles as a graph (the GraphEngine then fuses its last layer with the output l2norm)
+  g = models.compile_graph(models.VNet().create_model(models.placeholder(1500))["l2_norm"])
+  assert [e["op"] for e in g["spec"]] == ["input", "fc", "fc", "l2norm"]

@@ -198,3 +198,65 @@ def test_semihard_mining_definition():
       cand = [3 * j + c for j in range(B) for c in (1, 2) if g[j, c] not in (g[i, 0], g[i, 1])]
       dc = ((A[i] - E[cand]) ** 2).sum(-1)
       assert d_an[i] <= dc[(dc > dp[i]) & (dc < dp[i] + 0.8)].min() + 1e-12
+
+
+# ---------------------------------------------------------------- fusion towers (models.py:65-243)
+def _shrunk(spec):
+  """Same topology, toy widths (visual 30 / doc 12 columns) so the float64 checks run in milliseconds."""
+  out = []
+  for e in spec:
+    e = dict(e)
+    if e["op"] == "input":
+      e["lo"], e["hi"] = (0, 30) if e["lo"] == 0 else (30, 42)
+    elif e["op"] == "fc":
+      e["out"] = {5000: 56, 400: 24, 600: 32, 256: 16}[e["out"]]
+    out.append(e)
+  return out
+
+
+@pytest.mark.parametrize("name", ["MultiplyNet", "MlpNet", "ResNet", "ResNetV2"])
+def test_fusion_graph_backward_matches_torch_autograd(name):
+  """The oracle's op-list reverse sweep (graph_backward) against torch autograd of the same forward, float64."""
+  import torch
+  spec = _shrunk(O.fusion_spec(name))
+  params = O.init_graph(spec, seed=3, dtype=np.float64)
+  x = np.random.RandomState(0).rand(12, 42)
+  fwd = O.graph_forward(x, spec, params)
+  E = fwd["l2_norm"].reshape(-1, 3, 16)
+  grads = O.graph_backward(fwd, spec, params, O.hinge_loss_grad(E, 0.8).reshape(-1, 16))
+  tp = [(torch.tensor(W, requires_grad=True), torch.tensor(b, requires_grad=True)) for W, b in params]
+  xt, vals, li = torch.tensor(x), [], 0
+  l2n = lambda y: y * torch.rsqrt(torch.clamp((y * y).sum(-1, keepdim=True), min=1e-12))
+  for e in spec:
+    if e["op"] == "input":
+      vals.append(l2n(xt[:, e["lo"]:e["hi"]]))
+    elif e["op"] == "fc":
+      W, b = tp[li]
+      li += 1
+      vals.append(torch.nn.functional.leaky_relu(vals[e["src"]] @ W + b, 0.2))
+    elif e["op"] == "mul":
+      vals.append(vals[e["src"][0]] * vals[e["src"][1]])
+    elif e["op"] == "add":
+      vals.append(sum(vals[s] for s in e["src"]))
+    else:
+      vals.append(l2n(vals[e["src"]]))
+  Et = vals[-1].reshape(-1, 3, 16)
+  loss = torch.clamp(((Et[:, 0] - Et[:, 1]) ** 2).sum(-1) - ((Et[:, 0] - Et[:, 2]) ** 2).sum(-1) + 0.8, min=0).mean()
+  loss.backward()
+  assert np.allclose(vals[-1].detach().numpy(), fwd["l2_norm"], atol=1e-12)
+  assert abs(float(loss.detach()) - O.hinge_loss(E, 0.8)["hinge_loss"]) < 1e-12
+  for (gW, gb), (W, b) in zip(grads, tp):
+    assert np.allclose(gW, W.grad.numpy(), atol=1e-12) and np.allclose(gb, b.grad.numpy(), atol=1e-12)
+
+
+def test_fusion_spec_shapes_follow_models_py():
+  """Widths stated in models.py: visual 1500 -> 5000 -> 256 (:81-83), doc 128 -> 400 -> 256 (:86-88), MLP 600 (:118),
+  residual layers 256 (:149-151); biases 0.1."""
+  for name, shapes in (("MultiplyNet", [(1500, 5000), (5000, 256), (128, 400), (400, 256)]),
+                       ("MlpNet", [(1500, 5000), (5000, 256), (128, 400), (400, 256), (256, 600), (600, 256)]),
+                       ("ResNet", [(1500, 5000), (5000, 256), (128, 400), (400, 256), (256, 256), (256, 256)]),
+                       ("ResNetV2", [(1500, 5000), (5000, 256), (1500, 256), (128, 400), (400, 256), (128, 256), (256, 256),
+                                     (256, 256)])):
+    params = O.init_graph(O.fusion_spec(name), seed=2)
+    assert [W.shape for W, _ in params] == shapes
+    assert all(np.all(b == np.float32(0.1)) for _, b in params)
