@@ -37,6 +37,10 @@ _SIGNATURES = {
                              c_float, c_float, c_float, c_float, _P, c_int, _P]),
   "cdml_ew16": (c_int, [_P, c_int, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int, c_float, c_int, _P]),
   "cdml_rows_l2norm16": (c_int, [_P, _P, c_int64, c_int, c_int64, c_float, c_int, _P, c_int64, _P, _P, c_int64, _P]),
+  "cdml_desim_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
+  "cdml_desim": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P, c_int64, c_int, c_int64, c_int64, c_float, c_int, _P, _P,
+                         c_int64, _P]),
+  "cdml_desim_simple": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, _P]),
   "cdml_cast16": (c_int, [_P, _P, c_int64, _P, c_int, _P]),
   "cdml_fill_column16": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_float, c_int, _P]),
   "cdml_mine_semihard": (c_int, [_P, _P, c_int64, c_int, _P, c_int64, _P, c_int64, c_int, c_float, _P, _P, _P]),

@@ -1,0 +1,195 @@
+// De-similarity post-filter of the KNN lists (faiss_knn.py:134-244: desim, fliter_fI, iter_desim_mp) -- integer / set work,
+// HBM-bound.  The reference sweeps the columns of eI with 81 x Pool(22) numpy passes over a +1-shifted copy; rows are
+// independent, so here ONE WARP owns a row of eI in registers and walks its columns:
+//
+//   prepare:  F[v, j] = fI[v, j] if fD[v, j] <= threshold and fI[v, j] != v and 0 <= fI[v, j] < 2^31 else -1   (j < f_end)
+//             int32, row pitch fw_pad -- the table every pivot gathers from (fliter_fI, faiss_knn.py:146-155)
+//   rows:     for c = 0 .. ke-1: v = eI[r, c]; if alive: every later alive entry that occurs in F[v, :] is dropped (-1);
+//             finally the row's own id is dropped (faiss_knn.py:236-238).
+//
+// The only HBM traffic that matters is the gather of F rows (ke x fw_pad x 4 bytes per eI row, random rows): pivots are
+// fetched kAhead columns ahead of their use (an entry can only change to "dropped", so a prefetched row is either right
+// or ignored), which keeps kAhead x 128 bytes in flight per warp.
+#include "../../include/cdml.h"
+#include "ctx.cuh"
+
+namespace cdml {
+
+constexpr int kDesimWarps = 8;
+constexpr int kAhead = 4;
+
+__global__ void __launch_bounds__(256)
+desim_prepare_kernel(const int64_t* __restrict__ fI, const float* __restrict__ fD, int64_t nf, int kf, int64_t ld_fi,
+                     int64_t ld_fd, float threshold, int fw, int fw_pad, int32_t* __restrict__ F) {
+  const int64_t total = nf * fw_pad;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t v = i / fw_pad;
+    const int j = static_cast<int>(i - v * fw_pad);
+    int32_t out = -1;
+    if (j < fw) {
+      const int64_t id = fI[v * ld_fi + j];
+      const bool far = fD != nullptr && fD[v * ld_fd + j] > threshold;      // NaN distances are kept, like `fD > thr`
+      if (!far && id != v && id >= 0 && id < (1ll << 31)) out = static_cast<int32_t>(id);
+    }
+    F[i] = out;
+  }
+}
+
+// E = entries of the row per lane (ke <= 32 E), FC = 32-wide chunks of an F row (fw <= 32 FC).
+template <int E, int FC>
+__global__ void __launch_bounds__(kDesimWarps * 32)
+desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_e, const int32_t* __restrict__ F,
+                  int64_t nf, int fw, int fw_pad, int64_t* __restrict__ out, int64_t ld_o, int32_t* flags) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kDesimWarps + warp; r < n;
+       r += static_cast<int64_t>(gridDim.x) * kDesimWarps) {
+    int32_t ent[E];       // alive entry id, -1 = dropped / padding, -2 = not a pivot (id outside the feature table)
+    int64_t raw[E];
+    bool changed[E];
+#pragma unroll
+    for (int t = 0; t < E; ++t) {
+      const int c = lane + 32 * t;
+      raw[t] = c < ke ? eI[r * ld_e + c] : -1;
+      changed[t] = false;
+      if (raw[t] < 0) ent[t] = -1;
+      else if (raw[t] >= nf) {           // the reference would raise IndexError in fI[col_eI] (faiss_knn.py:179)
+        ent[t] = -2;
+        atomicOr(flags, 2);
+      } else ent[t] = static_cast<int32_t>(raw[t]);
+    }
+    auto entry_at = [&](int c) -> int32_t {   // warp-uniform read of column c
+      int32_t v = -1;
+#pragma unroll
+      for (int t = 0; t < E; ++t)
+        if ((c >> 5) == t) v = __shfl_sync(0xffffffffu, ent[t], c & 31);
+      return v;
+    };
+    auto fetch = [&](int c, int32_t (&buf)[FC]) {
+      const int32_t v = c < ke ? entry_at(c) : -1;
+#pragma unroll
+      for (int q = 0; q < FC; ++q) {
+        const int j = lane + 32 * q;
+        buf[q] = (v >= 0 && j < fw) ? __ldg(F + static_cast<int64_t>(v) * fw_pad + j) : -1;
+      }
+    };
+    int32_t fbuf[kAhead][FC];
+#pragma unroll
+    for (int p = 0; p < kAhead; ++p) fetch(p, fbuf[p]);
+    for (int c0 = 0; c0 < ke; c0 += kAhead) {
+#pragma unroll
+      for (int p = 0; p < kAhead; ++p) {
+        const int c = c0 + p;
+        if (c < ke) {
+          const int32_t v = entry_at(c);
+          if (v >= 0) {
+#pragma unroll
+            for (int q = 0; q < FC; ++q) {
+              const unsigned live = __ballot_sync(0xffffffffu, fbuf[p][q] >= 0);
+              for (unsigned m = live; m != 0; m &= m - 1) {
+                const int32_t f = __shfl_sync(0xffffffffu, fbuf[p][q], __ffs(m) - 1);
+#pragma unroll
+                for (int t = 0; t < E; ++t)
+                  if (ent[t] == f && lane + 32 * t > c) ent[t] = -1, changed[t] = true;
+              }
+            }
+          }
+        }
+        fetch(c + kAhead, fbuf[p]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < E; ++t) {
+      const int c = lane + 32 * t;
+      if (c < ke) {
+        int64_t w = raw[t];
+        if (changed[t] || w == r) w = -1;
+        if (w < 0) w = -1;
+        out[r * ld_o + c] = w;
+      }
+    }
+  }
+}
+
+// faiss_knn.desim (faiss_knn.py:134-143): eI[i, j] = -1 wherever eI[i, j] occurs in row i of fI.
+__global__ void __launch_bounds__(256)
+desim_simple_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_e, const int64_t* __restrict__ fI, int kf,
+                    int64_t ld_f, int64_t* __restrict__ out, int64_t ld_o) {
+  const int64_t total = n * ke;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / ke;
+    const int c = static_cast<int>(i - r * ke);
+    const int64_t v = eI[r * ld_e + c];
+    bool hit = false;
+    for (int j = 0; j < kf; ++j) hit |= fI[r * ld_f + j] == v;
+    out[r * ld_o + c] = hit ? -1 : v;
+  }
+}
+
+template <int E>
+static void launch_rows(int fc, int grid, cudaStream_t st, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int32_t* F,
+                        int64_t nf, int fw, int fw_pad, int64_t* out, int64_t ld_o, int32_t* flags) {
+  if (fc == 1) desim_rows_kernel<E, 1><<<grid, kDesimWarps * 32, 0, st>>>(eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o, flags);
+  else desim_rows_kernel<E, 2><<<grid, kDesimWarps * 32, 0, st>>>(eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o, flags);
+}
+
+static inline int desim_width(int kf, int f_end) { return f_end < kf ? f_end : kf; }
+static inline int pad32(int w) { return (w + 31) / 32 * 32; }
+
+}  // namespace cdml
+
+extern "C" {
+
+int64_t cdml_desim_workspace_bytes(int64_t nf, int kf, int f_end) {
+  if (nf <= 0 || kf <= 0 || f_end <= 0) return 0;
+  return nf * cdml::pad32(cdml::desim_width(kf, f_end)) * static_cast<int64_t>(sizeof(int32_t));
+}
+
+int cdml_desim(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int64_t* fI, const float* fD,
+               int64_t nf, int kf, int64_t ld_fi, int64_t ld_fd, float fD_threshold, int f_end, void* workspace,
+               int64_t* out, int64_t ld_out, void* stream) {
+  using namespace cdml;
+  CDML_REQUIRE(ctx && eI && fI && out && workspace, "cdml_desim: NULL argument");
+  CDML_REQUIRE(n >= 0 && ke > 0 && nf > 0 && kf > 0 && f_end > 0 && ld_e >= ke && ld_out >= ke && ld_fi >= kf &&
+               (fD == nullptr || ld_fd >= kf), "cdml_desim: bad geometry");
+  CDML_REQUIRE(ke <= 256, "cdml_desim: at most 256 neighbours per row (got %d; the reference uses 81)", ke);
+  CDML_REQUIRE(nf < (1ll << 31), "cdml_desim: feature table of %lld rows needs 64-bit ids", (long long)nf);
+  const int fw = desim_width(kf, f_end), fw_pad = pad32(fw);
+  CDML_REQUIRE(fw <= 64, "cdml_desim: at most 64 feature neighbours per pivot (got %d; the reference uses 31)", fw);
+  if (n == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int32_t* F = static_cast<int32_t*>(workspace);
+  {
+    const int64_t blocks = (nf * fw_pad + 255) / 256, cap = static_cast<int64_t>(ctx->num_sms) * 8;
+    desim_prepare_kernel<<<static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st>>>(fI, fD, nf, kf, ld_fi, ld_fd,
+                                                                                      fD_threshold, fw, fw_pad, F);
+    CDML_CHECK_CUDA(cudaGetLastError());
+  }
+  const int64_t blocks = (n + kDesimWarps - 1) / kDesimWarps, cap = static_cast<int64_t>(ctx->num_sms) * 8;
+  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  const int fc = fw_pad / 32;
+  const int e = (ke + 31) / 32;
+  if (e <= 1) launch_rows<1>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
+  else if (e == 2) launch_rows<2>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
+  else if (e == 3) launch_rows<3>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
+  else if (e == 4) launch_rows<4>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
+  else launch_rows<8>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cdml_desim_simple(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int64_t* fI, int kf,
+                      int64_t ld_f, int64_t* out, int64_t ld_out, void* stream) {
+  using namespace cdml;
+  CDML_REQUIRE(ctx && eI && fI && out, "cdml_desim_simple: NULL argument");
+  CDML_REQUIRE(n >= 0 && ke > 0 && kf > 0 && ld_e >= ke && ld_out >= ke && ld_f >= kf, "cdml_desim_simple: bad geometry");
+  if (n == 0) return 0;
+  const int64_t blocks = (n * ke + 255) / 256, cap = static_cast<int64_t>(ctx->num_sms) * 8;
+  desim_simple_kernel<<<static_cast<int>(blocks < cap ? blocks : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      eI, n, ke, ld_e, fI, kf, ld_f, out, ld_out);
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -68,6 +68,7 @@ class TowerEngine:
     self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
     self.F = self.dims[0]
     self.F_pad = _pad64(self.F + 1)     # always one spare column: it carries the ones of [x | 1] (bias gradient row)
+    self.loss_scale = 1.0          # multiplies the 16-bit backward signal; divided out inside the optimizer kernel's grad_scale
     self.fused_bias_grad = True    # bias gradients as an extra row of the weight-gradient GEMMs (no colsum kernels)
     self._ones_checked = {}
 
@@ -297,7 +298,7 @@ class TowerEngine:
       torch.distributed.all_reduce(self.g, group=self.pg)  # NCCL sum over ranks, one flat buffer
     ops.adam_prepare(self.step_counter, self.scalars, self.base_lr, self.lr_decay_steps, self.lr_decay, True,
                      self.beta1, self.beta2)
-    scale = 1.0 / (B_local * self.world)
+    scale = 1.0 / (B_local * self.world * self.loss_scale)
     plain_adam = self.opt_kind == ops.OPT_ADAM and self.clip_norm <= 0 and self.wd_reg == 0
     for l in range(self.L):
       for i, (w, g, w16, wd) in enumerate(((self.W[l], self.gW[l], self.W16[l], self.wd_reg), (self.b[l], self.gb[l], None, 0.0))):

@@ -2,7 +2,8 @@
 `write_process` / `write_knn` (:267-305), loaders (:52-66) and `main` (:359-402), same names / arguments / flags /
 file formats.  `faiss.Index*.add/search` is replaced by libcdml's exact flat index (tensor-core candidate pass +
 fp32 re-rank); with WORLD_SIZE>1 the index is row-sharded over the ranks and the per-shard top-k are all-gathered
-and merged on the GPU.  The de-similarity post-filter and cross_knn are SURVEY 8(f) rank 2 (next)."""
+and merged on the GPU.  The de-similarity post-filter (`desim`, `fliter_fI`, `iter_desim_mp`, faiss_knn.py:134-244) runs as
+libcdml's cdml_desim kernels; `strict_knn` / `cross_knn` (faiss_knn.py:308-351) compose them with calc_knn."""
 import json
 import multiprocessing as mp
 import os
@@ -25,6 +26,10 @@ if "embedding_file" not in FLAGS:
   flags.DEFINE_integer("nearest_num", 81, "neighbours per embedding (incl. the query itself)")
   flags.DEFINE_integer("desim_nearest_num", 26, "neighbours per raw feature vector (de-similarity)")
   flags.DEFINE_string("knn_result", "serving_dir/knn_result/newresult", "where knn results are written")
+  flags.DEFINE_string("knn_mode", "knn", "knn: calc_knn + knn_split* files (what cdml_run.sh:147 uploads) | strict: "
+                      "+ de-similarity against the raw-feature KNN (strict_knn, faiss_knn.py:308-322) | cross: video<->doc "
+                      "cross search + de-similarity (cross_knn, faiss_knn.py:325-351; the reference's main at HEAD)")
+  flags.DEFINE_integer("doc_location", 343455, "first doc row of the embeddings (hard-coded in the reference, faiss_knn.py:389)")
 
 DECODE_MAP = {}
 
@@ -115,6 +120,78 @@ def calc_knn(embeddings, q_embeddings=None, nearest_num=51, l2_norm=True, M=80, 
   return D, I
 
 
+# ============================ de-similarity  ============================
+def desim(eI, fI):
+  """eI[i, j] = -1 wherever eI[i, j] occurs in row i of fI (faiss_knn.py:134-143); returns the filtered copy."""
+  dev = _device()
+  e = torch.as_tensor(np.ascontiguousarray(eI, np.int64)).to(dev)
+  f = torch.as_tensor(np.ascontiguousarray(fI, np.int64)).to(dev)
+  return ops.desim_simple(e, f).cpu().numpy()
+
+
+def fliter_fI(fI, fD, fD_threshold):
+  """Feature neighbours farther than fD_threshold, and the row itself, become -1 (faiss_knn.py:146-155).  iter_desim_mp
+  applies this inside its own kernel; this entry point filters a table on its own (desim of an empty eI column)."""
+  dev = _device()
+  f = torch.as_tensor(np.ascontiguousarray(fI, np.int64)).to(dev)
+  d = torch.as_tensor(np.ascontiguousarray(fD, np.float32)).to(dev)
+  return ops.filter_fI(f, d, fD_threshold).cpu().numpy().astype(np.int64)
+
+
+def iter_desim_mp(eI, fI, fD, fD_threshold=1.4, fI_end=31, process_num=22, as_device=False):
+  """Greedy de-similarity of the KNN lists eI against the raw-feature KNN (fI, fD) (faiss_knn.py:187-244): per row, left
+  to right, a surviving entry removes every later entry that is one of its first fI_end near feature neighbours; the
+  row's own id is removed last.  Returns int64 [n,ke] with removed entries -1.  `process_num` is accepted and ignored
+  (one warp per row on the GPU instead of a process pool); unlike the reference, the inputs are not shifted in place
+  (faiss_knn.py:161-162)."""
+  begin = time.time()
+  dev = _device()
+  to_dev = lambda a, dt: a.to(dev) if torch.is_tensor(a) else torch.as_tensor(np.ascontiguousarray(a, dt)).to(dev)
+  out = ops.desim(to_dev(eI, np.int64), to_dev(fI, np.int64), to_dev(fD, np.float32), fD_threshold, fI_end)
+  if ops.poll_errors(out) & 2:
+    raise IndexError("iter_desim_mp: eI holds ids beyond the feature KNN table (%d rows)" % fI.shape[0])
+  if not as_device:
+    out = out.cpu().numpy()
+  print('faiss_knn iter_desim_mp cost: ', time.time() - begin)
+  return out
+
+
+def strict_knn(embeddings, fI, fD, knn_result=None, nearest_num=None, decode_map=None, process_group=None):
+  """KNN of the embeddings, de-similarised against the raw-feature KNN, written as `strict_knn*` (faiss_knn.py:308-322)."""
+  knn_result = FLAGS.knn_result if knn_result is None else knn_result
+  nearest_num = FLAGS.nearest_num if nearest_num is None else nearest_num
+  strictD, strictI = calc_knn(embeddings, nearest_num=nearest_num, process_group=process_group)
+  strictI_desim = iter_desim_mp(strictI, fI, fD)
+  if process_group is None or torch.distributed.get_rank(process_group) == 0:
+    np.save(knn_result + '/strictD.npy', strictD)
+    np.save(knn_result + '/strictI.npy', strictI)
+    np.save(knn_result + '/strictI_desim.npy', strictI_desim)
+    write_knn(knn_result, split_num=10, D=strictD, I=strictI_desim, prefix='strict_knn', decode_map=decode_map)
+  return strictD, strictI_desim
+
+
+def cross_knn(embeddings, doc_location, fI, fD, knn_result=None, nearest_num=None, decode_map=None, process_group=None):
+  """Video rows [0, doc_location) search the doc rows and vice versa; the joined lists are de-similarised and written as
+  `cross_knn*` (faiss_knn.py:325-351).  The reference at HEAD writes the un-filtered, +1-shifted crossI (its
+  own TODO at faiss_knn.py:349); this writes crossI_desim, which is what it saves as crossI_desim.npy."""
+  knn_result = FLAGS.knn_result if knn_result is None else knn_result
+  nearest_num = FLAGS.nearest_num if nearest_num is None else nearest_num
+  video_vec = embeddings[:doc_location]
+  doc_vec = embeddings[doc_location:]
+  vdD, vdI = calc_knn(doc_vec, video_vec, nearest_num=nearest_num, process_group=process_group)
+  vdI = np.where(vdI >= 0, vdI + doc_location, vdI)
+  dvD, dvI = calc_knn(video_vec, doc_vec, nearest_num=nearest_num, process_group=process_group)
+  crossI = np.concatenate((vdI, dvI), axis=0)
+  crossD = np.concatenate((vdD, dvD), axis=0)
+  crossI_desim = iter_desim_mp(crossI, fI, fD)
+  if process_group is None or torch.distributed.get_rank(process_group) == 0:
+    np.save(knn_result + '/crossD.npy', crossD)
+    np.save(knn_result + '/crossI.npy', crossI)
+    np.save(knn_result + '/crossI_desim.npy', crossI_desim)
+    write_knn(knn_result, split_num=10, D=crossD, I=crossI_desim, prefix='cross_knn', decode_map=decode_map)
+  return crossD, crossI, crossI_desim
+
+
 # ============================ write result ============================
 def format_rows(begin_index, D, I, decode_map):
   """Lines '<query_guid>,<nbr_guid>#<dist><...' ; column 0 skipped; a neighbour is kept iff idx > 0 and
@@ -175,6 +252,23 @@ def main(args):
       pg = torch.distributed.group.WORLD
     embeddings = load_embedding(FLAGS.embedding_file)
     print("faiss_knn embedding_file shape", embeddings.shape)
+    if FLAGS.knn_mode in ("strict", "cross"):
+      features = load_embedding(FLAGS.pred_feature_file)
+      desim_nearest_num = min(FLAGS.desim_nearest_num, FLAGS.nearest_num)                    # faiss_knn.py:376
+      fD, fI = calc_knn(features, nearest_num=desim_nearest_num, l2_norm=True, process_group=pg)
+      if pg is None or torch.distributed.get_rank() == 0:
+        np.save(FLAGS.knn_result + '/fD.npy', fD)
+        np.save(FLAGS.knn_result + '/fI.npy', fI)
+      if FLAGS.knn_mode == "cross":
+        if not 0 < FLAGS.doc_location < embeddings.shape[0]:                                 # faiss_knn.py:390
+          raise ValueError("doc_location %d outside (0, %d)" % (FLAGS.doc_location, embeddings.shape[0]))
+        cross_knn(embeddings, FLAGS.doc_location, fI, fD, process_group=pg)
+      else:
+        strict_knn(embeddings, fI, fD, process_group=pg)
+      if pg is None or torch.distributed.get_rank() == 0:
+        shutil.copyfile(FLAGS.decode_map_file, FLAGS.knn_result + '/decode_map.json')
+      print("faiss_knn cost: %fs" % (time.time() - global_begin))
+      return
     D, I = calc_knn(embeddings, nearest_num=FLAGS.nearest_num, process_group=pg)
     if pg is None or torch.distributed.get_rank() == 0:
       np.save(FLAGS.knn_result + '/strictD.npy', D)

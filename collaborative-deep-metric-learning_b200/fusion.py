@@ -39,7 +39,7 @@ def _widths(spec):
 
 class GraphEngine(TowerEngine):
 
-  def __init__(self, spec, feature_size=None, device=None, dtype16=F16, seed=2, init_params=None, **kw):
+  def __init__(self, spec, feature_size=None, device=None, dtype16=F16, seed=2, init_params=None, loss_scale=256.0, **kw):
     spec = [dict(e) for e in spec]
     if not spec or spec[-1]["op"] != "l2norm" or any(e["op"] == "l2norm" for e in spec[:-1]):
       raise ValueError("the op list must end with its only l2norm (the model output)")
@@ -79,6 +79,10 @@ class GraphEngine(TowerEngine):
     self.fused_out = last if (spec[last]["op"] == "fc" and len(self.consumers[last]) == 1 and D <= 256) else None
     super().__init__([F, D], device=device, dtype16=dtype16, seed=seed, init_params=init_params,
                      layer_shapes=[(self.widths[spec[i]["src"]], self.widths[i]) for i in self.fcs], **kw)
+    # The residual sums make |y| of the output large (rinv ~ 0.08 on an untrained ResNet), so the backward signal of the
+    # sum of hinges sits at 1e-4..1e-3 -- around fp16's smallest normal 6.1e-5.  A power-of-two loss scale lifts it into the
+    # normal range (headroom: |g| <= 4, rinv of order 1 -> <= ~1e4 of 65504); the optimizer kernel divides it out again.
+    self.loss_scale = float(loss_scale)
     self.names = [spec[i].get("name") or ("fully_connected" if l == 0 else "fully_connected_%d" % l)
                   for l, i in enumerate(self.fcs)]
 
@@ -216,7 +220,7 @@ class GraphEngine(TowerEngine):
     if mine:
       neg_row, _ = ops.mine_semihard(e16, buf["e"], guid, B, self.margin, want_dist=False)
     # loss + backward through the output L2-norm (and the last leaky when the output fc is fused)
-    ops.triplet_hinge(buf["e"], B, self.margin, neg_row=neg_row, grad_scale=1.0, rinv=buf["rinv"],
+    ops.triplet_hinge(buf["e"], B, self.margin, neg_row=neg_row, grad_scale=self.loss_scale, rinv=buf["rinv"],
                       leaky_alpha=self.alpha if self.fused_out is not None else 1.0, dz16=buf["dzo"],
                       workspace=buf["G"], out=buf["loss"])
     self.backward_rows(xsegs, R, buf, input_ones)

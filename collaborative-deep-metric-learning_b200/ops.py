@@ -221,6 +221,47 @@ def fill_column16(X16, col, value):
                                        dtype16_of(X16), stream_ptr()))
 
 
+def desim(eI, fI, fD=None, fD_threshold=1.4, f_end=31, out=None):
+  """De-similarity filter of KNN lists (cdml_desim; faiss_knn.py:187-244).  eI [n,ke] int64, fI [nf,kf] int64, fD [nf,kf]
+  fp32 device tensors -> int64 [n,ke] with dropped entries -1."""
+  if eI.dtype != torch.int64 or fI.dtype != torch.int64 or (fD is not None and fD.dtype != torch.float32):
+    raise TypeError("desim: eI / fI must be int64, fD float32")
+  n, ke = eI.shape
+  nf, kf = fI.shape
+  lib = _lib.load()
+  ws = torch.empty((max(int(lib.cdml_desim_workspace_bytes(nf, kf, int(f_end))), 4),), dtype=torch.uint8, device=eI.device)
+  if out is None:
+    out = torch.empty_like(eI)
+  _count(2)
+  check(lib.cdml_desim(_ctx(eI), ptr(eI), n, ke, _row_major_2d(eI, "eI"), ptr(fI), ptr(fD), nf, kf, _row_major_2d(fI, "fI"),
+                       _row_major_2d(fD, "fD") if fD is not None else 0, float(fD_threshold), int(f_end), ptr(ws), ptr(out),
+                       _row_major_2d(out, "out"), stream_ptr()))
+  return out
+
+
+def filter_fI(fI, fD, fD_threshold=1.4):
+  """fliter_fI (faiss_knn.py:146-155) on its own: the int32 table cdml_desim gathers from ([nf,kf] view)."""
+  nf, kf = fI.shape
+  probe = torch.full((1, 1), -1, dtype=torch.int64, device=fI.device)          # a row without pivots: only `prepare` matters
+  lib = _lib.load()
+  ws = torch.empty((int(lib.cdml_desim_workspace_bytes(nf, kf, kf)),), dtype=torch.uint8, device=fI.device)
+  _count(2)
+  check(lib.cdml_desim(_ctx(fI), ptr(probe), 1, 1, 1, ptr(fI), ptr(fD), nf, kf, _row_major_2d(fI, "fI"),
+                       _row_major_2d(fD, "fD"), float(fD_threshold), kf, ptr(ws), ptr(probe), 1, stream_ptr()))
+  return ws.view(torch.int32).view(nf, -1)[:, :kf]          # int32 ids, -1 = filtered
+
+
+def desim_simple(eI, fI, out=None):
+  """out[i,j] = -1 where eI[i,j] occurs in fI[i,:] (cdml_desim_simple; faiss_knn.py:134-143)."""
+  n, ke = eI.shape
+  if out is None:
+    out = torch.empty_like(eI)
+  _count(1)
+  check(_lib.load().cdml_desim_simple(_ctx(eI), ptr(eI), n, ke, _row_major_2d(eI, "eI"), ptr(fI), fI.shape[1],
+                                      _row_major_2d(fI, "fI"), ptr(out), _row_major_2d(out, "out"), stream_ptr()))
+  return out
+
+
 def mean_pair_dist(V, pairs):
   out = torch.empty((1,), dtype=torch.float32, device=V.device)
   pairs = pairs.to(torch.int64).contiguous()

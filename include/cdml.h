@@ -169,6 +169,22 @@ int cdml_knn_merge(cdml_ctx* ctx, const float* Dg, const int64_t* Ig, int G, int
 int cdml_mean_pair_dist(cdml_ctx* ctx, const float* V, int64_t ld, int D, const int64_t* pairs, int64_t P,
                         float* out_mean, void* stream);
 
+/* ---- de-similarity post-filter of the KNN lists -- replaces faiss_knn.iter_desim_mp (faiss_knn.py:187-244: fliter_fI,
+ *      add_invalid_row, 81 x Pool(22) column sweeps of desim_progress) and faiss_knn.desim (faiss_knn.py:134-143).
+ *      eI [n,ke] int64 embedding-KNN ids (-1 = padding), fI / fD [nf,kf] the raw-feature KNN (ids int64, squared distances
+ *      fp32; fD may be NULL = no distance filter).  Per row, left to right: an entry still alive is a pivot v; every LATER
+ *      entry found among v's first min(kf,f_end) feature neighbours (those with fD <= threshold, other than v itself) is
+ *      dropped; finally the row's own id is dropped.  out [n,ke] int64 = eI with dropped entries -1 (may alias eI).
+ *      workspace: cdml_desim_workspace_bytes(nf,kf,f_end) device bytes.  ke <= 256, min(kf,f_end) <= 64, nf < 2^31.
+ *      An id >= nf (IndexError in the reference) is left untouched and sets error flag bit 1 (cdml_ctx_poll_errors). */
+int64_t cdml_desim_workspace_bytes(int64_t nf, int kf, int f_end);
+int cdml_desim(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int64_t* fI, const float* fD,
+               int64_t nf, int kf, int64_t ld_fi, int64_t ld_fd, float fD_threshold, int f_end, void* workspace,
+               int64_t* out, int64_t ld_out, void* stream);
+/* out[i,j] = -1 where eI[i,j] occurs in fI[i,:], else eI[i,j]  (faiss_knn.desim). */
+int cdml_desim_simple(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int64_t* fI, int kf,
+                      int64_t ld_f, int64_t* out, int64_t ld_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

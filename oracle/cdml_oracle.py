@@ -330,18 +330,19 @@ def graph_backward(fwd, spec, params, dE, dtype=np.float64, rnd=None):
   return grads
 
 
-def graph_grads_emulated16(x, spec, params, margin, kind="fp16"):
+def graph_grads_emulated16(x, spec, params, margin, kind="fp16", loss_scale=1.0):
   """PRECISION MODEL of the fusion-tower step (test infrastructure), the counterpart of tower_grads_emulated16:
-  gradients of the SUM of hinges flow backwards in 16 bits, the 1/B is applied to the fp32 weight gradients."""
+  gradients of loss_scale * SUM of hinges flow backwards in 16 bits, 1/(B*loss_scale) is applied to the fp32 weight
+  gradients."""
   rnd = lambda a: round16(a, kind)
   fwd = graph_forward(x, spec, params, np.float64, rnd)
   e = fwd["l2_norm"]
   E = e.reshape(-1, 3, e.shape[-1])
   B = E.shape[0]
   loss = hinge_loss(E, margin)
-  g = hinge_loss_grad(E, margin).reshape(-1, e.shape[-1]) * B
+  g = hinge_loss_grad(E, margin).reshape(-1, e.shape[-1]) * (B * loss_scale)
   grads = graph_backward(fwd, spec, params, g, np.float64, rnd)
-  return {"l2_norm": e, "loss": loss, "grads": [(gw / B, gb / B) for gw, gb in grads]}
+  return {"l2_norm": e, "loss": loss, "grads": [(gw / (B * loss_scale), gb / (B * loss_scale)) for gw, gb in grads]}
 
 
 # --------------------------------------------------------------------------- #
@@ -591,6 +592,46 @@ def rencode_eval(features, cowatches):
   uniq = np.unique(np.asarray(cowatches).reshape(-1))
   remap = {int(o): i for i, o in enumerate(uniq)}
   return features[uniq], [[remap[int(a)], remap[int(b)]] for a, b in cowatches]
+
+
+# --------------------------------------------------------------------------- #
+# de-similarity post-filter (faiss_knn.py:134-244)                              #
+# --------------------------------------------------------------------------- #
+def desim_simple(eI, fI):
+  """faiss_knn.desim (faiss_knn.py:134-143): eI[i, j] = -1 wherever eI[i, j] occurs in row i of fI."""
+  eI = np.array(eI, np.int64)
+  for i in range(eI.shape[0]):
+    eI[i][np.isin(eI[i], fI[i])] = -1
+  return eI
+
+
+def filter_fI(fI, fD, fD_threshold=1.4):
+  """faiss_knn.fliter_fI (faiss_knn.py:146-155): feature neighbours farther than the threshold, and the row itself, -> -1."""
+  fI = np.array(fI, np.int64)
+  fI[np.asarray(fD) > fD_threshold] = -1
+  fI[fI == np.arange(fI.shape[0])[:, None]] = -1
+  return fI
+
+
+def iter_desim(eI, fI, fD, fD_threshold=1.4, fI_end=31):
+  """faiss_knn.iter_desim_mp (faiss_knn.py:187-244) without its +1 index shift, zero row and process pool, which only
+  serve the vectorised column sweep.  Row by row (rows are independent): walk the columns left to right; an entry that is
+  still alive is a pivot v, and every LATER entry of the row that occurs among v's first fI_end filtered feature
+  neighbours (filter_fI) is dropped (-1) and never becomes a pivot (faiss_knn.py:176-184, :203-233).  Finally the row's
+  own id is dropped (faiss_knn.py:236-238).  -1 entries (short KNN lists) stay -1."""
+  eI = np.array(eI, np.int64)
+  F = filter_fI(fI, fD, fD_threshold)[:, :fI_end]
+  for r in range(eI.shape[0]):
+    row = eI[r]
+    for c in range(row.shape[0]):
+      v = row[c]
+      if v < 0:
+        continue
+      near = F[v][F[v] >= 0]
+      tail = row[c + 1:]
+      tail[np.isin(tail, near)] = -1
+    row[row == r] = -1
+  return eI
 
 
 # --------------------------------------------------------------------------- #

@@ -260,3 +260,18 @@ def test_fusion_spec_shapes_follow_models_py():
     params = O.init_graph(O.fusion_spec(name), seed=2)
     assert [W.shape for W, _ in params] == shapes
     assert all(np.all(b == np.float32(0.1)) for _, b in params)
+
+
+# ---------------------------------------------------------------- de-similarity filter (faiss_knn.py:134-244)
+def test_desim_oracle_equals_reference_iter_desim_mp():
+  """oracle.iter_desim (row-wise restatement) against outputs of the reference's own iter_desim_mp / desim run in the
+  build container (tests/golden/make_desim_golden.py): column sweep, f_end cut, -1 padding, more processes than rows."""
+  g = np.load(os.path.join(GOLDEN, "desim_golden.npz"))
+  for name in "abcd":
+    f_end = int(g[name + "_args"][0])
+    eI, fI, fD = g[name + "_eI"], g[name + "_fI"], g[name + "_fD"]
+    keep = (eI.copy(), fI.copy(), fD.copy())
+    assert np.array_equal(O.iter_desim(eI, fI, fD, 1.4, f_end), g[name + "_out"]), name
+    assert np.array_equal(O.desim_simple(eI, fI), g[name + "_simple"]), name
+    assert all(np.array_equal(a, b) for a, b in zip(keep, (eI, fI, fD)))          # the oracle does not mutate its inputs
+  assert (g["b_out"] == -1).mean() > (g["b_eI"] == -1).mean()                     # something was actually filtered
