@@ -232,6 +232,8 @@ def desim(eI, fI, fD=None, fD_threshold=1.4, f_end=31, out=None):
   ws = torch.empty((max(int(lib.cdml_desim_workspace_bytes(nf, kf, int(f_end))), 4),), dtype=torch.uint8, device=eI.device)
   if out is None:
     out = torch.empty_like(eI)
+  if n == 0:
+    return out
   _count(2)
   check(lib.cdml_desim(_ctx(eI), ptr(eI), n, ke, _row_major_2d(eI, "eI"), ptr(fI), ptr(fD), nf, kf, _row_major_2d(fI, "fI"),
                        _row_major_2d(fD, "fD") if fD is not None else 0, float(fD_threshold), int(f_end), ptr(ws), ptr(out),
