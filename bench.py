@@ -25,7 +25,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TOWERS = {"vnet": ([1500, 5000, 256], "fp16"),                      # configs[1]: the default models.py tower
-          "wide": ([2048, 2048, 2048, 2048, 256], "bf16")}          # configs[2]: 2048-d input, 3 x 2048 hidden, bf16
+          "wide": ([2048, 2048, 2048, 2048, 256], "bf16"),          # configs[2]: 2048-d input, 3 x 2048 hidden, bf16
+          "resnet": ([1628, 256], "fp16")}                          # the fusion tower of train.py main()
 DIMS = TOWERS["vnet"][0]
 
 
@@ -36,6 +37,12 @@ def flop_per_triplet(dims):
 
 
 FLOP_PER_TRIPLET = flop_per_triplet(DIMS)
+
+
+def flop_per_triplet_graph(spec, widths):
+  """Same count over the op list of a fusion tower: forward + weight gradient for every fc, data gradient unless the fc
+  reads an input slice.  ResNet (models.py:125-157): 3 * (4*1500*5000 + 6*5000*256 + 4*128*400 + 6*400*256 + 2*6*256*256)."""
+  return 3 * sum((4 if spec[e["src"]]["op"] == "input" else 6) * widths[e["src"]] * e["out"] for e in spec if e["op"] == "fc")
 
 
 def peaks():
@@ -121,6 +128,76 @@ def cpu_knn_baseline(budget_s=10.0, N=1000000, d=256, k=100, nq_block=1024):
           "sample": "%d queries against N=%d d=%d k=%d (blocked sgemm + argpartition oracle) in %.1f s" % (n * nq_block, N, d, k, dt)}
 
 
+def _desim_inputs(rng_or_gen, n, ke, kf, torch=None, dev=None):
+  """KNN-shaped synthetic lists: row r starts with r, the rest are uniform ids (worst case for the filter: hardly any
+  overlap, so every entry stays a pivot and gathers its feature-neighbour row); distances ascending in [0, 2)."""
+  if torch is None:
+    eI = rng_or_gen.randint(0, n, (n, ke)).astype(np.int64)
+    fI = rng_or_gen.randint(0, n, (n, kf)).astype(np.int64)
+    eI[:, 0] = fI[:, 0] = np.arange(n)
+    fD = np.sort(rng_or_gen.rand(n, kf).astype(np.float32) * 2.0, axis=1)
+    return eI, fI, fD
+  eI = torch.randint(0, n, (n, ke), generator=rng_or_gen, device=dev, dtype=torch.int64)
+  fI = torch.randint(0, n, (n, kf), generator=rng_or_gen, device=dev, dtype=torch.int64)
+  eI[:, 0] = fI[:, 0] = torch.arange(n, device=dev)
+  fD = torch.sort(torch.rand((n, kf), generator=rng_or_gen, device=dev) * 2.0, dim=1).values
+  return eI, fI, fD
+
+
+def cpu_desim_baseline(budget_s=8.0, n=20000, ke=81, kf=26):
+  from oracle import cdml_oracle as O
+  eI, fI, fD = _desim_inputs(np.random.RandomState(6), n, ke, kf)
+  rows, t0 = 0, time.time()
+  while time.time() - t0 < budget_s and rows < n:
+    O.iter_desim(eI[rows:rows + 500], fI, fD, 1.4, 31)          # rows are independent: any slice is a valid sample
+    rows += 500
+  dt = time.time() - t0
+  return {"value": rows / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+          "sample": "%d rows of %d neighbours against a %d x %d feature-KNN table (row-wise numpy restatement of "
+                    "iter_desim_mp; the reference itself spawns 81 x Pool(22) numpy passes) in %.1f s" % (rows, ke, n, kf, dt)}
+
+
+def bench_desim(torch, ops, dev, n, world, rank, barrier, dist, pk, ke=81, kf=26, reps=5):
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(6 + rank)
+  eI, fI, fD = _desim_inputs(gen, n, ke, kf, torch, dev)
+  out = torch.empty_like(eI)
+  ops.desim(eI, fI, fD, 1.4, 31, out=out)                        # warm-up
+  barrier()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(reps):
+    ops.desim(eI, fI, fD, 1.4, 31, out=out)
+  e1.record()
+  barrier()
+  t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms = float(t.item())
+  # end to end through faiss_knn.iter_desim_mp: host numpy lists -> H2D -> kernels -> D2H
+  from cdml_b200 import faiss_knn
+  eh, fh, dh = eI.cpu().numpy(), fI.cpu().numpy(), fD.cpu().numpy()
+  barrier()
+  t0 = time.time()
+  res = faiss_knn.iter_desim_mp(eh, fh, dh)
+  e2e_s = time.time() - t0
+  survivors = int((out >= 0).sum().item())
+  fw_pad = 32
+  # algorithmic bytes: prepare pass (read fI int64 + fD fp32, write the int32 table) + eI in/out + one table row per
+  # alive pivot (= the survivors plus the row's own id)
+  alg = n * kf * 12 + n * fw_pad * 4 + 2 * n * ke * 8 + (survivors + n) * fw_pad * 4
+  return {"metric": "desim_rows_per_sec", "value": world * n / (ms / 1e3), "unit": "rows/s", "scaling": "weak",
+          "config": {"workload": "iter_desim_mp (faiss_knn.py:187-244): %d rows x %d neighbours per GPU against a %d x %d "
+                                 "feature-KNN table, fD_threshold 1.4, fI_end 31, uniform ids (every entry stays a pivot)"
+                                 % (n, ke, n, kf)},
+          "ms": ms, "dtype": "int64 ids / int32 table", "dropped_fraction": 1.0 - survivors / float(n * ke),
+          "e2e": {"value": n / e2e_s, "unit": "rows/s", "h2d_bytes": n * (ke * 8 + kf * 12), "d2h_bytes": n * ke * 8,
+                  "rows_equal_device_run": bool((torch.as_tensor(res) == out.cpu()).all().item())},
+          "roofline": {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                       "frac": alg / (ms / 1e3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                       "algorithmic_bytes": alg}}
+
+
 def run_reference(args):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
@@ -141,8 +218,11 @@ def run_reference(args):
 
 def workload_config(args, mine):
   dims, dt = TOWERS[getattr(args, "tower", "vnet")]
-  return {"workload": "configs[%d]: tower %s (%s operands), batch %d triplets/GPU, in-batch semi-hard mining %s, "
-                      "feature table %d guids resident in HBM" % (1 if dims is DIMS else 2, "-".join(map(str, dims)), dt,
+  label = {"vnet": "configs[1]: tower", "wide": "configs[2]: tower",
+           "resnet": "SURVEY 8f row 1: fusion tower ResNet (models.py:125-157; visual 1500-5000-256 x doc 128-400-256, two "
+                     "residual 256-256 layers), feature width"}[getattr(args, "tower", "vnet")]
+  return {"workload": "%s %s (%s operands), batch %d triplets/GPU, in-batch semi-hard mining %s, "
+                      "feature table %d guids resident in HBM" % (label, "-".join(map(str, dims)), dt,
                                                                   args.batch, "on" if mine else "off", args.guids),
           "tower": dims, "batch_per_gpu": args.batch, "guids": args.guids, "mining": bool(mine), "margin": 0.8,
           "optimizer": "adam(tf1) lr=1e-3", "parallelism": "dp%d" % args.gpus,
@@ -173,7 +253,10 @@ def main():
   ap.add_argument("--no-knn", action="store_true")
   ap.add_argument("--no-cpu", action="store_true")
   ap.add_argument("--no-graph", action="store_true")
-  ap.add_argument("--tower", default="vnet", choices=sorted(TOWERS), help="vnet = configs[1] (default), wide = configs[2]")
+  ap.add_argument("--tower", default="vnet", choices=sorted(TOWERS),
+                  help="vnet = configs[1] (default), wide = configs[2], resnet = the fusion tower of train.py main()")
+  ap.add_argument("--no-desim", action="store_true")
+  ap.add_argument("--desim-n", type=int, default=4000000)
   ap.add_argument("--knn-n", type=int, default=1000000)
   ap.add_argument("--knn-queries", type=int, default=65536)
   args = ap.parse_args()
@@ -200,17 +283,26 @@ def main():
   dims, dt16 = TOWERS[args.tower]
   flop_triplet = flop_per_triplet(dims)
   B, G, F = args.batch, args.guids, dims[0]
+  graph = None
+  if args.tower == "resnet":
+    from cdml_b200 import fusion, models
+    graph = models.compile_graph(models.ResNet().create_model(models.placeholder(F))["l2_norm"])
 
   # ---- synthetic inputs (seeded; uniform [0,1) features like imitation_data.gen_features) generated on the device
   gen = torch.Generator(device=dev)
   gen.manual_seed(1234)
-  eng = engine.TowerEngine(dims, device=dev, base_lr=1e-3, margin=0.8, seed=2, process_group=pg,
-                           dtype16=_lib.BF16 if dt16 == "bf16" else _lib.F16)
-  table16 = torch.empty((G, eng.F_pad), dtype=eng.t16, device=dev)
+  if graph is not None:
+    eng = fusion.GraphEngine(graph["spec"], feature_size=F, device=dev, base_lr=1e-3, margin=0.8, seed=2, process_group=pg)
+    flop_triplet = flop_per_triplet_graph(eng.spec, eng.widths)
+    table16 = tuple(torch.empty((G, engine._pad64(eng.widths[i] + 1)), dtype=eng.t16, device=dev) for i in eng.inputs)
+  else:
+    eng = engine.TowerEngine(dims, device=dev, base_lr=1e-3, margin=0.8, seed=2, process_group=pg,
+                             dtype16=_lib.BF16 if dt16 == "bf16" else _lib.F16)
+    table16 = torch.empty((G, eng.F_pad), dtype=eng.t16, device=dev)
   for s in range(0, G, 65536):                                            # normalise+cast in slabs (K2 folded, one-off)
     rows = min(65536, G - s)
     slab = torch.rand((rows, F), generator=gen, device=dev, dtype=torch.float32)
-    eng.prepare_table(slab, out=table16[s:s + rows])
+    eng.prepare_table(slab, out=[t[s:s + rows] for t in table16] if graph is not None else table16[s:s + rows])
   del slab
   gen.manual_seed(100 + rank)
   nbatch = args.steps + args.warmup
@@ -401,12 +493,18 @@ def main():
                                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s (per GPU)",
                                 "frac": 2.0 * nq * N * d / kms / 1e9 / world / pk["bf16_tflops_sustained"]}}
     index.close()
+  # ---- de-similarity filter of the KNN lists (integer work, HBM-bound; rows are independent -> each
+  # rank filters its own slice of the rows, no collective: weak scaling)
+  if not args.no_desim:
+    line["desim"] = bench_desim(torch, ops, dev, args.desim_n, world, rank, barrier, dist, pk)
   if rank != 0:
     if world > 1:
       dist.barrier()
       dist.destroy_process_group()
     return
   if not args.no_cpu and world == 1:
+    if not args.no_desim:
+      line["desim"]["cpu_baseline"] = cpu_desim_baseline()
     line["cpu_baseline"] = cpu_train_baseline()
     if not args.no_knn:
       line["knn"]["cpu_baseline"] = cpu_knn_baseline(N=min(args.knn_n, 1000000))

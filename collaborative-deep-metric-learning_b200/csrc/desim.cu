@@ -7,9 +7,9 @@
 //   rows:     for c = 0 .. ke-1: v = eI[r, c]; if alive: every later alive entry that occurs in F[v, :] is dropped (-1);
 //             finally the row's own id is dropped (faiss_knn.py:236-238).
 //
-// The only HBM traffic that matters is the gather of F rows (ke x fw_pad x 4 bytes per eI row, random rows): pivots are
-// fetched kAhead columns ahead of their use (an entry can only change to "dropped", so a prefetched row is either right
-// or ignored), which keeps kAhead x 128 bytes in flight per warp.
+// The only HBM traffic that matters is the gather of F rows (ke x fw_pad x 4 bytes per eI row, random rows): a column's
+// F row is fetched kAhead columns ahead of its use whether or not the column is still alive by then (a prefetched row is
+// either right or ignored), which keeps kAhead x 128 bytes in flight per warp.
 #include "../../include/cdml.h"
 #include "ctx.cuh"
 
@@ -37,36 +37,72 @@ desim_prepare_kernel(const int64_t* __restrict__ fI, const float* __restrict__ f
 }
 
 // E = entries of the row per lane (ke <= 32 E), FC = 32-wide chunks of an F row (fw <= 32 FC).
+//
+// The warp keeps the row in shared memory: the entry values, one alive bit per column, and an open-addressing hash of
+// the entry ids (id -> chain of the columns holding it; duplicates within a row chain up).  A pivot then costs one hash
+// probe per lane -- lane j looks up the pivot's j-th feature neighbour and clears the alive bits of the later columns
+// holding it -- instead of fw x ke comparisons (measured 46 ms -> see DESIGN.md for 1M x 81 rows).
+template <int E>
+struct DesimCfg {
+  static constexpr int kSlots = E <= 1 ? 64 : E == 2 ? 128 : E <= 4 ? 256 : 512;   // load factor <= 0.5
+  static constexpr int kWarps = E <= 4 ? kDesimWarps : 4;                          // <= 24 KB of static shared memory
+};
+
+__device__ __forceinline__ uint32_t desim_hash(int32_t id, int slots) {
+  return (static_cast<uint32_t>(id) * 2654435761u >> 16) & static_cast<uint32_t>(slots - 1);
+}
+
 template <int E, int FC>
-__global__ void __launch_bounds__(kDesimWarps * 32)
+__global__ void __launch_bounds__(DesimCfg<E>::kWarps * 32)
 desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_e, const int32_t* __restrict__ F,
                   int64_t nf, int fw, int fw_pad, int64_t* __restrict__ out, int64_t ld_o, int32_t* flags) {
+  constexpr int S = DesimCfg<E>::kSlots, W = DesimCfg<E>::kWarps;
+  constexpr uint32_t kNone = 0xffffffffu;
+  __shared__ int32_t s_key[W][S];
+  __shared__ uint32_t s_head[W][S];           // first column of the chain of columns holding s_key
+  __shared__ uint32_t s_next[W][32 * E];      // next column holding the same id
+  __shared__ int32_t s_val[W][32 * E];        // pivot id of a column, -1 = never a pivot
+  __shared__ uint32_t s_alive[W][E];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kDesimWarps + warp; r < n;
-       r += static_cast<int64_t>(gridDim.x) * kDesimWarps) {
-    int32_t ent[E];       // alive entry id, -1 = dropped / padding, -2 = not a pivot (id outside the feature table)
+  int32_t* key = s_key[warp];
+  uint32_t* head = s_head[warp];
+  uint32_t* next = s_next[warp];
+  int32_t* val = s_val[warp];
+  volatile uint32_t* alive = s_alive[warp];
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * W + warp; r < n; r += static_cast<int64_t>(gridDim.x) * W) {
+    __syncwarp();
+    for (int i = lane; i < S; i += 32) key[i] = -1, head[i] = kNone;
     int64_t raw[E];
-    bool changed[E];
+    int32_t ent[E];       // valid pivot id, -1 = padding, -2 = id outside the feature table (left untouched)
 #pragma unroll
     for (int t = 0; t < E; ++t) {
       const int c = lane + 32 * t;
       raw[t] = c < ke ? eI[r * ld_e + c] : -1;
-      changed[t] = false;
       if (raw[t] < 0) ent[t] = -1;
       else if (raw[t] >= nf) {           // the reference would raise IndexError in fI[col_eI] (faiss_knn.py:179)
         ent[t] = -2;
         atomicOr(flags, 2);
       } else ent[t] = static_cast<int32_t>(raw[t]);
+      val[c] = ent[t] >= 0 ? ent[t] : -1;
+      const uint32_t word = __ballot_sync(0xffffffffu, ent[t] >= 0);
+      if (lane == 0) alive[t] = word;
     }
-    auto entry_at = [&](int c) -> int32_t {   // warp-uniform read of column c
-      int32_t v = -1;
+    __syncwarp();
 #pragma unroll
-      for (int t = 0; t < E; ++t)
-        if ((c >> 5) == t) v = __shfl_sync(0xffffffffu, ent[t], c & 31);
-      return v;
-    };
+    for (int t = 0; t < E; ++t) {
+      if (ent[t] >= 0) {
+        uint32_t h = desim_hash(ent[t], S);
+        while (true) {
+          const int32_t old = atomicCAS(&key[h], -1, ent[t]);
+          if (old == -1 || old == ent[t]) break;
+          h = (h + 1) & (S - 1);
+        }
+        next[lane + 32 * t] = atomicExch(&head[h], static_cast<uint32_t>(lane + 32 * t));
+      }
+    }
+    __syncwarp();
     auto fetch = [&](int c, int32_t (&buf)[FC]) {
-      const int32_t v = c < ke ? entry_at(c) : -1;
+      const int32_t v = c < ke ? val[c] : -1;
 #pragma unroll
       for (int q = 0; q < FC; ++q) {
         const int j = lane + 32 * q;
@@ -80,31 +116,37 @@ desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_
 #pragma unroll
       for (int p = 0; p < kAhead; ++p) {
         const int c = c0 + p;
-        if (c < ke) {
-          const int32_t v = entry_at(c);
-          if (v >= 0) {
+        if (c < ke && val[c] >= 0 && ((alive[c >> 5] >> (c & 31)) & 1u)) {      // warp-uniform: a pivot
 #pragma unroll
-            for (int q = 0; q < FC; ++q) {
-              const unsigned live = __ballot_sync(0xffffffffu, fbuf[p][q] >= 0);
-              for (unsigned m = live; m != 0; m &= m - 1) {
-                const int32_t f = __shfl_sync(0xffffffffu, fbuf[p][q], __ffs(m) - 1);
-#pragma unroll
-                for (int t = 0; t < E; ++t)
-                  if (ent[t] == f && lane + 32 * t > c) ent[t] = -1, changed[t] = true;
+          for (int q = 0; q < FC; ++q) {
+            const int32_t f = fbuf[p][q];
+            if (f >= 0) {
+              uint32_t h = desim_hash(f, S);
+              while (true) {
+                const int32_t k = key[h];
+                if (k == f) {
+                  for (uint32_t col = head[h]; col != kNone; col = next[col])
+                    if (static_cast<int>(col) > c) atomicAnd(const_cast<uint32_t*>(&alive[col >> 5]), ~(1u << (col & 31)));
+                  break;
+                }
+                if (k == -1) break;
+                h = (h + 1) & (S - 1);
               }
             }
           }
+          __syncwarp();      // the drops of this pivot are visible before the next column is examined
         }
         fetch(c + kAhead, fbuf[p]);
       }
     }
+    __syncwarp();
 #pragma unroll
     for (int t = 0; t < E; ++t) {
       const int c = lane + 32 * t;
       if (c < ke) {
-        int64_t w = raw[t];
-        if (changed[t] || w == r) w = -1;
-        if (w < 0) w = -1;
+        int64_t w = raw[t] < 0 ? -1 : raw[t];
+        if (ent[t] >= 0 && !((alive[t] >> lane) & 1u)) w = -1;
+        if (w == r) w = -1;
         out[r * ld_o + c] = w;
       }
     }
@@ -130,8 +172,11 @@ desim_simple_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t l
 template <int E>
 static void launch_rows(int fc, int grid, cudaStream_t st, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int32_t* F,
                         int64_t nf, int fw, int fw_pad, int64_t* out, int64_t ld_o, int32_t* flags) {
-  if (fc == 1) desim_rows_kernel<E, 1><<<grid, kDesimWarps * 32, 0, st>>>(eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o, flags);
-  else desim_rows_kernel<E, 2><<<grid, kDesimWarps * 32, 0, st>>>(eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o, flags);
+  constexpr int W = DesimCfg<E>::kWarps;
+  const int64_t blocks = (n + W - 1) / W;
+  if (blocks < grid) grid = static_cast<int>(blocks);
+  if (fc == 1) desim_rows_kernel<E, 1><<<grid, W * 32, 0, st>>>(eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o, flags);
+  else desim_rows_kernel<E, 2><<<grid, W * 32, 0, st>>>(eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o, flags);
 }
 
 static inline int desim_width(int kf, int f_end) { return f_end < kf ? f_end : kf; }
@@ -166,8 +211,7 @@ int cdml_desim(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e
                                                                                       fD_threshold, fw, fw_pad, F);
     CDML_CHECK_CUDA(cudaGetLastError());
   }
-  const int64_t blocks = (n + kDesimWarps - 1) / kDesimWarps, cap = static_cast<int64_t>(ctx->num_sms) * 8;
-  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  const int grid = ctx->num_sms * 8;     // capped to the number of row groups inside launch_rows
   const int fc = fw_pad / 32;
   const int e = (ke + 31) / 32;
   if (e <= 1) launch_rows<1>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
