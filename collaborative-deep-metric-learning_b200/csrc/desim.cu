@@ -7,16 +7,13 @@
 //   rows:     for c = 0 .. ke-1: v = eI[r, c]; if alive: every later alive entry that occurs in F[v, :] is dropped (-1);
 //             finally the row's own id is dropped (faiss_knn.py:236-238).
 //
-// The only HBM traffic that matters is the gather of F rows (ke x fw_pad x 4 bytes per eI row, random rows): a column's
-// F row is fetched kAhead columns ahead of its use whether or not the column is still alive by then (a prefetched row is
-// either right or ignored), which keeps kAhead x 128 bytes in flight per warp.
+// The only HBM traffic that matters is the gather of F rows (ke x fw_pad x 4 bytes per eI row, random 128-byte rows).
 #include "../../include/cdml.h"
 #include "ctx.cuh"
 
 namespace cdml {
 
 constexpr int kDesimWarps = 8;
-constexpr int kAhead = 4;
 
 __global__ void __launch_bounds__(256)
 desim_prepare_kernel(const int64_t* __restrict__ fI, const float* __restrict__ fD, int64_t nf, int kf, int64_t ld_fi,
@@ -38,15 +35,21 @@ desim_prepare_kernel(const int64_t* __restrict__ fI, const float* __restrict__ f
 
 // E = entries of the row per lane (ke <= 32 E), FC = 32-wide chunks of an F row (fw <= 32 FC).
 //
-// The warp keeps the row in shared memory: the entry values, one alive bit per column, and an open-addressing hash of
-// the entry ids (id -> chain of the columns holding it; duplicates within a row chain up).  A pivot then costs one hash
-// probe per lane -- lane j looks up the pivot's j-th feature neighbour and clears the alive bits of the later columns
-// holding it -- instead of fw x ke comparisons (measured 46 ms -> see DESIGN.md for 1M x 81 rows).
+// Two phases per row, the warp's state in shared memory:
+//  (1) relation, fully parallel: an open-addressing hash of the row's ids (id -> chain of the columns holding it;
+//      duplicates chain up) is built once; then for EVERY column c -- alive or not, the answer does not depend on it --
+//      lane j probes the j-th feature neighbour of eI[r,c] and ORs the later columns holding it into kill[c] (a ke-bit
+//      mask).  All ke gathers of F rows are independent, kUnroll of them in flight per warp.
+//  (2) resolution, sequential but trivial: alive = valid columns; for c ascending: if alive[c]: alive &= ~kill[c].
+// The first version walked the columns sequentially with fw x ke comparisons per pivot (46 ms per 1M x 81 rows); hashing
+// with a sequential walk and 4 prefetched pivots reached 15.7 ms per 1M rows; this form is bounded by the random
+// 128-byte gathers.
 template <int E>
 struct DesimCfg {
   static constexpr int kSlots = E <= 1 ? 64 : E == 2 ? 128 : E <= 4 ? 256 : 512;   // load factor <= 0.5
-  static constexpr int kWarps = E <= 4 ? kDesimWarps : 4;                          // <= 24 KB of static shared memory
+  static constexpr int kWarps = E <= 2 ? 8 : E <= 4 ? 4 : 2;                       // static shared memory <= 28 KB
 };
+constexpr int kUnroll = 8;
 
 __device__ __forceinline__ uint32_t desim_hash(int32_t id, int slots) {
   return (static_cast<uint32_t>(id) * 2654435761u >> 16) & static_cast<uint32_t>(slots - 1);
@@ -62,18 +65,19 @@ desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_
   __shared__ uint32_t s_head[W][S];           // first column of the chain of columns holding s_key
   __shared__ uint32_t s_next[W][32 * E];      // next column holding the same id
   __shared__ int32_t s_val[W][32 * E];        // pivot id of a column, -1 = never a pivot
-  __shared__ uint32_t s_alive[W][E];
+  __shared__ uint32_t s_kill[W][32 * E][E];   // columns a pivot removes
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int32_t* key = s_key[warp];
   uint32_t* head = s_head[warp];
   uint32_t* next = s_next[warp];
   int32_t* val = s_val[warp];
-  volatile uint32_t* alive = s_alive[warp];
+  uint32_t(*kill)[E] = s_kill[warp];
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * W + warp; r < n; r += static_cast<int64_t>(gridDim.x) * W) {
     __syncwarp();
     for (int i = lane; i < S; i += 32) key[i] = -1, head[i] = kNone;
     int64_t raw[E];
     int32_t ent[E];       // valid pivot id, -1 = padding, -2 = id outside the feature table (left untouched)
+    uint32_t alive[E];    // warp-uniform copy of the alive words
 #pragma unroll
     for (int t = 0; t < E; ++t) {
       const int c = lane + 32 * t;
@@ -84,8 +88,9 @@ desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_
         atomicOr(flags, 2);
       } else ent[t] = static_cast<int32_t>(raw[t]);
       val[c] = ent[t] >= 0 ? ent[t] : -1;
-      const uint32_t word = __ballot_sync(0xffffffffu, ent[t] >= 0);
-      if (lane == 0) alive[t] = word;
+      alive[t] = __ballot_sync(0xffffffffu, ent[t] >= 0);
+#pragma unroll
+      for (int u = 0; u < E; ++u) kill[c][u] = 0;
     }
     __syncwarp();
 #pragma unroll
@@ -101,45 +106,50 @@ desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_
       }
     }
     __syncwarp();
-    auto fetch = [&](int c, int32_t (&buf)[FC]) {
-      const int32_t v = c < ke ? val[c] : -1;
+    // (1) relation
+    for (int c0 = 0; c0 < ke; c0 += kUnroll) {
+      int32_t f[kUnroll][FC];
 #pragma unroll
-      for (int q = 0; q < FC; ++q) {
-        const int j = lane + 32 * q;
-        buf[q] = (v >= 0 && j < fw) ? __ldg(F + static_cast<int64_t>(v) * fw_pad + j) : -1;
+      for (int p = 0; p < kUnroll; ++p) {
+        const int32_t v = c0 + p < ke ? val[c0 + p] : -1;
+#pragma unroll
+        for (int q = 0; q < FC; ++q) {
+          const int j = lane + 32 * q;
+          f[p][q] = (v >= 0 && j < fw) ? __ldg(F + static_cast<int64_t>(v) * fw_pad + j) : -1;
+        }
       }
-    };
-    int32_t fbuf[kAhead][FC];
 #pragma unroll
-    for (int p = 0; p < kAhead; ++p) fetch(p, fbuf[p]);
-    for (int c0 = 0; c0 < ke; c0 += kAhead) {
+      for (int p = 0; p < kUnroll; ++p) {
 #pragma unroll
-      for (int p = 0; p < kAhead; ++p) {
-        const int c = c0 + p;
-        if (c < ke && val[c] >= 0 && ((alive[c >> 5] >> (c & 31)) & 1u)) {      // warp-uniform: a pivot
-#pragma unroll
-          for (int q = 0; q < FC; ++q) {
-            const int32_t f = fbuf[p][q];
-            if (f >= 0) {
-              uint32_t h = desim_hash(f, S);
-              while (true) {
-                const int32_t k = key[h];
-                if (k == f) {
-                  for (uint32_t col = head[h]; col != kNone; col = next[col])
-                    if (static_cast<int>(col) > c) atomicAnd(const_cast<uint32_t*>(&alive[col >> 5]), ~(1u << (col & 31)));
-                  break;
-                }
-                if (k == -1) break;
-                h = (h + 1) & (S - 1);
-              }
+        for (int q = 0; q < FC; ++q) {
+          const int32_t id = f[p][q];
+          if (id >= 0) {
+            uint32_t h = desim_hash(id, S);
+            int32_t k = key[h];
+            while (k != id && k != -1) {
+              h = (h + 1) & (S - 1);
+              k = key[h];
+            }
+            if (k == id) {
+              for (uint32_t col = head[h]; col != kNone; col = next[col])
+                if (static_cast<int>(col) > c0 + p) atomicOr(&kill[c0 + p][col >> 5], 1u << (col & 31));
             }
           }
-          __syncwarp();      // the drops of this pivot are visible before the next column is examined
         }
-        fetch(c + kAhead, fbuf[p]);
       }
     }
     __syncwarp();
+    // (2) resolution: every lane runs the same recurrence on uniform shared-memory reads
+    for (int c = 0; c < ke; ++c) {
+      bool is_alive = false;
+#pragma unroll
+      for (int t = 0; t < E; ++t)
+        if ((c >> 5) == t) is_alive = (alive[t] >> (c & 31)) & 1u;
+      if (is_alive) {
+#pragma unroll
+        for (int t = 0; t < E; ++t) alive[t] &= ~kill[c][t];
+      }
+    }
 #pragma unroll
     for (int t = 0; t < E; ++t) {
       const int c = lane + 32 * t;
@@ -211,7 +221,7 @@ int cdml_desim(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e
                                                                                       fD_threshold, fw, fw_pad, F);
     CDML_CHECK_CUDA(cudaGetLastError());
   }
-  const int grid = ctx->num_sms * 8;     // capped to the number of row groups inside launch_rows
+  const int grid = ctx->num_sms * 16;    // capped to the number of row groups inside launch_rows
   const int fc = fw_pad / 32;
   const int e = (ke + 31) / 32;
   if (e <= 1) launch_rows<1>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
