@@ -36,24 +36,24 @@ desim_prepare_kernel(const int64_t* __restrict__ fI, const float* __restrict__ f
 // E = entries of the row per lane (ke <= 32 E), FC = 32-wide chunks of an F row (fw <= 32 FC).
 //
 // Two phases per row, the warp's state in shared memory:
-//  (1) relation, fully parallel: an open-addressing hash of the row's ids (id -> chain of the columns holding it;
-//      duplicates chain up) is built once; then for EVERY column c -- alive or not, the answer does not depend on it --
-//      lane j probes the j-th feature neighbour of eI[r,c] and ORs the later columns holding it into kill[c] (a ke-bit
-//      mask).  All ke gathers of F rows are independent, kUnroll of them in flight per warp.
-//  (2) resolution, sequential but trivial: alive = valid columns; for c ascending: if alive[c]: alive &= ~kill[c].
-// The first version walked the columns sequentially with fw x ke comparisons per pivot (46 ms per 1M x 81 rows); hashing
-// with a sequential walk and 4 prefetched pivots reached 15.7 ms per 1M rows; this form is bounded by the random
-// 128-byte gathers.
+//  (1) relation, fully parallel: a Bloom bitmap (8192 bits) and an open-addressing hash of the row's ids (id -> chain of
+//      the columns holding it; duplicates chain up) are built once; then for EVERY column c -- alive or not, the answer
+//      does not depend on it -- lane j tests the j-th feature neighbour of eI[r,c] against the bitmap (one LDS; ~1 % false
+//      positives), and only the lanes that pass probe the hash and OR the later columns holding the id into kill[c]
+//      (a ke-bit mask).  All ke gathers of F rows are independent, kUnroll of them in flight per warp.
+//  (2) resolution, sequential but sparse: alive = valid columns; for each column c WITH a non-empty kill mask, ascending:
+//      if alive[c]: alive &= ~kill[c].
+// History on 4M x 81 rows (ncu, profiles/): column walk with fw x ke comparisons 184 ms -> hash probe per neighbour, walk
+// in column order with 4 prefetched pivots 62.6 ms (14 k instructions per row, issue-bound) -> this form.
 template <int E>
 struct DesimCfg {
-  static constexpr int kSlots = E <= 1 ? 64 : E == 2 ? 128 : E <= 4 ? 256 : 512;   // load factor <= 0.5
-  static constexpr int kWarps = E <= 2 ? 8 : E <= 4 ? 4 : 2;                       // static shared memory <= 28 KB
+  static constexpr int kSlots = E <= 1 ? 128 : E == 2 ? 256 : E <= 4 ? 512 : 1024;   // load factor <= 0.25
+  static constexpr int kWarps = E <= 2 ? 8 : E <= 4 ? 4 : 2;                        // static shared memory <= 30 KB
 };
 constexpr int kUnroll = 8;
+constexpr int kBloomWords = 256;
 
-__device__ __forceinline__ uint32_t desim_hash(int32_t id, int slots) {
-  return (static_cast<uint32_t>(id) * 2654435761u >> 16) & static_cast<uint32_t>(slots - 1);
-}
+__device__ __forceinline__ uint32_t desim_mix(int32_t id) { return static_cast<uint32_t>(id) * 2654435761u; }
 
 template <int E, int FC>
 __global__ void __launch_bounds__(DesimCfg<E>::kWarps * 32)
@@ -63,20 +63,28 @@ desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_
   constexpr uint32_t kNone = 0xffffffffu;
   __shared__ int32_t s_key[W][S];
   __shared__ uint32_t s_head[W][S];           // first column of the chain of columns holding s_key
+  __shared__ uint32_t s_bloom[W][kBloomWords];
   __shared__ uint32_t s_next[W][32 * E];      // next column holding the same id
   __shared__ int32_t s_val[W][32 * E];        // pivot id of a column, -1 = never a pivot
   __shared__ uint32_t s_kill[W][32 * E][E];   // columns a pivot removes
+  __shared__ uint32_t s_any[W][E];            // columns with a non-empty kill mask
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int32_t* key = s_key[warp];
   uint32_t* head = s_head[warp];
+  uint32_t* bloom = s_bloom[warp];
   uint32_t* next = s_next[warp];
   int32_t* val = s_val[warp];
   uint32_t(*kill)[E] = s_kill[warp];
+  uint32_t* any = s_any[warp];
+  for (int i = lane; i < S; i += 32) key[i] = -1, head[i] = kNone;      // rows undo their own insertions afterwards
+  for (int i = lane; i < kBloomWords; i += 32) bloom[i] = 0;
+  if (lane < E) any[lane] = 0;
+  for (int i = lane; i < 32 * E * E; i += 32) (&kill[0][0])[i] = 0;     // rows re-zero the masks they used
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * W + warp; r < n; r += static_cast<int64_t>(gridDim.x) * W) {
     __syncwarp();
-    for (int i = lane; i < S; i += 32) key[i] = -1, head[i] = kNone;
     int64_t raw[E];
     int32_t ent[E];       // valid pivot id, -1 = padding, -2 = id outside the feature table (left untouched)
+    uint32_t slot[E];
     uint32_t alive[E];    // warp-uniform copy of the alive words
 #pragma unroll
     for (int t = 0; t < E; ++t) {
@@ -89,20 +97,18 @@ desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_
       } else ent[t] = static_cast<int32_t>(raw[t]);
       val[c] = ent[t] >= 0 ? ent[t] : -1;
       alive[t] = __ballot_sync(0xffffffffu, ent[t] >= 0);
-#pragma unroll
-      for (int u = 0; u < E; ++u) kill[c][u] = 0;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < E; ++t) {
+      slot[t] = 0;
       if (ent[t] >= 0) {
-        uint32_t h = desim_hash(ent[t], S);
+        const uint32_t m = desim_mix(ent[t]);
+        atomicOr(&bloom[(m >> 19) >> 5], 1u << ((m >> 19) & 31));
+        uint32_t h = (m >> 8) & (S - 1);
         while (true) {
           const int32_t old = atomicCAS(&key[h], -1, ent[t]);
           if (old == -1 || old == ent[t]) break;
           h = (h + 1) & (S - 1);
         }
-        next[lane + 32 * t] = atomicExch(&head[h], static_cast<uint32_t>(lane + 32 * t));
+        slot[t] = h;
+        next[c] = atomicExch(&head[h], static_cast<uint32_t>(c));
       }
     }
     __syncwarp();
@@ -123,8 +129,11 @@ desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_
 #pragma unroll
         for (int q = 0; q < FC; ++q) {
           const int32_t id = f[p][q];
-          if (id >= 0) {
-            uint32_t h = desim_hash(id, S);
+          const uint32_t m = desim_mix(id);
+          const bool maybe = id >= 0 && ((bloom[(m >> 19) >> 5] >> ((m >> 19) & 31)) & 1u);
+          if (maybe) {                                   // rare: ~1 % of the lanes
+            const int c = c0 + p;
+            uint32_t h = (m >> 8) & (S - 1);
             int32_t k = key[h];
             while (k != id && k != -1) {
               h = (h + 1) & (S - 1);
@@ -132,27 +141,44 @@ desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_
             }
             if (k == id) {
               for (uint32_t col = head[h]; col != kNone; col = next[col])
-                if (static_cast<int>(col) > c0 + p) atomicOr(&kill[c0 + p][col >> 5], 1u << (col & 31));
+                if (static_cast<int>(col) > c) {
+                  atomicOr(&kill[c][col >> 5], 1u << (col & 31));
+                  atomicOr(&any[c >> 5], 1u << (c & 31));
+                }
             }
           }
         }
       }
     }
     __syncwarp();
-    // (2) resolution: every lane runs the same recurrence on uniform shared-memory reads
-    for (int c = 0; c < ke; ++c) {
-      bool is_alive = false;
+    // (2) resolution over the columns that remove anything, ascending
 #pragma unroll
-      for (int t = 0; t < E; ++t)
-        if ((c >> 5) == t) is_alive = (alive[t] >> (c & 31)) & 1u;
-      if (is_alive) {
+    for (int t = 0; t < E; ++t) {
+      for (uint32_t todo = any[t]; todo != 0; todo &= todo - 1) {
+        const int c = 32 * t + __ffs(todo) - 1;
+        if ((alive[t] >> (c & 31)) & 1u) {
 #pragma unroll
-        for (int t = 0; t < E; ++t) alive[t] &= ~kill[c][t];
+          for (int u = 0; u < E; ++u) alive[u] &= ~kill[c][u];
+        }
       }
     }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < E; ++t) {
+      if ((any[t] >> lane) & 1u) {                           // leave the row state clean: re-zero the masks that were used
+#pragma unroll
+        for (int u = 0; u < E; ++u) kill[lane + 32 * t][u] = 0;
+      }
+    }
+    __syncwarp();
 #pragma unroll
     for (int t = 0; t < E; ++t) {
       const int c = lane + 32 * t;
+      if (ent[t] >= 0) {                                     // undo this row's insertions
+        const uint32_t m = desim_mix(ent[t]);
+        key[slot[t]] = -1, head[slot[t]] = kNone, bloom[(m >> 19) >> 5] = 0;
+      }
+      if (lane == 0) any[t] = 0;
       if (c < ke) {
         int64_t w = raw[t] < 0 ? -1 : raw[t];
         if (ent[t] >= 0 && !((alive[t] >> lane) & 1u)) w = -1;
