@@ -13,6 +13,7 @@
 
 namespace cdml {
 
+constexpr int kDesimWarps = 8;
 
 __global__ void __launch_bounds__(256)
 desim_prepare_kernel(const int64_t* __restrict__ fI, const float* __restrict__ fD, int64_t nf, int kf, int64_t ld_fi,
@@ -34,86 +35,60 @@ desim_prepare_kernel(const int64_t* __restrict__ fI, const float* __restrict__ f
 
 // E = entries of the row per lane (ke <= 32 E), FC = 32-wide chunks of an F row (fw <= 32 FC).
 //
-// Persistent kernel, one CTA per SM, as many warps as the shared memory holds; a warp owns a row and keeps its state in
-// its slice of (dynamic) shared memory.  Per row:
-//  (0) gather: lane c issues ONE bulk copy (cp.async.bulk, 128 / 256 bytes) of the feature-neighbour row of eI[r,c] into
-//      the warp's staging block and the warp waits on its mbarrier: all ke random gathers of the row are in flight at once
-//      and cost no registers (~10 KB per warp, ~100 KB per SM in flight);
+// Two phases per row, the warp's state in shared memory:
 //  (1) relation, fully parallel: a Bloom bitmap (8192 bits) and an open-addressing hash of the row's ids (id -> chain of
-//      the columns holding it; duplicates chain up) are built while the copies fly; then for EVERY column c -- alive or
-//      not, the answer does not depend on it -- lane j tests the j-th staged neighbour against the bitmap (one LDS; ~1 %
-//      false positives), and only the lanes that pass probe the hash and OR the later columns holding the id into
-//      kill[c] (a ke-bit mask);
+//      the columns holding it; duplicates chain up) are built once; then for EVERY column c -- alive or not, the answer
+//      does not depend on it -- lane j tests the j-th feature neighbour of eI[r,c] against the bitmap (one LDS; ~1 % false
+//      positives), and only the lanes that pass probe the hash and OR the later columns holding the id into kill[c]
+//      (a ke-bit mask).  All ke gathers of F rows are independent, kUnroll of them in flight per warp.
 //  (2) resolution, sequential but sparse: alive = valid columns; for each column c WITH a non-empty kill mask, ascending:
 //      if alive[c]: alive &= ~kill[c].
-// History on 4M x 81 rows: column walk with fw x ke comparisons 184 ms -> hash probe per neighbour, walk in column order
-// with 4 prefetched pivots 62.6 ms (ncu: 14 k instructions per row, issue-bound) -> Bloom + parallel relation with 8
-// register-staged gathers in flight 35.1 ms -> this form.
+// History on 4M x 81 rows (ncu, profiles/): column walk with fw x ke comparisons 184 ms -> hash probe per neighbour, walk
+// in column order with 4 prefetched pivots 62.6 ms (14 k instructions per row, issue-bound) -> this form 35.1 ms.
+// Tried and measured slower (39.9 ms, commit 90c5b28): a persistent CTA per SM whose warps stage all ke gathers of a row
+// with cp.async.bulk behind an mbarrier (12 KB of staging per warp leaves 11 warps per SM; the kernel is bound by the
+// dependent shared-memory chains of the probes, not by the number of gathers in flight).
 template <int E>
 struct DesimCfg {
   static constexpr int kSlots = E <= 1 ? 128 : E == 2 ? 256 : E <= 4 ? 512 : 1024;   // load factor <= 0.25
+  static constexpr int kWarps = E <= 2 ? 8 : E <= 4 ? 4 : 2;                        // static shared memory <= 30 KB
 };
+constexpr int kUnroll = 8;
 constexpr int kBloomWords = 256;
-constexpr int kDesimMaxWarps = 16;
-
-template <int E, int FC>
-struct DesimSmem {          // per-warp slice, offsets in bytes (every block 16-byte aligned)
-  static constexpr int S = DesimCfg<E>::kSlots;
-  static constexpr int kKey = 0;
-  static constexpr int kHead = kKey + 4 * S;
-  static constexpr int kBloom = kHead + 4 * S;
-  static constexpr int kNext = kBloom + 4 * kBloomWords;
-  static constexpr int kVal = kNext + 128 * E;
-  static constexpr int kKill = kVal + 128 * E;
-  static constexpr int kAny = kKill + 128 * E * E;
-  static constexpr int kBar = kAny + 16 * ((E + 3) / 4);
-  static constexpr int kStage = kBar + 16;
-  static constexpr int kBytes = kStage + 32 * E * 128 * FC;
-};
 
 __device__ __forceinline__ uint32_t desim_mix(int32_t id) { return static_cast<uint32_t>(id) * 2654435761u; }
 
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
-}
-
 template <int E, int FC>
-__global__ void __launch_bounds__(kDesimMaxWarps * 32)
+__global__ void __launch_bounds__(DesimCfg<E>::kWarps * 32)
 desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_e, const int32_t* __restrict__ F,
-                  int64_t nf, int fw, int64_t* __restrict__ out, int64_t ld_o, int32_t* flags) {
-  using L = DesimSmem<E, FC>;
-  constexpr int S = L::S;
-  constexpr int kRow = 32 * FC;               // staged ints per feature-neighbour row (= fw_pad)
+                  int64_t nf, int fw, int fw_pad, int64_t* __restrict__ out, int64_t ld_o, int32_t* flags) {
+  constexpr int S = DesimCfg<E>::kSlots, W = DesimCfg<E>::kWarps;
   constexpr uint32_t kNone = 0xffffffffu;
-  extern __shared__ __align__(128) uint8_t desim_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
-  uint8_t* base = desim_smem + static_cast<size_t>(warp) * L::kBytes;
-  int32_t* key = reinterpret_cast<int32_t*>(base + L::kKey);
-  uint32_t* head = reinterpret_cast<uint32_t*>(base + L::kHead);
-  uint32_t* bloom = reinterpret_cast<uint32_t*>(base + L::kBloom);
-  uint32_t* next = reinterpret_cast<uint32_t*>(base + L::kNext);
-  int32_t* val = reinterpret_cast<int32_t*>(base + L::kVal);
-  uint32_t(*kill)[E] = reinterpret_cast<uint32_t(*)[E]>(base + L::kKill);
-  uint32_t* any = reinterpret_cast<uint32_t*>(base + L::kAny);
-  const int32_t* stage = reinterpret_cast<const int32_t*>(base + L::kStage);
-  const uint32_t bar = smem_u32(base + L::kBar), stage_u32 = smem_u32(base + L::kStage);
+  __shared__ int32_t s_key[W][S];
+  __shared__ uint32_t s_head[W][S];           // first column of the chain of columns holding s_key
+  __shared__ uint32_t s_bloom[W][kBloomWords];
+  __shared__ uint32_t s_next[W][32 * E];      // next column holding the same id
+  __shared__ int32_t s_val[W][32 * E];        // pivot id of a column, -1 = never a pivot
+  __shared__ uint32_t s_kill[W][32 * E][E];   // columns a pivot removes
+  __shared__ uint32_t s_any[W][E];            // columns with a non-empty kill mask
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int32_t* key = s_key[warp];
+  uint32_t* head = s_head[warp];
+  uint32_t* bloom = s_bloom[warp];
+  uint32_t* next = s_next[warp];
+  int32_t* val = s_val[warp];
+  uint32_t(*kill)[E] = s_kill[warp];
+  uint32_t* any = s_any[warp];
   for (int i = lane; i < S; i += 32) key[i] = -1, head[i] = kNone;      // rows undo their own insertions afterwards
   for (int i = lane; i < kBloomWords; i += 32) bloom[i] = 0;
-  for (int i = lane; i < 32 * E * E; i += 32) (&kill[0][0])[i] = 0;     // rows re-zero the masks they used
   if (lane < E) any[lane] = 0;
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  uint32_t parity = 0;
+  for (int i = lane; i < 32 * E * E; i += 32) (&kill[0][0])[i] = 0;     // rows re-zero the masks they used
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * W + warp; r < n; r += static_cast<int64_t>(gridDim.x) * W) {
     __syncwarp();
     int64_t raw[E];
     int32_t ent[E];       // valid pivot id, -1 = padding, -2 = id outside the feature table (left untouched)
     uint32_t slot[E];
     uint32_t alive[E];    // warp-uniform copy of the alive words
-    uint32_t pivots = 0;
 #pragma unroll
     for (int t = 0; t < E; ++t) {
       const int c = lane + 32 * t;
@@ -123,22 +98,8 @@ desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_
         ent[t] = -2;
         atomicOr(flags, 2);
       } else ent[t] = static_cast<int32_t>(raw[t]);
-      alive[t] = __ballot_sync(0xffffffffu, ent[t] >= 0);
-      pivots += __popc(alive[t]);
-    }
-    // (0) gather
-    if (lane == 0) mbar_arrive_expect_tx(bar, pivots * kRow * 4);
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < E; ++t) {
-      const int c = lane + 32 * t;
-      if (ent[t] >= 0) bulk_load(stage_u32 + c * kRow * 4, F + static_cast<int64_t>(ent[t]) * kRow, kRow * 4, bar);
-    }
-    // row state, built while the copies fly
-#pragma unroll
-    for (int t = 0; t < E; ++t) {
-      const int c = lane + 32 * t;
       val[c] = ent[t] >= 0 ? ent[t] : -1;
+      alive[t] = __ballot_sync(0xffffffffu, ent[t] >= 0);
       slot[t] = 0;
       if (ent[t] >= 0) {
         const uint32_t m = desim_mix(ent[t]);
@@ -154,31 +115,40 @@ desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_
       }
     }
     __syncwarp();
-    mbar_wait(bar, parity, 900);
-    parity ^= 1u;
     // (1) relation
-#pragma unroll 4
-    for (int c = 0; c < ke; ++c) {
-      if (val[c] < 0) continue;                          // warp-uniform
+    for (int c0 = 0; c0 < ke; c0 += kUnroll) {
+      int32_t f[kUnroll][FC];
 #pragma unroll
-      for (int q = 0; q < FC; ++q) {
-        const int j = lane + 32 * q;
-        const int32_t id = j < fw ? stage[c * kRow + j] : -1;
-        const uint32_t m = desim_mix(id);
-        const bool maybe = id >= 0 && ((bloom[(m >> 19) >> 5] >> ((m >> 19) & 31)) & 1u);
-        if (maybe) {                                     // rare: ~1 % of the lanes
-          uint32_t h = (m >> 8) & (S - 1);
-          int32_t k = key[h];
-          while (k != id && k != -1) {
-            h = (h + 1) & (S - 1);
-            k = key[h];
-          }
-          if (k == id) {
-            for (uint32_t col = head[h]; col != kNone; col = next[col])
-              if (static_cast<int>(col) > c) {
-                atomicOr(&kill[c][col >> 5], 1u << (col & 31));
-                atomicOr(&any[c >> 5], 1u << (c & 31));
-              }
+      for (int p = 0; p < kUnroll; ++p) {
+        const int32_t v = c0 + p < ke ? val[c0 + p] : -1;
+#pragma unroll
+        for (int q = 0; q < FC; ++q) {
+          const int j = lane + 32 * q;
+          f[p][q] = (v >= 0 && j < fw) ? __ldg(F + static_cast<int64_t>(v) * fw_pad + j) : -1;
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < kUnroll; ++p) {
+#pragma unroll
+        for (int q = 0; q < FC; ++q) {
+          const int32_t id = f[p][q];
+          const uint32_t m = desim_mix(id);
+          const bool maybe = id >= 0 && ((bloom[(m >> 19) >> 5] >> ((m >> 19) & 31)) & 1u);
+          if (maybe) {                                   // rare: ~1 % of the lanes
+            const int c = c0 + p;
+            uint32_t h = (m >> 8) & (S - 1);
+            int32_t k = key[h];
+            while (k != id && k != -1) {
+              h = (h + 1) & (S - 1);
+              k = key[h];
+            }
+            if (k == id) {
+              for (uint32_t col = head[h]; col != kNone; col = next[col])
+                if (static_cast<int>(col) > c) {
+                  atomicOr(&kill[c][col >> 5], 1u << (col & 31));
+                  atomicOr(&any[c >> 5], 1u << (c & 31));
+                }
+            }
           }
         }
       }
@@ -238,32 +208,14 @@ desim_simple_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t l
   }
 }
 
-template <int E, int FC>
-static int launch_rows_fc(cdml_ctx* ctx, cudaStream_t st, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int32_t* F,
-                          int64_t nf, int fw, int64_t* out, int64_t ld_o) {
-  using L = DesimSmem<E, FC>;
-  auto kern = desim_rows_kernel<E, FC>;
-  int warps = static_cast<int>((227 * 1024 - 1024) / L::kBytes);         // one persistent CTA per SM
-  if (warps > kDesimMaxWarps) warps = kDesimMaxWarps;
-  CDML_REQUIRE(warps >= 1, "cdml_desim: row state of %d bytes does not fit in shared memory", L::kBytes);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CDML_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDesimMaxWarps * L::kBytes > 227 * 1024
-                                                                                           ? 227 * 1024 : kDesimMaxWarps * L::kBytes));
-    attr_set = true;
-  }
-  const int64_t blocks = (n + warps - 1) / warps;
-  const int grid = static_cast<int>(blocks < ctx->num_sms ? blocks : ctx->num_sms);
-  kern<<<grid, warps * 32, static_cast<size_t>(warps) * L::kBytes, st>>>(eI, n, ke, ld_e, F, nf, fw, out, ld_o, ctx->dev_flags);
-  CDML_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
 template <int E>
-static int launch_rows(cdml_ctx* ctx, int fc, cudaStream_t st, const int64_t* eI, int64_t n, int ke, int64_t ld_e,
-                       const int32_t* F, int64_t nf, int fw, int64_t* out, int64_t ld_o) {
-  if (fc == 1) return launch_rows_fc<E, 1>(ctx, st, eI, n, ke, ld_e, F, nf, fw, out, ld_o);
-  return launch_rows_fc<E, 2>(ctx, st, eI, n, ke, ld_e, F, nf, fw, out, ld_o);
+static void launch_rows(int fc, int grid, cudaStream_t st, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int32_t* F,
+                        int64_t nf, int fw, int fw_pad, int64_t* out, int64_t ld_o, int32_t* flags) {
+  constexpr int W = DesimCfg<E>::kWarps;
+  const int64_t blocks = (n + W - 1) / W;
+  if (blocks < grid) grid = static_cast<int>(blocks);
+  if (fc == 1) desim_rows_kernel<E, 1><<<grid, W * 32, 0, st>>>(eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o, flags);
+  else desim_rows_kernel<E, 2><<<grid, W * 32, 0, st>>>(eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o, flags);
 }
 
 static inline int desim_width(int kf, int f_end) { return f_end < kf ? f_end : kf; }
@@ -288,7 +240,7 @@ int cdml_desim(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e
   CDML_REQUIRE(ke <= 256, "cdml_desim: at most 256 neighbours per row (got %d; the reference uses 81)", ke);
   CDML_REQUIRE(nf < (1ll << 31), "cdml_desim: feature table of %lld rows needs 64-bit ids", (long long)nf);
   const int fw = desim_width(kf, f_end), fw_pad = pad32(fw);
-  CDML_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "cdml_desim: workspace must be 16-byte aligned (bulk copies)");
+  CDML_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "cdml_desim: workspace must be 16-byte aligned");
   CDML_REQUIRE(fw <= 64, "cdml_desim: at most 64 feature neighbours per pivot (got %d; the reference uses 31)", fw);
   if (n == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -299,13 +251,16 @@ int cdml_desim(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e
                                                                                       fD_threshold, fw, fw_pad, F);
     CDML_CHECK_CUDA(cudaGetLastError());
   }
+  const int grid = ctx->num_sms * 16;    // capped to the number of row groups inside launch_rows
   const int fc = fw_pad / 32;
   const int e = (ke + 31) / 32;
-  if (e <= 1) return launch_rows<1>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, out, ld_out);
-  if (e == 2) return launch_rows<2>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, out, ld_out);
-  if (e == 3) return launch_rows<3>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, out, ld_out);
-  if (e == 4) return launch_rows<4>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, out, ld_out);
-  return launch_rows<8>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, out, ld_out);
+  if (e <= 1) launch_rows<1>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
+  else if (e == 2) launch_rows<2>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
+  else if (e == 3) launch_rows<3>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
+  else if (e == 4) launch_rows<4>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
+  else launch_rows<8>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int cdml_desim_simple(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int64_t* fI, int kf,
