@@ -41,6 +41,7 @@ _SIGNATURES = {
   "cdml_desim": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P, c_int64, c_int, c_int64, c_int64, c_float, c_int, _P, _P,
                          c_int64, _P]),
   "cdml_desim_simple": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, _P]),
+  "cdml_sample_triplets": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, ctypes.c_uint64, _P, _P]),
   "cdml_cast16": (c_int, [_P, _P, c_int64, _P, c_int, _P]),
   "cdml_fill_column16": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_float, c_int, _P]),
   "cdml_mine_semihard": (c_int, [_P, _P, c_int64, c_int, _P, c_int64, _P, c_int64, c_int, c_float, _P, _P, _P]),

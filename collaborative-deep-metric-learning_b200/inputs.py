@@ -12,7 +12,10 @@ What changed underneath:
     a file is re-read `num_epochs` times back to back, the trailing partial batch is dropped, each negative is
     `randint(0,G)` re-drawn while it equals the anchor or the positive -- but runs in-process, files served
     round-robin, from a seeded RandomState (the reference forks unseeded workers that all replay one stream, Q10);
-  * rank/world sharding for data-parallel training: rank r serves batches r, r+world, ... of that round-robin order.
+  * rank/world sharding for data-parallel training: rank r serves batches r, r+world, ... of that round-robin order;
+  * `device_reader=True`: the pairs of every file stay resident in HBM and `get_batch_indices_device()`
+    produces the [B,3] triplets on the device (cdml_sample_triplets: same file order, wrap-around and negative rule, a
+    counter-based Philox generator per stream position instead of numpy's Mersenne Twister) -- no host work per step.
 """
 import glob
 import logging
@@ -54,7 +57,8 @@ def _load_pairs(path):
 
 
 class MPTripletPipe(object):
-  def __init__(self, cowatch_file_patten, feature_file=None, wait_times=30, seed=1, rank=0, world=1, device=None):
+  def __init__(self, cowatch_file_patten, feature_file=None, wait_times=30, seed=1, rank=0, world=1, device=None,
+               device_reader=False):
     global FEATURES, _DEVICE_FEATURES
     self.cowatch_files = sorted(glob.glob(cowatch_file_patten))
     self._pairs = [_load_pairs(f) for f in self.cowatch_files]
@@ -67,6 +71,8 @@ class MPTripletPipe(object):
         if torch.cuda.is_available() else None
     _DEVICE_FEATURES = None
     self._iter = None
+    self.device_reader = bool(device_reader)
+    self._dev_pairs, self._dev_iter = {}, None
     logging.info("MPTripletPipe __init__ cowatch_files: %s", self.cowatch_files)
 
   # the device copy of FEATURES is created lazily so CPU-only tests of the reader logic need no GPU
@@ -81,6 +87,7 @@ class MPTripletPipe(object):
   def create_pipe(self, num_epochs, batch_size, queue_length=2 ** 14):
     self.batch_size, self.num_epochs = batch_size, num_epochs
     self._iter = self._index_batches()
+    self._dev_iter = self._position_batches()
 
   def _file_batches(self, pairs, rng, num_guid):
     """One worker of the reference: stream of [B,3] batches over `num_epochs` passes of one file."""
@@ -115,6 +122,39 @@ class MPTripletPipe(object):
         k += 1
       streams = alive
 
+  def _position_batches(self):
+    """(file, start position) of every batch, in the order `_index_batches` serves them (round-robin over the files, a
+    file's stream is `num_epochs` passes back to back without its trailing partial batch, rank r takes every world-th)."""
+    B = self.batch_size
+    cursors = [(i, iter(range(0, len(p) * self.num_epochs - B + 1, B))) for i, p in enumerate(self._pairs) if len(p)]
+    k = 0
+    while cursors:
+      alive = []
+      for i, it in cursors:
+        start = next(it, None)
+        if start is None:
+          continue
+        alive.append((i, it))
+        if k % self.world == self.rank:
+          yield i, start
+        k += 1
+      cursors = alive
+
+  def get_batch_indices_device(self, out=None):
+    """Next [B,3] int64 triplets as a DEVICE tensor produced by cdml_sample_triplets, or None at end of data."""
+    if self._dev_iter is None:
+      raise RuntimeError("call create_pipe() first")
+    nxt = next(self._dev_iter, None)
+    if nxt is None:
+      return None
+    i, start = nxt
+    pairs = self._dev_pairs.get(i)
+    if pairs is None:
+      if self.device is None:
+        raise RuntimeError("the device reader needs a CUDA device")
+      pairs = self._dev_pairs[i] = torch.as_tensor(np.ascontiguousarray(self._pairs[i])).to(self.device)
+    return ops.sample_triplets(pairs, start, self.batch_size, len(FEATURES), self.seed + 7919 * i, out=out)
+
   def get_batch_indices(self):
     """Next [B,3] int64 (anchor, positive, negative) guid-index triplets as a host array, or None at end of data."""
     if self._iter is None:
@@ -131,7 +171,7 @@ class MPTripletPipe(object):
     return out.view(idx.shape[0], 3, table.shape[1]).cpu().numpy()
 
   def __del__(self):
-    self._iter = None
+    self._iter = self._dev_iter = None
 
 
 class TripletPipe(BasePipe):

@@ -221,6 +221,18 @@ def fill_column16(X16, col, value):
                                        dtype16_of(X16), stream_ptr()))
 
 
+def sample_triplets(pairs, start, B, num_guid, seed, out=None):
+  """[B,3] int64 (anchor, positive, negative) index triplets from device-resident pairs [n,2] (cdml_sample_triplets)."""
+  if pairs.dtype != torch.int64 or pairs.dim() != 2 or pairs.shape[1] != 2 or not pairs.is_contiguous():
+    raise TypeError("pairs must be a contiguous int64 [n,2] tensor")
+  if out is None:
+    out = torch.empty((B, 3), dtype=torch.int64, device=pairs.device)
+  _count(1)
+  check(_lib.load().cdml_sample_triplets(_ctx(pairs), ptr(pairs), pairs.shape[0], int(start), int(B), int(num_guid),
+                                         int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(out), stream_ptr()))
+  return out
+
+
 def desim(eI, fI, fD=None, fD_threshold=1.4, f_end=31, out=None):
   """De-similarity filter of KNN lists (cdml_desim; faiss_knn.py:187-244).  eI [n,ke] int64, fI [nf,kf] int64, fD [nf,kf]
   fp32 device tensors -> int64 [n,ke] with dropped entries -1."""

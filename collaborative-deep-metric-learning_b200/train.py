@@ -34,6 +34,7 @@ if "train_dir" not in FLAGS:
   flags.DEFINE_integer("num_epochs", 8, "passes over each *.train file (train.py:359)")
   flags.DEFINE_integer("batch_size", 1024, "triplets per step (train.py:360)")
   flags.DEFINE_boolean("mine_semihard", False, "in-batch semi-hard negative mining (SURVEY 8a row M)")
+  flags.DEFINE_boolean("device_reader", False, "sample the index triplets on the GPU (cdml_sample_triplets; SURVEY 8f row 3)")
   flags.DEFINE_string("compute_dtype", "fp16", "tensor-core operand type: fp16 | bf16 (fp32 accumulate)")
 
 
@@ -254,7 +255,9 @@ class Trainer():
     while True:
       try:
         fetch_start_time = time.time()
-        if fused:
+        if fused and getattr(self.pipe, "device_reader", False):
+          batch = self.pipe.get_batch_indices_device()            # triplets sampled on the GPU: no host work per step
+        elif fused:
           idx = self.pipe.get_batch_indices()
           batch = None if idx is None else torch.as_tensor(idx).to(engine.device, non_blocking=True)
         else:
@@ -312,7 +315,8 @@ def main(args):
     rank = torch.distributed.get_rank() if pg is not None else 0
     world = torch.distributed.get_world_size() if pg is not None else 1
     pipe = inputs.MPTripletPipe(cowatch_file_patten=FLAGS.train_dir + "/*.train",
-                                feature_file=FLAGS.train_dir + "/features.npy", wait_times=20, rank=rank, world=world)
+                                feature_file=FLAGS.train_dir + "/features.npy", wait_times=20, rank=rank, world=world,
+                                device_reader=FLAGS.device_reader)
     eval_cowatches = load_cowatches(FLAGS.train_dir + "/cowatches.eval")
     test_cowatches = load_cowatches(FLAGS.train_dir + "/cowatches.test")
     model = find_class_by_name(FLAGS.model, [models])()

@@ -185,6 +185,13 @@ int cdml_desim(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e
 int cdml_desim_simple(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int64_t* fI, int kf,
                       int64_t ld_f, int64_t* out, int64_t ld_out, void* stream);
 
+/* ---- on-device triplet reader -- replaces MPTripletPipe.subprocess + parse_data.yield_negative_index (inputs.py:102-142,
+ *      parse_data.py:292-298) for a *.train file whose pairs [n_pairs,2] int64 are resident on the device.
+ *      out[i] = (a, p, n), (a,p) = pairs[(start+i) % n_pairs], n uniform in [0,num_guid) re-drawn while n in {a,p}.
+ *      Generator: Philox4x32-10, key = seed, counter = (start+i, attempt); Lemire multiply-shift with rejection. */
+int cdml_sample_triplets(cdml_ctx* ctx, const int64_t* pairs, int64_t n_pairs, int64_t start, int64_t B, int64_t num_guid,
+                         uint64_t seed, int64_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -595,6 +595,47 @@ def rencode_eval(features, cowatches):
 
 
 # --------------------------------------------------------------------------- #
+# on-device triplet reader (inputs.py:102-142 with a counter-based generator)   #
+# --------------------------------------------------------------------------- #
+def philox4x32_10(ctr, key):
+  """Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11).  ctr: 4 arrays
+  of uint32 values, key: 2 ints.  Pinned in tests to the Random123 known-answer vectors."""
+  c = [np.asarray(x, np.uint64) for x in ctr]
+  k = [np.uint64(key[0]), np.uint64(key[1])]
+  mask = np.uint64(0xFFFFFFFF)
+  for _ in range(10):
+    p0 = np.uint64(0xD2511F53) * c[0]
+    p1 = np.uint64(0xCD9E8D57) * c[2]
+    c = [((p1 >> np.uint64(32)) ^ c[1] ^ k[0]) & mask, p1 & mask, ((p0 >> np.uint64(32)) ^ c[3] ^ k[1]) & mask, p0 & mask]
+    k = [(k[0] + np.uint64(0x9E3779B9)) & mask, (k[1] + np.uint64(0xBB67AE85)) & mask]
+  return c
+
+
+def sample_triplets_device(pairs, start, B, num_guid, seed):
+  """The device reader's statement of inputs.py:112-130: (a,p) = pairs[(start+i) % n]; n = randint(0,G) re-drawn while
+  n in {a,p}.  randint = word 0 of Philox4x32-10(key=seed, counter=(position, attempt)) mapped to [0,G) by Lemire's
+  multiply-shift with its rejection step (exactly uniform)."""
+  pairs = np.asarray(pairs, np.int64)
+  pos = np.arange(start, start + B, dtype=np.uint64)
+  ap = pairs[(pos % np.uint64(len(pairs))).astype(np.int64)]
+  G = np.uint64(num_guid)
+  threshold = np.uint64((2 ** 32) % int(num_guid))
+  neg = np.full(B, -1, np.int64)
+  attempt = np.zeros(B, np.uint64)
+  todo = np.arange(B)
+  while len(todo):
+    x = philox4x32_10((pos[todo] & np.uint64(0xFFFFFFFF), pos[todo] >> np.uint64(32), attempt[todo], np.zeros(len(todo), np.uint64)),
+                      (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))[0]
+    m = x * G
+    cand = (m >> np.uint64(32)).astype(np.int64)
+    ok = ((m & np.uint64(0xFFFFFFFF)) >= threshold) & (cand != ap[todo, 0]) & (cand != ap[todo, 1])
+    neg[todo[ok]] = cand[ok]
+    attempt[todo] += np.uint64(1)
+    todo = todo[~ok]
+  return np.concatenate([ap, neg[:, None]], axis=1)
+
+
+# --------------------------------------------------------------------------- #
 # de-similarity post-filter (faiss_knn.py:134-244)                              #
 # --------------------------------------------------------------------------- #
 def desim_simple(eI, fI):

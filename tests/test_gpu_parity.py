@@ -768,3 +768,49 @@ def test_strict_and_cross_knn_flows_match_oracle_composition(cd, tmp_path):
   assert_knn_matches(cD[doc_location:], cI[doc_location:], dvD, dvI, "L2", en[:doc_location], en[doc_location:])
   assert np.array_equal(cI_desim, O.iter_desim(cI, fI, fD, 1.4, 31))
   assert np.array_equal(np.load(out + "/crossI_desim.npy"), cI_desim) and os.path.exists(os.path.join(out, "cross_knn9"))
+
+
+# ---------------------------------------------------------------- on-device triplet reader
+def test_device_reader_bit_exact_vs_oracle_and_pipe_integration(cd, tmp_path):
+  """cdml_sample_triplets against the oracle's statement of the same counter-based sampler (integer work: bit-exact),
+  its distributional contract, and MPTripletPipe(device_reader=True) end to end."""
+  rng = np.random.RandomState(2)
+  for n_pairs, G, start, B, seed in ((1000, 1000, 0, 4096, 5), (77, 5000, 123456789, 1000, 2 ** 40 + 17), (1, 3, 0, 64, 1),
+                                     (50000, 4000000000, 2 ** 33, 2048, 9)):
+    pairs = rng.randint(0, min(G, 2 ** 31), (n_pairs, 2)).astype(np.int64)
+    pairs[:, 1] = (pairs[:, 0] + 1 + pairs[:, 1] % (G - 1)) % G
+    got = cd.ops.sample_triplets(dev_t(cd, pairs), start, B, G, seed).cpu().numpy()
+    assert np.array_equal(got, O.sample_triplets_device(pairs, start, B, G, seed)), (n_pairs, G)
+    assert ((got[:, 2] != got[:, 0]) & (got[:, 2] != got[:, 1]) & (got[:, 2] >= 0) & (got[:, 2] < G)).all()
+  G = 2000
+  pairs = np.stack([np.arange(G), (np.arange(G) + 7) % G], 1).astype(np.int64)
+  t = cd.ops.sample_triplets(dev_t(cd, pairs), 0, 1000000, G, 3).cpu().numpy()
+  h = np.bincount(t[:, 2], minlength=G)
+  assert abs(h - 500.0).max() < 6 * np.sqrt(500.0)                               # uniform negatives
+  assert cd.ops.sample_triplets(dev_t(cd, pairs), 0, 0, G, 3).shape == (0, 3)
+  # the pipe: device batches == oracle sampler at the positions the host reader would serve; a trainer consumes them
+  feats = O.synth_features(300, 1500, 0)
+  np.save(tmp_path / "features.npy", feats)
+  for i, n in enumerate((700, 333)):
+    with open(tmp_path / ("cowatches_%d.train" % i), "w") as f:
+      for a, p in O.synth_pairs(n, 300, seed=10 + i):
+        f.write("%d,%d\n" % (a, p))
+  pipe = cd.inputs.MPTripletPipe(str(tmp_path / "*.train"), str(tmp_path / "features.npy"), seed=4, device_reader=True)
+  pipe.create_pipe(num_epochs=2, batch_size=128)
+  pos = list(pipe._position_batches())
+  served = 0
+  while True:
+    b = pipe.get_batch_indices_device()
+    if b is None:
+      break
+    i, start = pos[served]
+    assert np.array_equal(b.cpu().numpy(), O.sample_triplets_device(pipe._pairs[i], start, 128, 300, 4 + 7919 * i))
+    served += 1
+  assert served == len(pos) == (1400 // 128) + (666 // 128)
+  pipe.create_pipe(num_epochs=2, batch_size=128)
+  trainer = cd.train.Trainer(pipe=pipe, num_epochs=2, batch_size=128, model=cd.models.VNet(), loss_fn=cd.losses.HingeLoss(),
+                             learning_rate=1e-3, margin=0.8, checkpoint_dir=str(tmp_path / "ckpt"),
+                             optimizer_class=cd.train.AdamOptimizer, config=None, eval_cowatches=np.array([[0, 1], [2, 3]]),
+                             test_cowatches=np.array([[4, 5]]), check_stop_epoch=3, max_steps=6)
+  eng = trainer.run()
+  assert eng.global_step == 6

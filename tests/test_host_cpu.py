@@ -262,3 +262,27 @@ def test_fusion_towers_compile_to_the_oracle_op_lists():
   # a plain chain still compiles as a graph (the GraphEngine then fuses its last layer with the output l2norm)
   g = models.compile_graph(models.VNet().create_model(models.placeholder(1500))["l2_norm"])
   assert [e["op"] for e in g["spec"]] == ["input", "fc", "fc", "l2norm"]
+
+
+def test_device_reader_serves_positions_in_the_host_readers_order(lib, tmp_path):
+  """`_position_batches` (what the device reader iterates) walks the files exactly as `_index_batches` does: same
+  (anchor, positive) pairs per batch, same rank sharding, trailing partial batches dropped."""
+  import cdml_b200  # noqa: F401
+  from cdml_b200 import inputs
+  _write_dataset(tmp_path)
+  for world in (1, 2):
+    for rank in range(world):
+      pipe = inputs.MPTripletPipe(str(tmp_path / "*.train"), str(tmp_path / "features.npy"), rank=rank, world=world,
+                                  device_reader=True)
+      pipe.create_pipe(num_epochs=3, batch_size=4)
+      host = []
+      while True:
+        b = pipe.get_batch_indices()
+        if b is None:
+          break
+        host.append(b)
+      pos = list(pipe._position_batches())
+      assert len(host) == len(pos) > 0
+      for batch, (i, start) in zip(host, pos):
+        want = O.sample_triplets_device(pipe._pairs[i], start, 4, len(inputs.FEATURES), pipe.seed + 7919 * i)
+        assert np.array_equal(batch[:, :2], want[:, :2])

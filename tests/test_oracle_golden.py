@@ -275,3 +275,27 @@ def test_desim_oracle_equals_reference_iter_desim_mp():
     assert np.array_equal(O.desim_simple(eI, fI), g[name + "_simple"]), name
     assert all(np.array_equal(a, b) for a, b in zip(keep, (eI, fI, fD)))          # the oracle does not mutate its inputs
   assert (g["b_out"] == -1).mean() > (g["b_eI"] == -1).mean()                     # something was actually filtered
+
+
+# ---------------------------------------------------------------- device reader generator
+def test_philox4x32_10_known_answers_and_sampler_properties():
+  """Random123 known-answer vectors (kat_vectors: philox4x32 10) pin the generator the device reader is stated with;
+  the sampler never returns the anchor or the positive and is uniform over the rest."""
+  kat = (((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+         ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+         ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+          (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)))
+  for ctr, key, want in kat:
+    assert tuple(int(x) for x in O.philox4x32_10(ctr, key)) == want
+  G = 1000
+  pairs = np.stack([np.arange(G), (np.arange(G) + 1) % G], 1)
+  t = O.sample_triplets_device(pairs, 5, 300000, G, seed=5)
+  assert np.array_equal(t[:, :2], pairs[(5 + np.arange(300000)) % G])            # wrap-around over the file
+  assert ((t[:, 2] != t[:, 0]) & (t[:, 2] != t[:, 1])).all() and t[:, 2].min() == 0 and t[:, 2].max() == G - 1
+  h = np.bincount(t[:, 2], minlength=G)
+  assert abs(h - 300.0).max() < 6 * np.sqrt(300.0)                               # uniform: 6 sigma of a Poisson(300) bin
+  tiny = O.sample_triplets_device(np.array([[0, 1]]), 0, 64, 3, seed=1)          # only one id is admissible
+  assert (tiny[:, 2] == 2).all()
+  a = O.sample_triplets_device(pairs, 0, 100, G, seed=7)
+  b = O.sample_triplets_device(pairs, 50, 50, G, seed=7)
+  assert np.array_equal(a[50:], b)                                               # a position owns its stream
