@@ -227,6 +227,8 @@ def sample_triplets(pairs, start, B, num_guid, seed, out=None):
     raise TypeError("pairs must be a contiguous int64 [n,2] tensor")
   if out is None:
     out = torch.empty((B, 3), dtype=torch.int64, device=pairs.device)
+  if B == 0:
+    return out
   _count(1)
   check(_lib.load().cdml_sample_triplets(_ctx(pairs), ptr(pairs), pairs.shape[0], int(start), int(B), int(num_guid),
                                          int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(out), stream_ptr()))
