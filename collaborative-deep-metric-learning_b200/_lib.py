@@ -42,6 +42,9 @@ _SIGNATURES = {
                          c_int64, _P]),
   "cdml_desim_simple": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, _P]),
   "cdml_sample_triplets": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, ctypes.c_uint64, _P, _P]),
+  "cdml_format_knn_rows": (c_int64, [_P, _P, c_int64, c_int, c_int64, c_int64, _P, _P, c_int64, _P, c_int64]),
+  "cdml_format_f32": (c_int64, [_P, c_int64, _P, c_int64]),
+  "cdml_parse_features_txt": (c_int64, [_P, c_int64, c_int, _P, c_int64, _P, _P, c_int]),
   "cdml_cast16": (c_int, [_P, _P, c_int64, _P, c_int, _P]),
   "cdml_fill_column16": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_float, c_int, _P]),
   "cdml_mine_semihard": (c_int, [_P, _P, c_int64, c_int, _P, c_int64, _P, c_int64, c_int, c_float, _P, _P, _P]),

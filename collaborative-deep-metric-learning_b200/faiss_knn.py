@@ -5,7 +5,7 @@ fp32 re-rank); with WORLD_SIZE>1 the index is row-sharded over the ranks and the
 and merged on the GPU.  The de-similarity post-filter (`desim`, `fliter_fI`, `iter_desim_mp`, faiss_knn.py:134-244) runs as
 libcdml's cdml_desim kernels; `strict_knn` / `cross_knn` (faiss_knn.py:308-351) compose them with calc_knn."""
 import json
-import multiprocessing as mp
+from multiprocessing.pool import ThreadPool
 import os
 import shutil
 import time
@@ -207,12 +207,44 @@ def format_rows(begin_index, D, I, decode_map):
   return lines
 
 
+class GuidTable(object):
+  """The decode map {0: guid, ..., n-1: guid} as one UTF-8 blob + offsets: what cdml_format_knn_rows indexes."""
+
+  def __init__(self, decode_map):
+    n = len(decode_map)
+    try:
+      guids = [decode_map[i].encode("utf-8") for i in range(n)]
+    except KeyError:
+      raise KeyError("the decode map must hold every row index 0..%d" % (n - 1))
+    self.n = n
+    self.max_len = max((len(g) for g in guids), default=0)
+    self.offsets = np.zeros(n + 1, np.int64)
+    np.cumsum([len(g) for g in guids], out=self.offsets[1:])
+    self.blob = np.frombuffer(b"".join(guids) + b"\0", np.uint8)
+
+
+def format_rows_bytes(begin_index, D, I, table):
+  """The bytes of `format_rows` for a block of rows, produced by libcdml (cdml_format_knn_rows, host code)."""
+  from . import _lib
+  D = np.ascontiguousarray(D, np.float32)
+  I = np.ascontiguousarray(I, np.int64)
+  nq, k = I.shape
+  out = np.empty(nq * (table.max_len + 2 + (k - 1) * (table.max_len + 42)) + 64, np.uint8)
+  n = _lib.load().cdml_format_knn_rows(D.ctypes.data, I.ctypes.data, nq, k, k, int(begin_index), table.blob.ctypes.data,
+                                       table.offsets.ctypes.data, table.n, out.ctypes.data, out.size)
+  if n < 0:
+    _lib.check(-1)
+  return out[:n].tobytes()
+
+
 def write_process(path, index, begin_index, D, I, prefix='knn_split', decode_map=None):
   """One shard file `<path>/<prefix><index>` (faiss_knn.py:267-283)."""
   decode_map = DECODE_MAP if decode_map is None else decode_map
+  table = decode_map if isinstance(decode_map, GuidTable) else GuidTable(decode_map)
   try:
-    with open(os.path.join(path, prefix + str(index)), 'w') as fp:
-      fp.writelines(format_rows(begin_index, D, I, decode_map))
+    with open(os.path.join(path, prefix + str(index)), 'wb') as fp:
+      for lo in range(0, I.shape[0], 65536):                         # bounded scratch: 64k rows at a time
+        fp.write(format_rows_bytes(begin_index + lo, D[lo:lo + 65536], I[lo:lo + 65536], table))
   except Exception:
     print(traceback.format_exc())
     raise
@@ -222,6 +254,7 @@ def write_knn(knn_result, split_num=10, D=None, I=None, prefix='knn_result', dec
   """split_num contiguous patches, the last takes the remainder, one process each (faiss_knn.py:285-305)."""
   os.makedirs(knn_result, exist_ok=True)
   decode_map = DECODE_MAP if decode_map is None else decode_map
+  table = GuidTable(decode_map)
   total_num = D.shape[0]
   patch_num = total_num // split_num
   begin = time.time()
@@ -229,13 +262,10 @@ def write_knn(knn_result, split_num=10, D=None, I=None, prefix='knn_result', dec
   for i in range(split_num):
     lo = i * patch_num
     hi = (i + 1) * patch_num if i < split_num - 1 else total_num
-    jobs.append((knn_result, i, lo, D[lo:hi], I[lo:hi], prefix, decode_map))
-  if total_num >= 200000:
-    with mp.get_context("fork").Pool(processes=split_num) as pool:
-      pool.starmap(write_process, jobs)
-  else:
-    for job in jobs:
-      write_process(*job)
+    jobs.append((knn_result, i, lo, D[lo:hi], I[lo:hi], prefix, table))
+  # the formatter is native code called through ctypes (GIL released): threads replace the reference's process pool
+  with ThreadPool(processes=min(split_num, os.cpu_count() or 1)) as pool:
+    pool.starmap(write_process, jobs)
   print('write_knn cost: %fs' % (time.time() - begin))
 
 

@@ -30,29 +30,30 @@ def feature_size():
     return FLAGS["feature_size"].default
 
 
-def read_features_txt(filename, width=None):
-  """Lines 'guid#f1,f2,...' -> (float32 [n,width], {guid:i}, {i:guid}); rows of the wrong width are dropped."""
+def read_features_txt(filename, width=None, num_threads=0):
+  """Lines 'guid#f1,f2,...' -> (float32 [n,width], {guid:i}, {i:guid}); lines without exactly one '#', with a field that
+  float() would reject or with another field count are dropped (online_data.py:48-84).  Parsed by libcdml's host code
+  (cdml_parse_features_txt: the file image is split into lines and parsed on all cores)."""
+  from . import _lib
   width = feature_size() if width is None else width
-  rows, encode_map, decode_map = [], {}, {}
-  with open(filename, "r") as f:
-    for line in f:
-      line = line.rstrip("\n")
-      parts = line.split("#")
-      if len(parts) != 2:
-        logging.warning("read_features_txt: malformed line dropped")
-        continue
-      try:
-        vals = np.array(parts[1].split(","), dtype=np.float64)
-      except ValueError as e:
-        logging.warning("read_features_txt: drop feature. %s", e)
-        continue
-      if vals.shape[0] != width:
-        continue
-      encode_map[parts[0]] = len(rows)
-      decode_map[len(rows)] = parts[0]
-      rows.append(vals.astype(np.float32))
-  feats = np.stack(rows).astype(np.float32) if rows else np.zeros((0, width), np.float32)
-  return feats, encode_map, decode_map
+  data = np.fromfile(filename, dtype=np.uint8)
+  if data.size == 0:
+    return np.zeros((0, width), np.float32), {}, {}
+  max_rows = int(np.count_nonzero(data == 10)) + 1
+  feats = np.empty((max_rows, width), np.float32)
+  gb, gl = np.empty(max_rows, np.int64), np.empty(max_rows, np.int32)
+  n = _lib.load().cdml_parse_features_txt(data.ctypes.data, data.size, int(width), feats.ctypes.data, max_rows,
+                                          gb.ctypes.data, gl.ctypes.data, int(num_threads))
+  if n < 0:
+    _lib.check(-1)
+  raw = data.tobytes()
+  encode_map, decode_map = {}, {}
+  for i in range(n):
+    guid = raw[gb[i]:gb[i] + gl[i]].decode("utf-8")
+    encode_map[guid] = i
+    decode_map[i] = guid
+  logging.info("read_features_txt drop features count:%d", max_rows - n)
+  return feats[:n].copy() if n < max_rows else feats, encode_map, decode_map
 
 
 def read_features_npy(filename):

@@ -192,6 +192,23 @@ int cdml_desim_simple(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64
 int cdml_sample_triplets(cdml_ctx* ctx, const int64_t* pairs, int64_t n_pairs, int64_t start, int64_t B, int64_t num_guid,
                          uint64_t seed, int64_t* out, void* stream);
 
+/* ---- host-side text formats either side of the path (HOST pointers, no device work) ---------------------------------
+ * cdml_format_knn_rows: the line format of faiss_knn.write_process (faiss_knn.py:267-283) for rows [begin_index,
+ *      begin_index+nq): '<guid[q]>,' then for columns 1..k-1 with I > 0 and 0 < D < 1.4: '<guid[I]>#<str(np.float32(D))><',
+ *      then '\n'.  guid_blob / guid_off [n_guids+1]: the decode map as one UTF-8 blob + offsets.  Returns the number of
+ *      bytes written to out (capacity cap), or -1.
+ * cdml_format_f32: str(numpy.float32(v)) + '\n' per value (the float formatting used above, exposed for tests).
+ * cdml_parse_features_txt: online_data.read_features_txt (online_data.py:48-84) over a whole file image: every line
+ *      'guid#f1,...,f<width>' whose fields parse as Python float() does (text -> double -> float32) becomes a row of out
+ *      [max_rows,width] (max_rows >= number of lines), kept rows compacted to the front in file order; guid_begin /
+ *      guid_len give each kept row's guid as a slice of buf.  Lines without exactly one '#', with an unparsable field or
+ *      with another field count are dropped.  Returns the number of kept rows, or -1. */
+int64_t cdml_format_knn_rows(const float* D, const int64_t* I, int64_t nq, int k, int64_t ld, int64_t begin_index,
+                             const char* guid_blob, const int64_t* guid_off, int64_t n_guids, char* out, int64_t cap);
+int64_t cdml_format_f32(const float* v, int64_t n, char* out, int64_t cap);
+int64_t cdml_parse_features_txt(const char* buf, int64_t len, int width, float* out, int64_t max_rows, int64_t* guid_begin,
+                                int32_t* guid_len, int num_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -286,3 +286,70 @@ def test_device_reader_serves_positions_in_the_host_readers_order(lib, tmp_path)
       for batch, (i, start) in zip(host, pos):
         want = O.sample_triplets_device(pipe._pairs[i], start, 4, len(inputs.FEATURES), pipe.seed + 7919 * i)
         assert np.array_equal(batch[:, :2], want[:, :2])
+
+
+# ---------------------------------------------------------------- native text formats
+def test_native_float32_formatting_equals_numpy_str(lib):
+  """cdml_format_f32 == str(np.float32(v)) (the distance format of knn_split*, faiss_knn.py:277) on 400k values: the KNN
+  distance range, tiny values in scientific notation, both notation thresholds, signs and specials."""
+  from cdml_b200 import _lib
+  rng = np.random.RandomState(0)
+  v = np.concatenate([rng.rand(250000).astype(np.float32) * 1.4, (rng.rand(50000) * 1e-3).astype(np.float32),
+                      np.float32(10) ** rng.uniform(-12, 20, 100000).astype(np.float32),
+                      np.array([1.0, 0.5, 1e-4, 9.9999e-5, 1e6, 999999.94, 123456.0, 0.1, 1e-5, 5e-5, 3e10, 0.0, -0.0, -2.5, 1.4,
+                                1e-45, 3.4028235e38, np.inf, -np.inf, np.nan], np.float32)])
+  out = np.empty(32 * len(v), np.uint8)
+  n = _lib.load().cdml_format_f32(v.ctypes.data, len(v), out.ctypes.data, out.size)
+  assert out[:n].tobytes().decode().split("\n")[:-1] == [str(x) for x in v]
+
+
+def test_native_knn_row_formatter_equals_python_statement_and_golden(lib, tmp_path):
+  from cdml_b200 import faiss_knn
+  rng = np.random.RandomState(1)
+  n, k = 500, 12
+  decode = {i: ("g%d" % i if i % 7 else "视频_%d" % i) for i in range(n)}                    # non-ASCII guids too
+  I = rng.randint(-1, n, (n, k)).astype(np.int64)
+  D = (rng.rand(n, k) * 1.6).astype(np.float32)
+  D[rng.rand(n, k) < 0.05] = 0.0
+  D[3, 4], D[5, 6], D[7, 8] = np.float32(1.4), np.float32(1e-7), np.inf
+  table = faiss_knn.GuidTable(decode)
+  want = "".join(O.format_knn_rows(0, D, I, decode)).encode("utf-8")
+  assert faiss_knn.format_rows_bytes(0, D, I, table) == want
+  assert faiss_knn.format_rows_bytes(100, D[100:160], I[100:160], table) == "".join(O.format_knn_rows(100, D[100:160], I[100:160], decode)).encode("utf-8")
+  assert "".join(faiss_knn.format_rows(0, D, I, decode)).encode("utf-8") == want
+  faiss_knn.write_knn(str(tmp_path), split_num=3, D=D, I=I, prefix="knn_split", decode_map=decode)
+  got = b"".join(open(tmp_path / ("knn_split%d" % j), "rb").read() for j in range(3))
+  assert got == want
+  bad = I.copy()
+  bad[0, 1], D[0, 1] = n + 3, 0.5
+  with pytest.raises(Exception):
+    faiss_knn.format_rows_bytes(0, D, bad, table)
+
+
+def test_native_feature_text_reader_follows_python_float_semantics(lib, tmp_path):
+  from cdml_b200 import online_data
+  lines = ["a#1,2.5,-3e-2", "b#1,2", "c#1,2,x", "no hash here", "d#4,5,6#7", "e# 7 ,+8.0,\t9e0", "f#inf,-Infinity,nan",
+           "g#1e999,1e-999,.5", "", "h#0.1,0.2,0.30000001192092896\r", "视频#1,1,1", "a#9,9,9", "i#1,,3", "j#1_0,2,3",
+           "k#0x10,2,3", "l#5.,6.,7."]
+  path = tmp_path / "features.txt"
+  path.write_text("\n".join(lines), encoding="utf-8")                                       # no newline after the last line
+  feats, enc, dec = online_data.read_features_txt(str(path), width=3, num_threads=3)
+  want_rows, want_guids = [], []
+  for line in lines:                                                                          # online_data.py:66-77
+    parts = line.split("#")
+    if len(parts) != 2:
+      continue
+    try:
+      if "_" in parts[1]:
+        raise ValueError("digit separators are not accepted by the native reader (documented deviation)")
+      vals = list(map(float, parts[1].split(",")))
+    except ValueError:
+      continue
+    if len(vals) == 3:
+      want_rows.append(np.asarray(vals, np.float64).astype(np.float32))
+      want_guids.append(parts[0])
+  assert [dec[i] for i in range(len(dec))] == want_guids and len(want_guids) == 8
+  assert np.array_equal(feats, np.stack(want_rows), equal_nan=True) and feats.dtype == np.float32
+  assert enc["a"] == want_guids.index("a", 1) and enc["视频"] == want_guids.index("视频")   # a later duplicate guid wins
+  (tmp_path / "empty.txt").write_text("")
+  assert online_data.read_features_txt(str(tmp_path / "empty.txt"), width=3)[0].shape == (0, 3)
