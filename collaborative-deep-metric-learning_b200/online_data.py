@@ -46,10 +46,10 @@ def read_features_txt(filename, width=None, num_threads=0):
                                           gb.ctypes.data, gl.ctypes.data, int(num_threads))
   if n < 0:
     _lib.check(-1)
-  raw = data.tobytes()
   encode_map, decode_map = {}, {}
+  view = memoryview(data)
   for i in range(n):
-    guid = raw[gb[i]:gb[i] + gl[i]].decode("utf-8")
+    guid = bytes(view[gb[i]:gb[i] + gl[i]]).decode("utf-8")
     encode_map[guid] = i
     decode_map[i] = guid
   logging.info("read_features_txt drop features count:%d", max_rows - n)
