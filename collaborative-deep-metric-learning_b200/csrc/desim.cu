@@ -212,14 +212,28 @@ desim_simple_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t l
   }
 }
 
-template <int E>
-static void launch_rows(int fc, int grid, cudaStream_t st, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int32_t* F,
-                        int64_t nf, int fw, int fw_pad, int64_t* out, int64_t ld_o, int32_t* flags) {
+template <int E, int FC>
+static int launch_rows_fc(cdml_ctx* ctx, cudaStream_t st, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int32_t* F,
+                          int64_t nf, int fw, int fw_pad, int64_t* out, int64_t ld_o) {
   constexpr int W = DesimCfg<E>::kWarps;
-  const int64_t blocks = (n + W - 1) / W;
-  if (blocks < grid) grid = static_cast<int>(blocks);
-  if (fc == 1) desim_rows_kernel<E, 1><<<grid, W * 32, 0, st>>>(eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o, flags);
-  else desim_rows_kernel<E, 2><<<grid, W * 32, 0, st>>>(eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o, flags);
+  auto kern = desim_rows_kernel<E, FC>;
+  static int resident = 0;               // CTAs per SM: the grid is exactly one wave (rows are strided over it)
+  if (resident == 0) {
+    CDML_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, W * 32, 0));
+    if (resident < 1) resident = 1;
+  }
+  const int64_t blocks = (n + W - 1) / W, cap = static_cast<int64_t>(ctx->num_sms) * resident;
+  kern<<<static_cast<int>(blocks < cap ? blocks : cap), W * 32, 0, st>>>(eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o,
+                                                                        ctx->dev_flags);
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int E>
+static int launch_rows(cdml_ctx* ctx, int fc, cudaStream_t st, const int64_t* eI, int64_t n, int ke, int64_t ld_e,
+                       const int32_t* F, int64_t nf, int fw, int fw_pad, int64_t* out, int64_t ld_o) {
+  if (fc == 1) return launch_rows_fc<E, 1>(ctx, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o);
+  return launch_rows_fc<E, 2>(ctx, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o);
 }
 
 static inline int desim_width(int kf, int f_end) { return f_end < kf ? f_end : kf; }
@@ -255,16 +269,13 @@ int cdml_desim(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e
                                                                                       fD_threshold, fw, fw_pad, F);
     CDML_CHECK_CUDA(cudaGetLastError());
   }
-  const int grid = ctx->num_sms * 16;    // capped to the number of row groups inside launch_rows
   const int fc = fw_pad / 32;
   const int e = (ke + 31) / 32;
-  if (e <= 1) launch_rows<1>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
-  else if (e == 2) launch_rows<2>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
-  else if (e == 3) launch_rows<3>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
-  else if (e == 4) launch_rows<4>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
-  else launch_rows<8>(fc, grid, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, ctx->dev_flags);
-  CDML_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  if (e <= 1) return launch_rows<1>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out);
+  if (e == 2) return launch_rows<2>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out);
+  if (e == 3) return launch_rows<3>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out);
+  if (e == 4) return launch_rows<4>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out);
+  return launch_rows<8>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out);
 }
 
 int cdml_desim_simple(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int64_t* fI, int kf,
