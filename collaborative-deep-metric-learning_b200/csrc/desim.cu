@@ -44,13 +44,15 @@ desim_prepare_kernel(const int64_t* __restrict__ fI, const float* __restrict__ f
 //  (2) resolution, sequential but sparse: alive = valid columns; for each column c WITH a non-empty kill mask, ascending:
 //      if alive[c]: alive &= ~kill[c].
 // History on 4M x 81 rows (ncu, profiles/): column walk with fw x ke comparisons 184 ms -> hash probe per neighbour, walk
-// in column order with 4 prefetched pivots 62.6 ms (14 k instructions per row, issue-bound) -> this form 35.1 ms.
+// in column order with 4 prefetched pivots 62.6 ms (14 k instructions per row, issue-bound) -> this form 35.1 ms -> one-wave
+// grid, two-bit blocked Bloom words, 256-slot hash 32.0 ms (4.3 k instructions per row; 8 -> 4 gathers in flight per warp
+// costs 35 %: the kernel lives on memory-level parallelism x resident warps, 70 registers and 5 KB of row state per warp).
 // Tried and measured slower (39.9 ms, commit 90c5b28): a persistent CTA per SM whose warps stage all ke gathers of a row
 // with cp.async.bulk behind an mbarrier (12 KB of staging per warp leaves 11 warps per SM; the kernel is bound by the
 // dependent shared-memory chains of the probes, not by the number of gathers in flight).
 template <int E>
 struct DesimCfg {
-  static constexpr int kSlots = E <= 1 ? 128 : E == 2 ? 256 : E <= 4 ? 512 : 1024;   // load factor <= 0.25
+  static constexpr int kSlots = E <= 1 ? 64 : E == 2 ? 128 : E <= 4 ? 256 : 512;     // load factor <= 0.5
   static constexpr int kWarps = E <= 2 ? 8 : E <= 4 ? 4 : 2;                        // static shared memory <= 30 KB
 };
 constexpr int kUnroll = 8;
