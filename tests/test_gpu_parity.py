@@ -814,3 +814,17 @@ def test_device_reader_bit_exact_vs_oracle_and_pipe_integration(cd, tmp_path):
                              test_cowatches=np.array([[4, 5]]), check_stop_epoch=3, max_steps=6)
   eng = trainer.run()
   assert eng.global_step == 6
+
+
+@pytest.mark.parametrize("N,d,nq,k", [(6000, 1628, 700, 26), (3000, 300, 300, 26), (40000, 1500, 1200, 26), (2500, 8, 100, 5)])
+def test_flat_knn_over_raw_feature_widths(cd, N, d, nq, k):
+  """The raw-feature KNN of faiss_knn.main (faiss_knn.py:378: calc_knn(features, nearest_num=desim_nearest_num)) runs on
+  1628- / 1500-wide rows, i.e. outside the d <= 256 resident-panel kernels: generic tcgen05 scans, long-row re-rank."""
+  rng = np.random.RandomState(12)
+  X = O.knn_normalize(rng.rand(N, d).astype(np.float32) + 0.05 * rng.standard_normal((N, d)).astype(np.float32))
+  index = cd.ops.FlatIndex(dev_t(cd, X), "L2")
+  D, I = index.search(dev_t(cd, X[:nq]), k)
+  Dw, Iw = O.flat_knn(X, X[:nq], k=k, l2_norm=False)
+  assert_knn_matches(D.cpu().numpy(), I.cpu().numpy(), Dw, Iw, "L2", X, X[:nq])
+  assert (I[:, 0].cpu().numpy() == np.arange(nq)).all()
+  index.close()
