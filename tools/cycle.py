@@ -1,6 +1,7 @@
 """Local, HDFS-free composition of the reference's serving cycle (cdml_run.sh:73-150; BASELINE configs[4]) through the
 public API: train (train.Trainer on *.train index triplets) -> embed every guid (predict.Prediction.run_features) ->
-exact top-k KNN (faiss_knn.calc_knn semantics, device resident) -> knn_split* files (faiss_knn.write_knn).
+exact top-k KNN (faiss_knn.calc_knn semantics, device resident) -> raw-feature KNN + de-similarity filter
+(faiss_knn.py:376-378, iter_desim_mp) -> knn_split* files (faiss_knn.write_knn, native formatter).
 
   python tools/cycle.py [--guids G] [--triplets T] [--batch B] [--knn-k K] [--write-rows R] [--out DIR]
 
@@ -28,6 +29,8 @@ ap.add_argument("--batch", type=int, default=65536)
 ap.add_argument("--knn-k", type=int, default=100)
 ap.add_argument("--write-rows", type=int, default=100000, help="rows of the KNN result formatted into knn_split* files")
 ap.add_argument("--out", default="")
+ap.add_argument("--no-desim", action="store_true", help="skip the raw-feature KNN + de-similarity stage")
+ap.add_argument("--feat-k", type=int, default=26, help="desim_nearest_num (faiss_knn.py:46)")
 ap.add_argument("--mine", action="store_true", help="in-batch semi-hard mining (default: the reference's random negatives)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -47,12 +50,15 @@ def tick(name, t0):
 t0 = time.time()
 eng = engine.TowerEngine([F, 5000, 256], device=dev, base_lr=1e-3, margin=0.8)
 table16 = torch.empty((G, eng.F_pad), dtype=eng.t16, device=dev)
+feats32 = None if args.no_desim else torch.empty((G, F), dtype=torch.float32, device=dev)   # features.npy of predict.py:150
 centres = torch.rand((1000, F), generator=gen, device=dev)
 cluster = torch.randint(0, 1000, (G,), generator=gen, device=dev)
 for s in range(0, G, 65536):
   rows = min(65536, G - s)
   slab = centres[cluster[s:s + rows]] + 0.25 * torch.rand((rows, F), generator=gen, device=dev)
   eng.prepare_table(slab, out=table16[s:s + rows])
+  if feats32 is not None:
+    feats32[s:s + rows] = slab
 tick("build_feature_table_s", t0)
 
 # ---- stage 1: one training epoch over `triplets` cowatch pairs (anchor/positive from the same cluster, random negative)
@@ -100,6 +106,29 @@ tick("knn_s", t0)
 same_cluster = float((cluster[I[:, 1:6]] == cluster[:, None]).float().mean().item())
 self_first = float((I[:, 0] == torch.arange(G, device=dev)).float().mean().item())
 
+# ---- stage 3b: raw-feature KNN (faiss_knn.py:378) and the de-similarity filter of the embedding lists (iter_desim_mp)
+desim_info = None
+if not args.no_desim:
+  t0 = time.time()
+  index.close()
+  torch.nn.functional.normalize(feats32, dim=1, out=feats32)            # calc_knn(l2_norm=True): plumbing-level normalisation of the synthetic rows
+  findex = ops.FlatIndex(feats32, "L2")
+  fD = torch.empty((G, args.feat_k), dtype=torch.float32, device=dev)
+  fI = torch.empty((G, args.feat_k), dtype=torch.int64, device=dev)
+  for s in range(0, G, 131072):
+    rows = min(131072, G - s)
+    fD[s:s + rows], fI[s:s + rows] = findex.search(feats32[s:s + rows], args.feat_k)
+  fstats = findex.last_stats()
+  findex.close()
+  tick("feature_knn_s", t0)
+  t0 = time.time()
+  I_desim = ops.desim(I, fI, fD, 1.4, 31)
+  tick("desim_s", t0)
+  desim_info = {"feature_knn_queries_per_s": G / t["feature_knn_s"], "desim_rows_per_s": G / t["desim_s"],
+                "dropped_fraction": float((I_desim < 0).float().mean().item()),
+                "feature_knn_fallback_queries_last_block": fstats["fallback_queries"]}
+  I = I_desim
+
 # ---- stage 4: knn_split* files (write_knn format) for the first `write_rows` queries
 t0 = time.time()
 out_dir = args.out or tempfile.mkdtemp(prefix="cdml_cycle_")
@@ -111,4 +140,5 @@ print(json.dumps({"guids": G, "triplets": steps * B, "steps": steps, "knn_k": ar
                   "train_triplets_per_s": steps * B / t["train_s"], "embed_rows_per_s": G / t["embed_s"],
                   "knn_queries_per_s": G / t["knn_s"], "loss_first_last": [losses[0], losses[-1]],
                   "top5_same_cluster": same_cluster, "self_is_first_neighbour": self_first,
-                  "knn_fallback_queries_last_block": stats["fallback_queries"], "mining": bool(args.mine), "out_dir": out_dir}))
+                  "knn_fallback_queries_last_block": stats["fallback_queries"], "mining": bool(args.mine), "desim": desim_info,
+                  "write_rows": R, "write_rows_per_s": R / t["write_s"] if R else None, "out_dir": out_dir}))
