@@ -278,16 +278,11 @@ struct EpiL2Norm {
       for (int j = 0; j < 32; ++j)
         f[j] = leaky(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_lane, j), alpha) * r;
       store_chunk32(out, ld, row - static_cast<int>(threadIdx.x & 31), nb, s.M, s.N, stg, f);
-      if (row_ok) {
-        if (out16 != nullptr) {
-          uint16_t* o16 = out16 + static_cast<int64_t>(row) * ld16;
+      if (out16 != nullptr) {   // warp-uniform.  The 16-bit copy (mining / KNN operand) goes through the same staging
+        uint32_t pk[16];        // transpose as the hidden layers: 8 rows x 64 bytes per store instead of 32 x 2 bytes
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const uint32_t pk = pack2<kBf16>(f[j], f[j + 1]);
-            if (nb + j < s.N) o16[nb + j] = static_cast<uint16_t>(pk);
-            if (nb + j + 1 < s.N) o16[nb + j + 1] = static_cast<uint16_t>(pk >> 16);
-          }
-        }
+        for (int j = 0; j < 16; ++j) pk[j] = pack2<kBf16>(f[2 * j], f[2 * j + 1]);
+        store_chunk16(out16, ld16, row - static_cast<int>(threadIdx.x & 31), nb, s.M, s.N, stg, pk);
       }
     }
   }
