@@ -29,6 +29,7 @@ ap.add_argument("--batch", type=int, default=65536)
 ap.add_argument("--knn-k", type=int, default=100)
 ap.add_argument("--write-rows", type=int, default=100000, help="rows of the KNN result formatted into knn_split* files")
 ap.add_argument("--out", default="")
+ap.add_argument("--lr", type=float, default=1e-4, help="Adam base learning rate (1e-3 collapses this synthetic set within 76 steps)")
 ap.add_argument("--no-desim", action="store_true", help="skip the raw-feature KNN + de-similarity stage")
 ap.add_argument("--feat-k", type=int, default=26, help="desim_nearest_num (faiss_knn.py:46)")
 ap.add_argument("--mine", action="store_true", help="in-batch semi-hard mining (default: the reference's random negatives)")
@@ -48,7 +49,7 @@ def tick(name, t0):
 
 # ---- stage 0: resident feature table (normalised 16-bit, built slab by slab) + guid clusters so that there is a signal
 t0 = time.time()
-eng = engine.TowerEngine([F, 5000, 256], device=dev, base_lr=1e-3, margin=0.8)
+eng = engine.TowerEngine([F, 5000, 256], device=dev, base_lr=args.lr, margin=0.8)
 table16 = torch.empty((G, eng.F_pad), dtype=eng.t16, device=dev)
 feats32 = None if args.no_desim else torch.empty((G, F), dtype=torch.float32, device=dev)   # features.npy of predict.py:150
 centres = torch.rand((1000, F), generator=gen, device=dev)
