@@ -39,7 +39,7 @@ _SIGNATURES = {
   "cdml_rows_l2norm16": (c_int, [_P, _P, c_int64, c_int, c_int64, c_float, c_int, _P, c_int64, _P, _P, c_int64, _P]),
   "cdml_desim_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
   "cdml_desim": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P, c_int64, c_int, c_int64, c_int64, c_float, c_int, _P, _P,
-                         c_int64, _P]),
+                         c_int64, c_int64, _P]),
   "cdml_desim_simple": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, c_int, c_int64, _P, c_int64, _P]),
   "cdml_sample_triplets": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, ctypes.c_uint64, _P, _P]),
   "cdml_format_knn_rows": (c_int64, [_P, _P, c_int64, c_int, c_int64, c_int64, _P, _P, c_int64, _P, c_int64]),

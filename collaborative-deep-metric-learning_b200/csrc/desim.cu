@@ -67,7 +67,7 @@ __device__ __forceinline__ uint32_t bloom_bits(uint32_t m) { return (1u << ((m >
 template <int E, int FC>
 __global__ void __launch_bounds__(DesimCfg<E>::kWarps * 32)
 desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_e, const int32_t* __restrict__ F,
-                  int64_t nf, int fw, int fw_pad, int64_t* __restrict__ out, int64_t ld_o, int32_t* flags) {
+                  int64_t nf, int fw, int fw_pad, int64_t* __restrict__ out, int64_t ld_o, int64_t row_offset, int32_t* flags) {
   constexpr int S = DesimCfg<E>::kSlots, W = DesimCfg<E>::kWarps;
   constexpr uint32_t kNone = 0xffffffffu;
   __shared__ int32_t s_key[W][S];
@@ -191,7 +191,7 @@ desim_rows_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t ld_
       if (c < ke) {
         int64_t w = raw[t] < 0 ? -1 : raw[t];
         if (ent[t] >= 0 && !((alive[t] >> lane) & 1u)) w = -1;
-        if (w == r) w = -1;
+        if (w == r + row_offset) w = -1;                   // the row's own id (rows of a slice keep their global number)
         out[r * ld_o + c] = w;
       }
     }
@@ -216,7 +216,7 @@ desim_simple_kernel(const int64_t* __restrict__ eI, int64_t n, int ke, int64_t l
 
 template <int E, int FC>
 static int launch_rows_fc(cdml_ctx* ctx, cudaStream_t st, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int32_t* F,
-                          int64_t nf, int fw, int fw_pad, int64_t* out, int64_t ld_o) {
+                          int64_t nf, int fw, int fw_pad, int64_t* out, int64_t ld_o, int64_t row_offset) {
   constexpr int W = DesimCfg<E>::kWarps;
   auto kern = desim_rows_kernel<E, FC>;
   static int resident = 0;               // CTAs per SM: the grid is exactly one wave (rows are strided over it)
@@ -226,16 +226,16 @@ static int launch_rows_fc(cdml_ctx* ctx, cudaStream_t st, const int64_t* eI, int
   }
   const int64_t blocks = (n + W - 1) / W, cap = static_cast<int64_t>(ctx->num_sms) * resident;
   kern<<<static_cast<int>(blocks < cap ? blocks : cap), W * 32, 0, st>>>(eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o,
-                                                                        ctx->dev_flags);
+                                                                        row_offset, ctx->dev_flags);
   CDML_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int E>
 static int launch_rows(cdml_ctx* ctx, int fc, cudaStream_t st, const int64_t* eI, int64_t n, int ke, int64_t ld_e,
-                       const int32_t* F, int64_t nf, int fw, int fw_pad, int64_t* out, int64_t ld_o) {
-  if (fc == 1) return launch_rows_fc<E, 1>(ctx, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o);
-  return launch_rows_fc<E, 2>(ctx, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o);
+                       const int32_t* F, int64_t nf, int fw, int fw_pad, int64_t* out, int64_t ld_o, int64_t row_offset) {
+  if (fc == 1) return launch_rows_fc<E, 1>(ctx, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o, row_offset);
+  return launch_rows_fc<E, 2>(ctx, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_o, row_offset);
 }
 
 static inline int desim_width(int kf, int f_end) { return f_end < kf ? f_end : kf; }
@@ -252,7 +252,7 @@ int64_t cdml_desim_workspace_bytes(int64_t nf, int kf, int f_end) {
 
 int cdml_desim(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int64_t* fI, const float* fD,
                int64_t nf, int kf, int64_t ld_fi, int64_t ld_fd, float fD_threshold, int f_end, void* workspace,
-               int64_t* out, int64_t ld_out, void* stream) {
+               int64_t* out, int64_t ld_out, int64_t row_offset, void* stream) {
   using namespace cdml;
   CDML_REQUIRE(ctx && eI && fI && out && workspace, "cdml_desim: NULL argument");
   CDML_REQUIRE(n >= 0 && ke > 0 && nf > 0 && kf > 0 && f_end > 0 && ld_e >= ke && ld_out >= ke && ld_fi >= kf &&
@@ -273,11 +273,11 @@ int cdml_desim(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e
   }
   const int fc = fw_pad / 32;
   const int e = (ke + 31) / 32;
-  if (e <= 1) return launch_rows<1>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out);
-  if (e == 2) return launch_rows<2>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out);
-  if (e == 3) return launch_rows<3>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out);
-  if (e == 4) return launch_rows<4>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out);
-  return launch_rows<8>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out);
+  if (e <= 1) return launch_rows<1>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, row_offset);
+  if (e == 2) return launch_rows<2>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, row_offset);
+  if (e == 3) return launch_rows<3>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, row_offset);
+  if (e == 4) return launch_rows<4>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, row_offset);
+  return launch_rows<8>(ctx, fc, st, eI, n, ke, ld_e, F, nf, fw, fw_pad, out, ld_out, row_offset);
 }
 
 int cdml_desim_simple(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int64_t* fI, int kf,

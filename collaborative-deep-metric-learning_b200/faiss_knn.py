@@ -138,7 +138,29 @@ def fliter_fI(fI, fD, fD_threshold):
   return ops.filter_fI(f, d, fD_threshold).cpu().numpy().astype(np.int64)
 
 
-def iter_desim_mp(eI, fI, fD, fD_threshold=1.4, fI_end=31, process_num=22, as_device=False):
+def sharded_desim(eI, fI, fD, fD_threshold=1.4, fI_end=31, process_group=None, desim_fn=None):
+  """De-similarity filter with the ROWS of eI split over the ranks (rows are independent: no exchange on the data path);
+  every rank holds the whole feature-KNN table (its rows are gathered at random) and the filtered slices are joined by one
+  all-gather.  Device tensors in and out, identical on every rank.  `desim_fn` lets the CPU tests drive this protocol
+  over gloo with an oracle-backed stand-in for cdml_desim."""
+  desim_fn = desim_fn or ops.desim
+  world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+  if world == 1:
+    return desim_fn(eI, fI, fD, fD_threshold, fI_end)
+  rank = torch.distributed.get_rank(process_group)
+  n = eI.shape[0]
+  per = -(-n // world)                                   # equal slices (the last ones padded with -1 rows) for all_gather
+  lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+  mine = torch.full((per, eI.shape[1]), -1, dtype=eI.dtype, device=eI.device)
+  if hi > lo:
+    # the filter drops a row's own id: slice rows keep their GLOBAL row number through the row offset argument
+    mine[:hi - lo] = desim_fn(eI[lo:hi].contiguous(), fI, fD, fD_threshold, fI_end, row_offset=lo)
+  out = torch.empty((world * per, eI.shape[1]), dtype=eI.dtype, device=eI.device)
+  torch.distributed.all_gather_into_tensor(out, mine, group=process_group)
+  return out[:n]
+
+
+def iter_desim_mp(eI, fI, fD, fD_threshold=1.4, fI_end=31, process_num=22, as_device=False, process_group=None):
   """Greedy de-similarity of the KNN lists eI against the raw-feature KNN (fI, fD) (faiss_knn.py:187-244): per row, left
   to right, a surviving entry removes every later entry that is one of its first fI_end near feature neighbours; the
   row's own id is removed last.  Returns int64 [n,ke] with removed entries -1.  `process_num` is accepted and ignored
@@ -147,7 +169,7 @@ def iter_desim_mp(eI, fI, fD, fD_threshold=1.4, fI_end=31, process_num=22, as_de
   begin = time.time()
   dev = _device()
   to_dev = lambda a, dt: a.to(dev) if torch.is_tensor(a) else torch.as_tensor(np.ascontiguousarray(a, dt)).to(dev)
-  out = ops.desim(to_dev(eI, np.int64), to_dev(fI, np.int64), to_dev(fD, np.float32), fD_threshold, fI_end)
+  out = sharded_desim(to_dev(eI, np.int64), to_dev(fI, np.int64), to_dev(fD, np.float32), fD_threshold, fI_end, process_group)
   if ops.poll_errors(out) & 2:
     raise IndexError("iter_desim_mp: eI holds ids beyond the feature KNN table (%d rows)" % fI.shape[0])
   if not as_device:
@@ -161,7 +183,7 @@ def strict_knn(embeddings, fI, fD, knn_result=None, nearest_num=None, decode_map
   knn_result = FLAGS.knn_result if knn_result is None else knn_result
   nearest_num = FLAGS.nearest_num if nearest_num is None else nearest_num
   strictD, strictI = calc_knn(embeddings, nearest_num=nearest_num, process_group=process_group)
-  strictI_desim = iter_desim_mp(strictI, fI, fD)
+  strictI_desim = iter_desim_mp(strictI, fI, fD, process_group=process_group)
   if process_group is None or torch.distributed.get_rank(process_group) == 0:
     np.save(knn_result + '/strictD.npy', strictD)
     np.save(knn_result + '/strictI.npy', strictI)
@@ -183,7 +205,7 @@ def cross_knn(embeddings, doc_location, fI, fD, knn_result=None, nearest_num=Non
   dvD, dvI = calc_knn(video_vec, doc_vec, nearest_num=nearest_num, process_group=process_group)
   crossI = np.concatenate((vdI, dvI), axis=0)
   crossD = np.concatenate((vdD, dvD), axis=0)
-  crossI_desim = iter_desim_mp(crossI, fI, fD)
+  crossI_desim = iter_desim_mp(crossI, fI, fD, process_group=process_group)
   if process_group is None or torch.distributed.get_rank(process_group) == 0:
     np.save(knn_result + '/crossD.npy', crossD)
     np.save(knn_result + '/crossI.npy', crossI)

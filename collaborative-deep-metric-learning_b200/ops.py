@@ -235,7 +235,7 @@ def sample_triplets(pairs, start, B, num_guid, seed, out=None):
   return out
 
 
-def desim(eI, fI, fD=None, fD_threshold=1.4, f_end=31, out=None):
+def desim(eI, fI, fD=None, fD_threshold=1.4, f_end=31, out=None, row_offset=0):
   """De-similarity filter of KNN lists (cdml_desim; faiss_knn.py:187-244).  eI [n,ke] int64, fI [nf,kf] int64, fD [nf,kf]
   fp32 device tensors -> int64 [n,ke] with dropped entries -1."""
   if eI.dtype != torch.int64 or fI.dtype != torch.int64 or (fD is not None and fD.dtype != torch.float32):
@@ -251,7 +251,7 @@ def desim(eI, fI, fD=None, fD_threshold=1.4, f_end=31, out=None):
   _count(2)
   check(lib.cdml_desim(_ctx(eI), ptr(eI), n, ke, _row_major_2d(eI, "eI"), ptr(fI), ptr(fD), nf, kf, _row_major_2d(fI, "fI"),
                        _row_major_2d(fD, "fD") if fD is not None else 0, float(fD_threshold), int(f_end), ptr(ws), ptr(out),
-                       _row_major_2d(out, "out"), stream_ptr()))
+                       _row_major_2d(out, "out"), int(row_offset), stream_ptr()))
   return out
 
 
@@ -263,7 +263,7 @@ def filter_fI(fI, fD, fD_threshold=1.4):
   ws = torch.empty((int(lib.cdml_desim_workspace_bytes(nf, kf, kf)),), dtype=torch.uint8, device=fI.device)
   _count(2)
   check(lib.cdml_desim(_ctx(fI), ptr(probe), 1, 1, 1, ptr(fI), ptr(fD), nf, kf, _row_major_2d(fI, "fI"),
-                       _row_major_2d(fD, "fD"), float(fD_threshold), kf, ptr(ws), ptr(probe), 1, stream_ptr()))
+                       _row_major_2d(fD, "fD"), float(fD_threshold), kf, ptr(ws), ptr(probe), 1, 0, stream_ptr()))
   return ws.view(torch.int32).view(nf, -1)[:, :kf]          # int32 ids, -1 = filtered
 
 

@@ -174,13 +174,14 @@ int cdml_mean_pair_dist(cdml_ctx* ctx, const float* V, int64_t ld, int D, const 
  *      eI [n,ke] int64 embedding-KNN ids (-1 = padding), fI / fD [nf,kf] the raw-feature KNN (ids int64, squared distances
  *      fp32; fD may be NULL = no distance filter).  Per row, left to right: an entry still alive is a pivot v; every LATER
  *      entry found among v's first min(kf,f_end) feature neighbours (those with fD <= threshold, other than v itself) is
- *      dropped; finally the row's own id is dropped.  out [n,ke] int64 = eI with dropped entries -1 (may alias eI).
+ *      dropped; finally the row's own id (row + row_offset: eI may be a slice of the rows, one slice per rank) is
+ *      dropped.  out [n,ke] int64 = eI with dropped entries -1 (may alias eI).
  *      workspace: cdml_desim_workspace_bytes(nf,kf,f_end) device bytes.  ke <= 256, min(kf,f_end) <= 64, nf < 2^31.
  *      An id >= nf (IndexError in the reference) is left untouched and sets error flag bit 1 (cdml_ctx_poll_errors). */
 int64_t cdml_desim_workspace_bytes(int64_t nf, int kf, int f_end);
 int cdml_desim(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int64_t* fI, const float* fD,
                int64_t nf, int kf, int64_t ld_fi, int64_t ld_fd, float fD_threshold, int f_end, void* workspace,
-               int64_t* out, int64_t ld_out, void* stream);
+               int64_t* out, int64_t ld_out, int64_t row_offset, void* stream);
 /* out[i,j] = -1 where eI[i,j] occurs in fI[i,:], else eI[i,j]  (faiss_knn.desim). */
 int cdml_desim_simple(cdml_ctx* ctx, const int64_t* eI, int64_t n, int ke, int64_t ld_e, const int64_t* fI, int kf,
                       int64_t ld_f, int64_t* out, int64_t ld_out, void* stream);

@@ -654,7 +654,7 @@ def filter_fI(fI, fD, fD_threshold=1.4):
   return fI
 
 
-def iter_desim(eI, fI, fD, fD_threshold=1.4, fI_end=31):
+def iter_desim(eI, fI, fD, fD_threshold=1.4, fI_end=31, row_offset=0):
   """faiss_knn.iter_desim_mp (faiss_knn.py:187-244) without its +1 index shift, zero row and process pool, which only
   serve the vectorised column sweep.  Row by row (rows are independent): walk the columns left to right; an entry that is
   still alive is a pivot v, and every LATER entry of the row that occurs among v's first fI_end filtered feature
@@ -671,7 +671,7 @@ def iter_desim(eI, fI, fD, fD_threshold=1.4, fI_end=31):
       near = F[v][F[v] >= 0]
       tail = row[c + 1:]
       tail[np.isin(tail, near)] = -1
-    row[row == r] = -1
+    row[row == r + row_offset] = -1          # eI may be a slice of the rows starting at row_offset
   return eI
 
 

@@ -722,6 +722,10 @@ def test_desim_kernels_bit_exact_vs_reference_golden_and_oracle(cd):
     got = cd.faiss_knn.iter_desim_mp(eI.copy(), fI.copy(), fD.copy(), fI_end=f_end)
     assert np.array_equal(got, want), (n, ke, kf, f_end)
     assert (want == -1).sum() > (eI == -1).sum()
+  # a slice of the rows keeps its global row numbers through row_offset (what each rank of sharded_desim filters)
+  lo, hi = n // 3, n // 3 + 20
+  part = cd.ops.desim(dev_t(cd, eI[lo:hi]), dev_t(cd, fI), dev_t(cd, fD), 1.4, f_end, row_offset=lo)
+  assert np.array_equal(part.cpu().numpy(), want[lo:hi])
   # in place (out aliases eI), empty input, ids beyond the feature table (IndexError in the reference)
   e = dev_t(cd, eI)
   assert cd.ops.desim(e, dev_t(cd, fI), dev_t(cd, fD), 1.4, f_end, out=e) is e and np.array_equal(e.cpu().numpy(), want)

@@ -227,6 +227,17 @@ for nq in (300, 301):      # divisible by the world size (all-to-all path) and n
   Dm, Im = faiss_knn.sharded_search(ShardIndex(X[lo:hi]), torch.tensor(X[:nq]), 7, lo, "L2", dist.group.WORLD, merge_fn=cpu_merge)
   assert np.array_equal(Im.numpy(), Iw[:nq]) and np.allclose(Dm.numpy(), Dw[:nq], atol=1e-6), nq
   assert (Im.numpy() >= 0).all()
+# --- de-similarity filter with the rows split over the ranks (PRODUCT's sharded_desim, oracle-backed stand-in for cdml_desim)
+rs = np.random.RandomState(3)
+n, ke, kf = 101, 9, 6          # 101 rows: the last slice is short and padded for the all-gather
+eI = np.stack([np.concatenate(([r], rs.choice(n, ke - 1, replace=False))) for r in range(n)]).astype(np.int64)
+fI = np.stack([np.concatenate(([r], eI[r, 1:4], rs.choice(n, kf - 4, replace=False))) for r in range(n)]).astype(np.int64)
+fD = np.sort(rs.rand(n, kf).astype(np.float32) * 2.0, axis=1)
+def cpu_desim(e, f, d, thr, f_end, row_offset=0):
+  return torch.tensor(O.iter_desim(e.numpy(), f.numpy(), d.numpy(), thr, f_end, row_offset=row_offset))
+got = faiss_knn.sharded_desim(torch.tensor(eI), torch.tensor(fI), torch.tensor(fD), 1.4, 31, dist.group.WORLD, desim_fn=cpu_desim)
+want = O.iter_desim(eI, fI, fD, 1.4, 31)
+assert np.array_equal(got.numpy(), want) and (want != eI).sum() > n
 dist.barrier(); dist.destroy_process_group()
 print("rank %d ok" % rank)
 '''
