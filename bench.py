@@ -446,10 +446,16 @@ def main():
 
   # ---- second BASELINE metric: exact KNN top-100 queries/sec on a 1M-item index.  N>1: the index is row-sharded over
   # the ranks (strong scaling: same 1M rows, same queries), per-shard top-k all-gathered over NCCL and merged on the GPU.
+  # the training engine -- and with it the captured CUDA graph, which holds NCCL kernels when N>1 -- is released before
+  # anything else runs and long before the process group is torn down (a live NCCL graph at teardown was seen to hang the
+  # exit of a 2-GPU --no-knn run after the line had been printed)
+  del table16, idx_all, eng, replay
+  import gc
+  gc.collect()
+  torch.cuda.synchronize()
+  torch.cuda.empty_cache()
   if not args.no_knn:
     from cdml_b200 import faiss_knn
-    del table16, idx_all, eng, replay
-    torch.cuda.empty_cache()
     N, nq, k, d = args.knn_n, args.knn_queries, 100, 256
     gen.manual_seed(4)
     X = torch.nn.functional.normalize(torch.randn((N, d), generator=gen, device=dev), dim=1)   # same on every rank
@@ -497,6 +503,10 @@ def main():
   # rank filters its own slice of the rows, no collective: weak scaling)
   if not args.no_desim:
     line["desim"] = bench_desim(torch, ops, dev, args.desim_n, world, rank, barrier, dist, pk)
+  if world > 1:                       # a teardown that does not finish within a minute must not hold the job
+    t = threading.Timer(60.0, os._exit, (0,))
+    t.daemon = True
+    t.start()
   if rank != 0:
     if world > 1:
       dist.barrier()
