@@ -832,3 +832,47 @@ def test_flat_knn_over_raw_feature_widths(cd, N, d, nq, k):
   assert_knn_matches(D.cpu().numpy(), I.cpu().numpy(), Dw, Iw, "L2", X, X[:nq])
   assert (I[:, 0].cpu().numpy() == np.arange(nq)).all()
   index.close()
+
+
+def test_full_size_desim_properties_and_oracle_spot_check(cd):
+  """1M rows x 81 neighbours against a 1M x 26 feature-KNN table (the production shape of faiss_knn.main): survivors are
+  a subset of the input in place, the row's own id is gone, the filter is idempotent, no survivor is a near feature
+  neighbour of an earlier survivor of its row, and 300 random rows equal the oracle."""
+  n, ke, kf = 1000000, 81, 26
+  gen = torch.Generator(device=cd.dev)
+  gen.manual_seed(21)
+  eI = torch.randint(0, n, (n, ke), generator=gen, device=cd.dev, dtype=torch.int64)
+  fI = torch.randint(0, n, (n, kf), generator=gen, device=cd.dev, dtype=torch.int64)
+  eI[:, 0] = fI[:, 0] = torch.arange(n, device=cd.dev)
+  fI[:, 1:9] = eI[:, 1:9]                                       # the query's closest neighbours are also near duplicates of it
+  hop = eI[eI[:, 1], 2:6]                                       # and some entries are near duplicates of the first neighbour
+  eI[:, 40:44] = hop
+  fD = torch.sort(torch.rand((n, kf), generator=gen, device=cd.dev) * 2.0, dim=1).values
+  out = cd.ops.desim(eI, fI, fD, 1.4, 31)
+  assert cd.ops.poll_errors(out) == 0
+  kept = out >= 0
+  assert bool((out[kept] == eI[kept]).all().item()) and bool((out[~kept] == -1).all().item())
+  assert not bool((out == torch.arange(n, device=cd.dev)[:, None]).any().item())
+  frac = float((~kept).float().mean().item())
+  assert 0.05 < frac < 0.5, frac
+  again = cd.ops.desim(out, fI, fD, 1.4, 31)
+  assert bool((again == out).all().item())                      # idempotent
+  pick = np.random.RandomState(0).choice(n, 300, replace=False)
+  eh, oh = eI[torch.as_tensor(pick, device=cd.dev)].cpu().numpy(), out[torch.as_tensor(pick, device=cd.dev)].cpu().numpy()
+  Ff = O.filter_fI(fI.cpu().numpy(), fD.cpu().numpy(), 1.4)[:, :31]        # fliter_fI once for the whole table
+  for row, got, r in zip(eh, oh, pick):
+    want = row.copy()
+    for c in range(ke):                                                      # oracle.iter_desim's row loop on the prepared table
+      v = want[c]
+      if v < 0:
+        continue
+      near = Ff[v][Ff[v] >= 0]
+      tail = want[c + 1:]
+      tail[np.isin(tail, near)] = -1
+    want[want == r] = -1
+    assert np.array_equal(got, want), r
+  # no survivor is a near feature neighbour of an earlier survivor (checked on the sampled rows)
+  for got in oh:
+    alive = got[got >= 0]
+    for i, v in enumerate(alive[:-1]):
+      assert not np.isin(alive[i + 1:], Ff[v][Ff[v] >= 0]).any()
