@@ -191,6 +191,16 @@ def bench_desim(torch, ops, dev, n, world, rank, barrier, dist, pk, ke=81, kf=26
   # algorithmic bytes: prepare pass (read fI int64 + fD fp32, write the int32 table) + eI in/out + one table row per
   # alive pivot (= the survivors plus the row's own id)
   alg = n * kf * 12 + n * fw_pad * 4 + 2 * n * ke * 8 + (survivors + n) * fw_pad * 4
+  # DRAM bytes per call from the committed ncu --set full capture of the same workload (4M rows), if present
+  traffic, traffic_src = None, None
+  prof = os.path.join(ROOT, "profiles", "r01_ncu_desim_summary.json")
+  if os.path.exists(prof) and n == 4000000 and ke == 81 and kf == 26:
+    try:
+      ks = json.load(open(prof))["kernels"]
+      traffic = sum((k["dram_read_GB"] + k["dram_write_GB"]) * 1e9 for k in ks)
+      traffic_src = "profiles/r01_ncu_desim_summary.json: desim_prepare_kernel + desim_rows_kernel"
+    except Exception:
+      traffic = None
   return {"metric": "desim_rows_per_sec", "value": world * n / (ms / 1e3), "unit": "rows/s", "scaling": "weak",
           "config": {"workload": "iter_desim_mp (faiss_knn.py:187-244): %d rows x %d neighbours per GPU against a %d x %d "
                                  "feature-KNN table, fD_threshold 1.4, fI_end 31, uniform ids (every entry stays a pivot)"
@@ -198,7 +208,7 @@ def bench_desim(torch, ops, dev, n, world, rank, barrier, dist, pk, ke=81, kf=26
           "ms": ms, "dtype": "int64 ids / int32 table", "dropped_fraction": 1.0 - survivors / float(n * ke),
           "e2e": e2e,
           "roofline": {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                       "frac": alg / (ms / 1e3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                       "frac": alg / (ms / 1e3) / 1e9 / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                        "algorithmic_bytes": alg}}
 
 
