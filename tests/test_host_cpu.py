@@ -364,3 +364,27 @@ def test_native_feature_text_reader_follows_python_float_semantics(lib, tmp_path
   assert enc["a"] == want_guids.index("a", 1) and enc["视频"] == want_guids.index("视频")   # a later duplicate guid wins
   (tmp_path / "empty.txt").write_text("")
   assert online_data.read_features_txt(str(tmp_path / "empty.txt"), width=3)[0].shape == (0, 3)
+
+
+def test_graph_recorder_rejects_what_the_engine_cannot_run(lib):
+  """compile_graph's error paths: output must be an l2_normalize, slices only on the input placeholder, inner l2_normalize
+  only on (a slice of) the input, one leaky slope, equal widths for joins; GuidTable needs every row index."""
+  from cdml_b200 import faiss_knn, models
+  x = models.placeholder(40)
+  h = models.fully_connected(models.l2_normalize(x[:, :24]), 16)
+  with pytest.raises(NotImplementedError):
+    models.compile_graph(h)                                                   # not normalised
+  with pytest.raises(NotImplementedError):
+    models.compile_graph(models.l2_normalize(models.fully_connected(models.l2_normalize(h), 8)))   # inner l2norm on a layer
+  with pytest.raises(NotImplementedError):
+    models.compile_graph(models.l2_normalize(models.fully_connected(h[:, :8], 8)))                 # slice of a layer
+  with pytest.raises(ValueError):
+    models.multiply(h, models.fully_connected(models.l2_normalize(x[:, 24:]), 8))                  # widths differ
+  with pytest.raises(ValueError):
+    x[:, 30:30]
+  with pytest.raises(NotImplementedError):
+    x[::2]
+  g = models.compile_graph(models.l2_normalize(h + h * h))                   # x + x*x: the same node twice in a join
+  assert [e["op"] for e in g["spec"]] == ["input", "fc", "mul", "add", "l2norm"] and g["spec"][2]["src"] == [1, 1]
+  with pytest.raises(KeyError):
+    faiss_knn.GuidTable({0: "a", 2: "c"})
