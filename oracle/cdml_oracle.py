@@ -12,6 +12,16 @@ Pinning status (see DESIGN.md "Oracle"):
     run in the build container (tests/golden/make_golden.py, fixtures committed).
   * hinge loss: pinned against the known answers derived from the reference's
     fixture tests/test_losses.py:13-18 (the reference asserts nothing itself).
+  * de-similarity filter (iter_desim, desim_simple, filter_fI): pinned against
+    outputs of the reference's own faiss_knn.iter_desim_mp / desim / fliter_fI
+    run in the build container (tests/golden/make_desim_golden.py).
+  * device reader: the counter-based generator is pinned to the Random123
+    known-answer vectors of philox4x32-10; the sampling rule follows
+    inputs.py:112-130 (the reference's own stream is unseeded: only the
+    distribution can be matched).
+  * fusion towers (fusion_spec / graph_forward / graph_backward): **parity
+    unpinned** like the chain tower (TensorFlow ops); cross-checked by torch
+    autograd of the same forward to 1e-12.
   * tower forward/backward, TF1 Adam, flat KNN: **parity unpinned** -- the
     arithmetic lives in tensorflow-gpu==1.13.1 and faiss-gpu==1.5.x
     (README.md:19-22), neither vendored nor installable here.  The oracle
