@@ -452,8 +452,8 @@ __global__ void opt_apply_kernel(int kind, float* __restrict__ w, float* __restr
       const float acc = momentum * m[i] + gi;
       wi -= lr * gi + lr * momentum * acc;
       m[i] = acc;
-    } else if (kind == 2) {                              // LARS: weight decay joins the gradient, plain momentum
-      const float acc = momentum * m[i] + (gi + lars_wd * wi);
+    } else if (kind == 2) {   // LARS as of TF r1.13 (_apply_dense -> apply_momentum(var, mom, lr*trust, grad, momentum)): weight
+      const float acc = momentum * m[i] + gi;   // decay enters the trust ratio ONLY; the later "grad + wd*var" form is not 1.13's
       wi -= lr * trust * acc;
       m[i] = acc;
     } else {

@@ -10,6 +10,7 @@ Backward = the written-out autodiff of train.py:141-142 (see oracle/cdml_oracle.
 """
 import math
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -96,6 +97,7 @@ class TowerEngine:
     self.norms = torch.zeros((2 * self.L, 2), dtype=torch.float32, device=dev)       # per variable: {sum g_eff^2, sum w^2}
     self.opt_ws = torch.empty((ops.opt_workspace_floats(),), dtype=torch.float32, device=dev)
     self._bufs = {}
+    self._pinned_bufs = set()      # keys of self._bufs whose pointers are baked into a captured CUDA graph
     self._ws = {}
 
     if init_params is None:
@@ -126,11 +128,26 @@ class TowerEngine:
   def get_params(self):
     return [(self.W[l].detach().cpu().numpy().copy(), self.b[l].detach().cpu().numpy().copy()) for l in range(self.L)]
 
+  OPT_NAMES = {ops.OPT_ADAM: "adam", ops.OPT_MOMENTUM: "momentum", ops.OPT_LARS: "lars", ops.OPT_SGD: "sgd"}
+
+  def hyper(self):
+    """Everything besides the tensors that a served / resumed tower must agree on (saved with every checkpoint): the
+    operand type the tower was TRAINED in, the activation slope, which optimizer the m / v slots belong to."""
+    return {"dtype16": int(self.dtype16), "alpha": self.alpha, "optimizer": self.OPT_NAMES[self.opt_kind],
+            "loss_scale": self.loss_scale, "margin": self.margin, "base_lr": self.base_lr,
+            "lr_decay_steps": self.lr_decay_steps, "lr_decay": self.lr_decay, "beta1": self.beta1, "beta2": self.beta2,
+            "eps": self.eps, "clip_norm": self.clip_norm, "wd_reg": self.wd_reg, "momentum": self.momentum,
+            "lars_weight_decay": self.lars_wd, "lars_eeta": self.lars_eeta}
+
   def state_dict(self):
     return {"dims": self.dims, "w": self.w.cpu().numpy(), "m": self.m.cpu().numpy(), "v": self.v.cpu().numpy(),
-            "step": int(self.step_counter.item())}
+            "step": int(self.step_counter.item()), "hyper": self.hyper()}
 
   def load_state_dict(self, sd):
+    have = sd.get("hyper")
+    if have is not None and have.get("optimizer", self.OPT_NAMES[self.opt_kind]) != self.OPT_NAMES[self.opt_kind]:
+      # the m / v slots of another optimizer mean something else (Momentum / LARS accumulators are not Adam moments)
+      raise ValueError("checkpoint optimizer state is %s, this engine runs %s" % (have["optimizer"], self.OPT_NAMES[self.opt_kind]))
     self.w.copy_(torch.as_tensor(sd["w"]))
     self.m.copy_(torch.as_tensor(sd["m"]))
     self.v.copy_(torch.as_tensor(sd["v"]))
@@ -146,6 +163,8 @@ class TowerEngine:
     key = (R, train)
     buf = self._bufs.get(key)
     if buf is not None:
+      if key not in self._pinned_bufs:
+        self._bufs[key] = self._bufs.pop(key)      # most recently used goes last
       return buf
     dev, t16 = self.device, self.t16
     D = self.dims[-1]
@@ -177,10 +196,17 @@ class TowerEngine:
       buf["partials"] = torch.empty((max(part, 1),), dtype=torch.float32, device=dev)
       buf["colsum_ws"] = torch.empty((max(ops.colsum_workspace_floats(R, d) for d in self.dims[1:]),),
                                      dtype=torch.float32, device=dev)
-    if len(self._bufs) > 4:
-      self._bufs.clear()
-    self._bufs[key] = buf
+    self._store_buffers(key, buf)
     return buf
+
+  def _store_buffers(self, key, buf):
+    """Cache policy: a captured CUDA graph holds the raw pointers of its (R, train=True) buffers, so those are pinned for
+    the life of the engine (`_pinned_bufs`); everything else is an LRU of 4 entries (eval batch, eval tail, predict
+    batch, predict tail come and go with different row counts and must not push the training buffers out)."""
+    self._bufs[key] = buf
+    loose = [k for k in self._bufs if k not in self._pinned_bufs]
+    for k in loose[:max(0, len(loose) - 4)]:       # dict order = insertion order; hits are re-inserted by _buffers
+      del self._bufs[k]
 
   def _bias_row_ok(self, width, pitch):
     """[x | 1]^T . dz = [dW ; db]: possible when the input matrix has a spare pitch column for the ones and the bias
@@ -223,14 +249,17 @@ class TowerEngine:
   def _input_has_ones(self, x16):
     """First use of an input matrix: does its padding column F hold the ones `prepare_table` plants?  (One 2-byte
     read per distinct buffer; a table built by other means silently falls back to the column-sum kernel.)"""
-    key = (x16.data_ptr(), x16.stride(0))
-    ok = self._ones_checked.get(key)
-    if ok is None:
-      ok = bool(self._bias_row_ok(self.F, x16.stride(0)) and float(x16[0, :self.F + 1][-1].item()) == 1.0
-                and float(x16[x16.shape[0] - 1, :self.F + 1][-1].item()) == 1.0) if x16.shape[0] else False
-      if len(self._ones_checked) > 64:
-        self._ones_checked.clear()
-      self._ones_checked[key] = ok
+    key = (x16.data_ptr(), x16.stride(0), x16.shape[0])
+    hit = self._ones_checked.get(key)
+    # the verdict is tied to the tensor's STORAGE (weak reference): an address the allocator hands out again after the
+    # checked buffer was freed must be looked at again
+    if hit is not None and hit[1]() is not None and hit[1]()._cdata == x16.untyped_storage()._cdata:
+      return hit[0]
+    ok = bool(self._bias_row_ok(self.F, x16.stride(0)) and float(x16[0, :self.F + 1][-1].item()) == 1.0
+              and float(x16[x16.shape[0] - 1, :self.F + 1][-1].item()) == 1.0) if x16.shape[0] else False
+    if len(self._ones_checked) > 64:
+      self._ones_checked.clear()
+    self._ones_checked[key] = (ok, weakref.ref(x16.untyped_storage()))
     return ok
 
   def train_step_indices(self, table16, idx, mine=False, guid=None):
@@ -356,7 +385,9 @@ class TowerEngine:
     self.w.copy_(snap[0]), self.m.copy_(snap[1]), self.v.copy_(snap[2]), self.step_counter.copy_(snap[3])
     self.refresh_shadows()
     torch.cuda.synchronize()
-    self._graph_keepalive = (graph, static_idx, stats)
+    # the graph replays raw pointers: pin the training buffers (activations, dz, G, partials, loss) and the workspaces
+    self._pinned_bufs.add((3 * B, True))
+    self._graph_keepalive = (graph, static_idx, stats, self._bufs[(3 * B, True)])
 
     def replay(idx):
       static_idx.copy_(idx, non_blocking=True)

@@ -115,6 +115,8 @@ class GraphEngine(TowerEngine):
     key = (R, train)
     buf = self._bufs.get(key)
     if buf is not None:
+      if key not in self._pinned_bufs:
+        self._bufs[key] = self._bufs.pop(key)      # most recently used goes last (TowerEngine._store_buffers)
       return buf
     dev, t16, spec, D = self.device, self.t16, self.spec, self.widths[-1]
 
@@ -144,9 +146,7 @@ class GraphEngine(TowerEngine):
       buf["partials"] = torch.empty((max(part, 1),), dtype=torch.float32, device=dev)
       buf["colsum_ws"] = torch.empty((max(ops.colsum_workspace_floats(R, fo) for _, fo in self.shapes),),
                                      dtype=torch.float32, device=dev)
-    if len(self._bufs) > 4:
-      self._bufs.clear()
-    self._bufs[key] = buf
+    self._store_buffers(key, buf)
     return buf
 
   def _scratch(self, buf, key, cols):

@@ -12,7 +12,8 @@ What changed underneath:
     a file is re-read `num_epochs` times back to back, the trailing partial batch is dropped, each negative is
     `randint(0,G)` re-drawn while it equals the anchor or the positive -- but runs in-process, files served
     round-robin, from a seeded RandomState (the reference forks unseeded workers that all replay one stream, Q10);
-  * rank/world sharding for data-parallel training: rank r serves batches r, r+world, ... of that round-robin order;
+  * rank/world sharding for data-parallel training: rank r serves batches r, r+world, ... of that round-robin order, in
+    complete rounds of `world` batches (a trailing incomplete round is dropped so every rank runs the same step count);
   * `device_reader=True`: the pairs of every file stay resident in HBM and `get_batch_indices_device()`
     produces the [B,3] triplets on the device (cdml_sample_triplets: same file order, wrap-around and negative rule, a
     counter-based Philox generator per stream position instead of numpy's Mersenne Twister) -- no host work per step.
@@ -105,40 +106,44 @@ class MPTripletPipe(object):
         bad = (neg == ap[:, 0]) | (neg == ap[:, 1])
       yield np.concatenate([ap, neg[:, None]], axis=1)
 
+  def _shard(self, ordered):
+    """Rank r takes every world-th item of the round-robin order, in whole ROUNDS of `world` items: when fewer than
+    `world` items remain they are dropped on every rank, so all ranks run the same number of steps (each step ends in a
+    collective; a rank with one batch more than its peers would wait in the all-reduce forever)."""
+    round_ = []
+    for item in ordered:
+      round_.append(item)
+      if len(round_) == self.world:
+        yield round_[self.rank]
+        round_ = []
+
+  @staticmethod
+  def _round_robin(streams):
+    while streams:
+      alive = []
+      for s in streams:
+        item = next(s, None)
+        if item is None:
+          continue
+        alive.append(s)
+        yield item
+      streams = alive
+
   def _index_batches(self):
     num_guid = len(FEATURES)
     streams = [self._file_batches(p, np.random.RandomState(self.seed + 7919 * i), num_guid)
                for i, p in enumerate(self._pairs)]
-    k = 0
-    while streams:
-      alive = []
-      for s in streams:
-        batch = next(s, None)
-        if batch is None:
-          continue
-        alive.append(s)
-        if k % self.world == self.rank:
-          yield batch
-        k += 1
-      streams = alive
+    return self._shard(self._round_robin(streams))
 
   def _position_batches(self):
     """(file, start position) of every batch, in the order `_index_batches` serves them (round-robin over the files, a
-    file's stream is `num_epochs` passes back to back without its trailing partial batch, rank r takes every world-th)."""
+    file's stream is `num_epochs` passes back to back without its trailing partial batch, rank r takes every world-th of
+    each complete round of `world` batches)."""
     B = self.batch_size
-    cursors = [(i, iter(range(0, len(p) * self.num_epochs - B + 1, B))) for i, p in enumerate(self._pairs) if len(p)]
-    k = 0
-    while cursors:
-      alive = []
-      for i, it in cursors:
-        start = next(it, None)
-        if start is None:
-          continue
-        alive.append((i, it))
-        if k % self.world == self.rank:
-          yield i, start
-        k += 1
-      cursors = alive
+    def cursor(i, n):
+      return ((i, start) for start in range(0, n * self.num_epochs - B + 1, B))
+    cursors = [cursor(i, len(p)) for i, p in enumerate(self._pairs) if len(p)]
+    return self._shard(self._round_robin(cursors))
 
   def get_batch_indices_device(self, out=None):
     """Next [B,3] int64 triplets as a DEVICE tensor produced by cdml_sample_triplets, or None at end of data."""

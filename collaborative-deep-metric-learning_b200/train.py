@@ -157,11 +157,15 @@ def build_graph(input_batch, model, output_size=256, loss_fn=None, base_learning
 # checkpoints: model.ckpt-<step>.npz + a TF-style `checkpoint` index file (train.py:240, :275; predict.py:119-132)
 # --------------------------------------------------------------------------------------------------
 def save_checkpoint(engine, checkpoint_dir, step, model_name):
+  """tf.train.Saver(max_to_keep=1).save (train.py:240, :275): the new file is written completely (temp name + rename),
+  then the `checkpoint` index is switched to it, and only then are older checkpoints removed -- a crash at any point
+  leaves an index that names an existing, complete file.  Format: one .npz with the flat fp32 buffers (w, m, v), the
+  per-variable arrays under their slim scope names, and `hyper` (JSON: operand dtype, leaky slope, optimizer kind, loss
+  scale, margin, ...) so that predict.load_engine serves / resumes the tower as it was trained.  TensorFlow's own
+  .meta/.index/.data files are a different container and are NOT read or written."""
   os.makedirs(checkpoint_dir, exist_ok=True)
-  for f in os.listdir(checkpoint_dir):   # Saver(max_to_keep=1)
-    if f.startswith("model.ckpt-") and f.endswith(".npz"):
-      os.remove(os.path.join(checkpoint_dir, f))
-  prefix = os.path.join(checkpoint_dir, "model.ckpt-%d" % step)
+  name = "model.ckpt-%d" % step
+  prefix = os.path.join(checkpoint_dir, name)
   sd = engine.state_dict()
   names = {}
   scopes = getattr(engine, "names", None)        # fusion towers name their layers (models.py:82-88)
@@ -170,10 +174,24 @@ def save_checkpoint(engine, checkpoint_dir, step, model_name):
     names[scope + "/weights"], names[scope + "/biases"] = W, b
   if "spec" in sd:
     names["spec"] = np.asarray(sd["spec"])
-  np.savez(prefix + ".npz", dims=np.asarray(sd["dims"]), w=sd["w"], m=sd["m"], v=sd["v"], step=sd["step"],
-           model=model_name, **names)
-  with open(os.path.join(checkpoint_dir, "checkpoint"), "w") as f:
-    f.write('model_checkpoint_path: "model.ckpt-%d"\nall_model_checkpoint_paths: "model.ckpt-%d"\n' % (step, step))
+  tmp = prefix + ".npz.tmp%d" % os.getpid()
+  try:
+    with open(tmp, "wb") as f:
+      np.savez(f, dims=np.asarray(sd["dims"]), w=sd["w"], m=sd["m"], v=sd["v"], step=sd["step"], model=model_name,
+               hyper=np.asarray(json.dumps(sd.get("hyper", {}))), **names)
+      f.flush()
+      os.fsync(f.fileno())
+    os.replace(tmp, prefix + ".npz")
+  finally:
+    if os.path.exists(tmp):
+      os.remove(tmp)
+  index_tmp = os.path.join(checkpoint_dir, "checkpoint.tmp%d" % os.getpid())
+  with open(index_tmp, "w") as f:
+    f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (name, name))
+  os.replace(index_tmp, os.path.join(checkpoint_dir, "checkpoint"))
+  for f in os.listdir(checkpoint_dir):   # max_to_keep=1: older checkpoints go last
+    if f.startswith("model.ckpt-") and f.endswith(".npz") and f != name + ".npz":
+      os.remove(os.path.join(checkpoint_dir, f))
   return prefix
 
 

@@ -103,7 +103,8 @@ int cdml_adam_apply(cdml_ctx* ctx, float* w, float* m, float* v, const float* g,
  *      per-variable tf.clip_by_norm (train.py:47-64): g_eff *= clip_norm / max(||g_eff||, clip_norm) when clip_norm > 0;
  *      kind 0 Adam, 1 MomentumOptimizer(momentum, use_nesterov=True) (train.py:115-116),
  *           2 tf.contrib.opt.LARSOptimizer (train.py:354: trust = eeta*||w|| / (||g|| + wd*||w|| + eps) when both norms > 0,
- *             g += wd*w, acc = momentum*acc + g, w -= lr*trust*acc), 3 GradientDescent.
+ *             acc = momentum*acc + g, w -= lr*trust*acc -- TF r1.13's apply_momentum(var, mom, lr*trust, grad, momentum): the
+ *             weight decay enters the trust ratio only), 3 GradientDescent.
  *      cdml_opt_sumsq writes out2 = {sum g_eff^2, sum w^2} for one variable (deterministic two-stage reduction;
  *      workspace fp32 [cdml_opt_workspace_floats()]); cdml_opt_apply reads them as `norms` (needed for clipping and
  *      LARS, NULL otherwise).  scalars = cdml_adam_prepare's output ([0] bias-corrected Adam step size, [1] decayed lr). */

@@ -391,13 +391,16 @@ def momentum_step_tf1(w, acc, g, lr, momentum=0.9, nesterov=True):
 
 
 def lars_step_tf1(w, acc, g, lr, momentum=0.9, weight_decay=1e-4, eeta=1e-3, epsilon=0.0):
-  """tf.contrib.opt.LARSOptimizer (TF 1.13 defaults; the optimizer of main(), train.py:354), restated from its published
-  compute_lr / _apply_dense:  trust = eeta*|w| / (|g| + wd*|w| + eps) if |w| > 0 and |g| > 0 else 1 ;
-  g <- g + wd*w ; acc <- momentum*acc + g ; w <- w - (lr*trust)*acc   (use_nesterov=False)."""
+  """tf.contrib.opt.LARSOptimizer as of tensorflow r1.13 (the release README.md:20 pins; the optimizer of main(),
+  train.py:354), restated from contrib/opt/python/training/lars_optimizer.py of that branch:
+    compute_lr:   trust = eeta*|w| / (|g| + wd*|w| + eps) if |w| > 0 and |g| > 0 else 1 ; scaled_lr = lr*trust
+    _apply_dense: training_ops.apply_momentum(var, mom, scaled_lr, grad, momentum, use_nesterov=False)
+                  = acc <- momentum*acc + g ; w <- w - scaled_lr*acc
+  weight_decay enters the trust ratio ONLY.  (Later releases add `grad + wd*var` and move scaled_lr inside the
+  accumulator; that is not what 1.13.1 runs.)"""
   wn = float(np.sqrt(np.sum(np.asarray(w, np.float64) ** 2)))
   gn = float(np.sqrt(np.sum(np.asarray(g, np.float64) ** 2)))
   trust = eeta * wn / (gn + weight_decay * wn + epsilon) if (wn > 0 and gn > 0) else 1.0
-  g = g + weight_decay * w
   acc = momentum * acc + g
   return w - (lr * trust) * acc, acc
 
@@ -408,9 +411,10 @@ class OracleTrainer:
   Defaults = Trainer._build_model's constants (train.py:210-222): Adam, clip off, reg penalty 0, decay 0.96 / 1e6 steps."""
 
   def __init__(self, params, lr=1e-3, margin=0.8, decay_steps=1000000, decay=0.96, dtype=np.float64, optimizer="adam",
-               clip_norm=0.0, reg_penalty=0.0, l2_penalty=1e-8, spec=None):
+               clip_norm=0.0, reg_penalty=0.0, l2_penalty=1e-8, spec=None, emulate16=None):
     self.dtype = dtype
     self.spec = spec            # op list of a fusion tower (fusion_spec); None = the fully_connected chain
+    self.emulate16 = emulate16  # "fp16" | "bf16": gradients from the 16-bit PRECISION MODEL (tower_grads_emulated16)
     self.params = [(np.asarray(W, dtype).copy(), np.asarray(b, dtype).copy()) for W, b in params]
     self.m = [(np.zeros_like(W), np.zeros_like(b)) for W, b in self.params]
     self.v = [(np.zeros_like(W), np.zeros_like(b)) for W, b in self.params]
@@ -419,6 +423,10 @@ class OracleTrainer:
     self.global_step = 0
 
   def loss_and_grads(self, x_rows):
+    if self.emulate16 is not None and self.spec is None:
+      # master weights stay float64/float32 here exactly as the kernels keep fp32 masters; only the step's operands round
+      model = tower_grads_emulated16(x_rows, self.params, self.margin, self.emulate16)
+      return {"l2_norm": model["l2_norm"]}, model["loss"], model["grads"]
     if self.spec is not None:
       fwd = graph_forward(x_rows, self.spec, self.params, dtype=self.dtype)
     else:
@@ -503,6 +511,47 @@ def mine_semihard(E, guid_triplets, margin, dtype=np.float64):
     neg_row[i] = cand_rows[j]
     d_an[i] = d[j]
   return neg_row, d_an
+
+
+def mine_semihard_emulated16(E, guid_triplets, margin, kind="fp16"):
+  """PRECISION MODEL of cdml_mine_semihard (test infrastructure): the same definition as mine_semihard, with the
+  selection arithmetic the kernel uses -- scores s = a16 . c16 on operands rounded to 16 bits (accumulated here in
+  float64, rounded once to fp32; the tensor core accumulates in fp32), dp = |a-p|^2 from the fp32 embeddings,
+  s_hi = 1 - dp/2, d = max(fma(-2, s, 2), 0) in fp32, valid = (s < s_hi) & (d > dp) & guid not in {a_i, p_i};
+  pick = argmin over (d, row).  (1)/(2) of the definition collapse into that one criterion (csrc/mine.cu).
+  Returns (neg_row [B] int32, d_sel [B] fp32 selection distances, runner_up_gap [B] fp32: distance between the two best
+  valid selection distances -- picks whose gap is at fp32 accumulation noise may legitimately differ)."""
+  E32 = np.asarray(E, np.float32)
+  g = np.asarray(guid_triplets)
+  B = g.shape[0]
+  E16 = round16(E32, kind)
+  A16 = E16[0::3]
+  dpf = np.sum((E32[0::3] - E32[1::3]) ** 2, -1, dtype=np.float32)
+  s_hi = (np.float32(1.0) - np.float32(0.5) * dpf).astype(np.float32)
+  cand_rows = np.stack([3 * np.arange(B) + 1, 3 * np.arange(B) + 2], 1).reshape(-1)
+  cand_guid = g[:, 1:3].reshape(-1)
+  C16 = E16[cand_rows]
+  neg_row = np.empty(B, np.int32)
+  d_sel = np.full(B, np.inf, np.float32)
+  gap = np.full(B, np.inf, np.float32)
+  for s in range(0, B, 1024):
+    S = (A16[s:s + 1024] @ C16.T).astype(np.float32)
+    d = np.maximum(np.float32(2.0) - np.float32(2.0) * S, np.float32(0.0)).astype(np.float32)
+    ok = (S < s_hi[s:s + 1024, None]) & (d > dpf[s:s + 1024, None])
+    ok &= (cand_guid[None, :] != g[s:s + 1024, 0:1]) & (cand_guid[None, :] != g[s:s + 1024, 1:2])
+    dm = np.where(ok, d, np.inf)
+    for i in range(dm.shape[0]):
+      row = dm[i]
+      m = row.min()
+      if not np.isfinite(m):
+        neg_row[s + i] = 3 * (s + i) + 2
+        continue
+      j = np.flatnonzero(row == m)
+      neg_row[s + i] = cand_rows[j].min()                     # ties -> lowest row
+      d_sel[s + i] = m
+      rest = row[row > m]
+      gap[s + i] = 0.0 if len(j) > 1 else (rest.min() - m if len(rest) else np.inf)
+  return neg_row, d_sel, gap
 
 
 # --------------------------------------------------------------------------- #

@@ -31,3 +31,14 @@ def pytest_collection_modifyitems(config, items):
 def golden():
   import numpy as np
   return np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def knn_golden():
+  """Ids returned by the reference's own show_knn.calc_nn (tests/golden/make_knn_golden.py) + the seeded row generator."""
+  import importlib.util
+  import numpy as np
+  spec = importlib.util.spec_from_file_location("_make_knn_golden", os.path.join(GOLDEN, "make_knn_golden.py"))
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  return {"ids": np.load(os.path.join(GOLDEN, "knn_ids_golden.npz")), "cases": mod.CASES, "rows": mod.rows}

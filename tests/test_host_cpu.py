@@ -116,8 +116,10 @@ def test_reader_semantics_and_rank_sharding(lib, tmp_path):
     while (b := p.get_batch_indices()) is not None:
       s.append(b)
     shards.append(s)
-  assert len(shards[0]) == 4 and len(shards[1]) == 3
-  assert all(np.array_equal(shards[0][i], batches[2 * i]) for i in range(4))
+  # 7 batches over 2 ranks: three complete rounds; the odd batch is dropped on BOTH ranks -- a rank with one step more
+  # than its peer would wait forever in that step's all-reduce (every step ends in a collective)
+  assert len(shards[0]) == 3 and len(shards[1]) == 3
+  assert all(np.array_equal(shards[0][i], batches[2 * i]) for i in range(3))
   assert all(np.array_equal(shards[1][i], batches[2 * i + 1]) for i in range(3))
 
 
@@ -167,6 +169,47 @@ def test_checkpoint_index_and_deploy_fallback(lib, tmp_path):
   os.utime(d1, (1, 1))
   with pytest.raises(IOError):
     predict._deployed_checkpoint(str(tmp_path))
+
+
+class _FakeEngine(object):
+  """Host stand-in with the three members save_checkpoint touches (the real engine needs a GPU)."""
+
+  def __init__(self, step, fail=False):
+    self.step, self.fail = step, fail
+
+  def state_dict(self):
+    if self.fail:
+      raise IOError("disk full")
+    return {"dims": [4, 8, 4], "w": np.full(7, self.step, np.float32), "m": np.zeros(7, np.float32),
+            "v": np.zeros(7, np.float32), "step": self.step, "hyper": {"dtype16": 1, "optimizer": "lars", "alpha": 0.2}}
+
+  def get_params(self):
+    return [(np.zeros((4, 8), np.float32), np.zeros(8, np.float32)), (np.zeros((8, 4), np.float32), np.zeros(4, np.float32))]
+
+
+def test_checkpoint_write_is_atomic_and_carries_hyper(lib, tmp_path, monkeypatch):
+  """Saver(max_to_keep=1) order: new file complete -> index switched -> old file removed.  A failure while writing leaves
+  the previous checkpoint and an index that names it; the npz carries the hyper-parameters load_engine honours."""
+  from cdml_b200 import predict, train
+  train.save_checkpoint(_FakeEngine(10), str(tmp_path), 10, "VNet")
+  assert sorted(os.listdir(tmp_path)) == ["checkpoint", "model.ckpt-10.npz"]
+  real_savez = np.savez
+
+  def broken_savez(f, **kw):
+    f.write(b"partial")
+    raise IOError("disk full")
+  monkeypatch.setattr(np, "savez", broken_savez)
+  with pytest.raises(IOError):
+    train.save_checkpoint(_FakeEngine(20), str(tmp_path), 20, "VNet")
+  monkeypatch.setattr(np, "savez", real_savez)
+  assert sorted(os.listdir(tmp_path)) == ["checkpoint", "model.ckpt-10.npz"]          # nothing lost, no debris
+  assert predict.latest_checkpoint(str(tmp_path)).endswith("model.ckpt-10")
+  assert float(np.load(tmp_path / "model.ckpt-10.npz")["w"][0]) == 10.0
+  train.save_checkpoint(_FakeEngine(30), str(tmp_path), 30, "VNet")
+  assert sorted(os.listdir(tmp_path)) == ["checkpoint", "model.ckpt-30.npz"]
+  z = np.load(tmp_path / "model.ckpt-30.npz")
+  assert json.loads(str(z["hyper"])) == {"dtype16": 1, "optimizer": "lars", "alpha": 0.2}
+  assert "fully_connected/weights" in z.files and "fully_connected_1/biases" in z.files
 
 
 def test_imitation_data_matches_reference_stream(lib, golden):
@@ -238,6 +281,32 @@ def cpu_desim(e, f, d, thr, f_end, row_offset=0):
 got = faiss_knn.sharded_desim(torch.tensor(eI), torch.tensor(fI), torch.tensor(fD), 1.4, 31, dist.group.WORLD, desim_fn=cpu_desim)
 want = O.iter_desim(eI, fI, fD, 1.4, 31)
 assert np.array_equal(got.numpy(), want) and (want != eI).sum() > n
+# --- end of data with a batch count that is not a multiple of the world size: every step ends in a collective, so both
+#     ranks must leave the reader loop after the same number of steps (7 batches -> 3 steps each; the old k % world
+#     split gave rank 0 a 4th batch and it waited in its all-reduce until the timeout)
+from cdml_b200 import inputs
+pipe = inputs.MPTripletPipe(os.path.join(sys.argv[4], "*.train"), os.path.join(sys.argv[4], "features.npy"), seed=5, rank=rank, world=world)
+pipe.create_pipe(num_epochs=2, batch_size=8)
+steps, seen = 0, torch.zeros(1)
+while (b := pipe.get_batch_indices()) is not None:
+  t = torch.tensor([float(b[:, :2].sum())]); dist.all_reduce(t); seen += t; steps += 1
+cnt = torch.tensor([steps, -steps]); dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+assert steps == 3 and cnt.tolist() == [3, -3], (steps, cnt)
+# --- Prediction.run_features with the rows split over the ranks (predict.py:71-96 batches are independent): no collective
+#     on the data path, one all-gather to join; 103 rows -> slices of 51 / 52, batch 20 with a tail batch in each slice
+from cdml_b200 import predict
+class HostTower:
+  device, dims, calls = torch.device("cpu"), [6, 4], 0
+  def embed(self, x):
+    HostTower.calls += x.shape[0]
+    return torch.tanh(x[:, :4] * 3.0 + x[:, 2:6])
+feats = np.random.RandomState(9).rand(103, 6).astype(np.float32)
+p = predict.Prediction(sess=HostTower())
+whole = HostTower().embed(torch.tensor(feats)).numpy(); HostTower.calls = 0
+got = p.run_features(feats, 20, process_group=dist.group.WORLD)
+assert np.array_equal(got, whole) and HostTower.calls == (103 * (rank + 1) // 2 - 103 * rank // 2)
+part = p.run_features(feats, 20, process_group=dist.group.WORLD, gather=False)
+assert np.array_equal(part, whole[103 * rank // 2:103 * (rank + 1) // 2])
 dist.barrier(); dist.destroy_process_group()
 print("rank %d ok" % rank)
 '''
@@ -246,8 +315,10 @@ print("rank %d ok" % rank)
 def test_two_rank_protocol_over_gloo(tmp_path):
   script = tmp_path / "gloo_worker.py"
   script.write_text(_GLOO_WORKER)
+  (tmp_path / "data").mkdir()
+  _write_dataset(tmp_path / "data")
   port = str(29500 + os.getpid() % 2000)
-  procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+  procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), str(tmp_path / "data")], stdout=subprocess.PIPE,
                             stderr=subprocess.STDOUT, text=True) for r in range(2)]
   outs = [p.communicate(timeout=240)[0] for p in procs]
   for r, (p, o) in enumerate(zip(procs, outs)):

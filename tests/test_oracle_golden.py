@@ -132,12 +132,18 @@ def test_clip_momentum_lars_and_regularizer_statements():
     opt.step()
     wn, acc = O.momentum_step_tf1(wn, acc, g * (i + 1), 0.1)
   assert np.abs(wn - wt.detach().numpy()).max() < 1e-12
-  # LARS first step (acc = 0): w1 = w - lr * eeta*|w|/(|g| + wd*|w|) * (g + wd*w); zero gradient -> trust ratio 1
+  # LARS as of TF r1.13 (weight decay in the trust ratio only; apply_momentum(var, mom, lr*trust, grad, momentum)).
+  # First step (acc = 0): w1 = w - lr * eeta*|w|/(|g| + wd*|w|) * g; zero gradient -> trust ratio 1 and no movement
   w1, acc1 = O.lars_step_tf1(w, np.zeros_like(w), g, lr=1.0)
   wn_, gn_ = np.linalg.norm(w), np.linalg.norm(g)
-  assert np.allclose(w1, w - 1e-3 * wn_ / (gn_ + 1e-4 * wn_) * (g + 1e-4 * w), rtol=1e-12)
+  assert np.allclose(w1, w - 1e-3 * wn_ / (gn_ + 1e-4 * wn_) * g, rtol=1e-12) and np.array_equal(acc1, g)
   w2, _ = O.lars_step_tf1(w, np.zeros_like(w), np.zeros_like(w), lr=0.5)
-  assert np.allclose(w2, w - 0.5 * 1e-4 * w)
+  assert np.array_equal(w2, w)
+  # second step: the accumulator carries the RAW gradient (the trust ratio of step 1 is not folded into it)
+  g2 = rng.standard_normal((7, 5))
+  w3, acc3 = O.lars_step_tf1(w1, acc1, g2, lr=1.0)
+  t2 = 1e-3 * np.linalg.norm(w1) / (np.linalg.norm(g2) + 1e-4 * np.linalg.norm(w1))
+  assert np.allclose(acc3, 0.9 * g + g2) and np.allclose(w3, w1 - t2 * (0.9 * g + g2), rtol=1e-12)
   # regularizer: d(reg_penalty * reg_loss)/dW by finite differences, and its use in step()
   params = O.init_tower([6, 8, 4], seed=2, dtype=np.float64)
   tr = O.OracleTrainer(params, optimizer="sgd", lr=0.5, reg_penalty=3.0, l2_penalty=1e-2)
@@ -175,6 +181,51 @@ def test_flat_knn_against_independent_brute_force_and_merge():
   # inner product
   Dip, Iip = O.flat_knn(X, k=5, l2_norm=False, metric="IP")
   assert (np.diff(Dip, axis=1) <= 0).all() and Iip[3, 0] == np.argmax(X @ X[3])
+
+
+def test_flat_knn_ids_pinned_to_reference_show_knn_and_sklearn(knn_golden):
+  """Pin of the exact-KNN ids: (1) the ids the reference's OWN brute force (show_knn.calc_nn, executed under import shims
+  by tests/golden/make_knn_golden.py) returned for seeded rows; (2) scikit-learn's brute-force NearestNeighbors as a
+  third, independent statement.  The oracle must reproduce both except where the k-th / (k+1)-th inner products differ by
+  less than fp32 summation noise (north_star's exact-tie exemption) -- and then only as a permutation inside the tie."""
+  from sklearn.neighbors import NearestNeighbors
+  for name, (seed, N, d, nq, k, clustered) in knn_golden["cases"].items():
+    X = knn_golden["rows"](seed, N, d, clustered)
+    q = knn_golden["ids"][name + "_queries"]
+    want, gap = knn_golden["ids"][name + "_ids"], knn_golden["ids"][name + "_gap"]
+    assert np.array_equal(want[:, 0], q)                                  # a row is its own nearest neighbour
+    clear = gap > 2e-6
+    assert clear.mean() > 0.9
+    for metric in ("IP", "L2"):
+      D, I = O.flat_knn(X, X[q], k=k, l2_norm=False, metric=metric)
+      assert np.array_equal(I[clear], want[clear]), (name, metric)
+      assert all(set(I[i]) ^ set(want[i]) == set() or gap[i] <= 2e-6 for i in range(nq))
+      if metric == "L2":
+        assert np.all(np.diff(D, axis=1) >= 0) and np.allclose(D[:, 0], 0, atol=2e-6)
+    nn = NearestNeighbors(n_neighbors=k, algorithm="brute", metric="euclidean").fit(X.astype(np.float64))
+    dist, ids = nn.kneighbors(X[q].astype(np.float64))
+    assert np.array_equal(ids[clear], want[clear]), name                   # third statement agrees with the reference's
+    D, _ = O.flat_knn(X, X[q], k=k, l2_norm=False, metric="L2")
+    assert np.allclose(D, dist ** 2, atol=5e-6)
+
+
+def test_emulated16_selection_model_is_the_mining_definition_on_rounded_operands():
+  """mine_semihard_emulated16 (the precision model the GPU test gates against) == mine_semihard evaluated on the rounded
+  embeddings, wherever the pick is not a near-tie of the rounding itself."""
+  rng = np.random.RandomState(3)
+  B, D, G = 96, 32, 60
+  trip = O.synth_triplets(B, G, seed=5)
+  E = O.l2_normalize(O.l2_normalize(rng.standard_normal((G, D)))[trip.reshape(-1)] + 0.3 * rng.standard_normal((3 * B, D))).astype(np.float32)
+  row16, d16, gap = O.mine_semihard_emulated16(E, trip, 0.8, "fp16")
+  row, d = O.mine_semihard(O.round16(E, "fp16"), trip, 0.8)
+  # the two differ only in HOW the rounded operands enter (d = 2 - 2 a16.c16 against the fp32 dp here, |a16 - c16|^2
+  # against the rounded dp there: rounded rows are unit only to ~3e-4), which moves picks that sit at the d > dp boundary
+  same = row16 == row
+  assert same.mean() > 0.95
+  assert np.allclose(d16[same], d[same], atol=2e-3)
+  dp = ((E[0::3].astype(np.float64) - E[1::3]) ** 2).sum(-1)
+  for i in np.flatnonzero(~same):
+    assert min(abs(d16[i] - dp[i]), abs(d[i] - dp[i])) < 2e-3 or gap[i] < 2e-3, i
 
 
 def test_semihard_mining_definition():
