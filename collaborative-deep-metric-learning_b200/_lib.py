@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcdml.so")
 
 F16, BF16 = 0, 1
-EPI_STORE_F32, EPI_STORE_16, EPI_L2NORM, EPI_MASK_LEAKY = 0, 1, 2, 3
+EPI_STORE_F32, EPI_STORE_16, EPI_L2NORM, EPI_MASK_LEAKY, EPI_MASK_BITS = 0, 1, 2, 3, 4
 METRIC_L2, METRIC_IP = 0, 1
 
 _P = c_void_p
@@ -48,6 +48,7 @@ _SIGNATURES = {
   "cdml_cast16": (c_int, [_P, _P, c_int64, _P, c_int, _P]),
   "cdml_fill_column16": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_float, c_int, _P]),
   "cdml_mine_semihard": (c_int, [_P, _P, c_int64, c_int, _P, c_int64, _P, c_int64, c_int, c_float, _P, _P, _P]),
+  "cdml_mine_last_stats": (c_int, [_P, _P, _P]),
   "cdml_knn_index_build": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, POINTER(c_void_p)]),
   "cdml_knn_index_destroy": (c_int, [_P]),
   "cdml_knn_search": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, c_int64, _P]),

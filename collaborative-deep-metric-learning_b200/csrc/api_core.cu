@@ -72,6 +72,7 @@ int cdml_ctx_create(int device, cdml_ctx** out) {
   c->num_sms = prop.multiProcessorCount;
   c->encode_tiled = nullptr;
   c->scratch = nullptr, c->scratch_bytes = 0;
+  c->mine_stats = nullptr;
   {  // keep stream-ordered allocations cached across synchronisation points
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -101,6 +102,7 @@ int cdml_ctx_destroy(cdml_ctx* ctx) {
   if (ctx == nullptr) return 0;
   cudaFree(ctx->dev_flags);
   cudaFree(ctx->scratch);
+  cudaFree(ctx->mine_stats);
   delete ctx;
   return 0;
 }

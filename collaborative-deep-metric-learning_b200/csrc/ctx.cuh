@@ -13,6 +13,7 @@ struct cdml_ctx {
   cdml_encode_tiled_fn encode_tiled;
   void* scratch;         // grow-only device scratch for kernels that need a few MB of workspace (mining)
   size_t scratch_bytes;
+  unsigned long long* mine_stats;  // device [2]: re-scans and mined anchors of the last cdml_mine_semihard (diagnostics)
 };
 
 namespace cdml {

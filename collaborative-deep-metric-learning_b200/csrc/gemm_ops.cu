@@ -26,11 +26,12 @@ static int dispatch_epilogue(cdml_ctx* ctx, const void* A, int64_t lda, const vo
       return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, num_splits, e, stream);
     }
     case 1: {
+      CDML_REQUIRE(aux0 == nullptr || ld_aux1 >= M, "STORE_16: the sign-mask pitch (ld_aux1, words) must be >= M");
       if (bf) {
-        EpiStore16<kBN, 1> e{static_cast<uint16_t*>(out), ld_out, bias, alpha};
+        EpiStore16<kBN, 1> e{static_cast<uint16_t*>(out), ld_out, bias, alpha, static_cast<uint32_t*>(aux0), ld_aux1};
         return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
       }
-      EpiStore16<kBN, 0> e{static_cast<uint16_t*>(out), ld_out, bias, alpha};
+      EpiStore16<kBN, 0> e{static_cast<uint16_t*>(out), ld_out, bias, alpha, static_cast<uint32_t*>(aux0), ld_aux1};
       return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
     }
     case 2: {
@@ -51,6 +52,15 @@ static int dispatch_epilogue(cdml_ctx* ctx, const void* A, int64_t lda, const vo
         return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
       }
       EpiMaskLeaky<kBN, 0> e{static_cast<uint16_t*>(out), ld_out, static_cast<const uint16_t*>(aux1), ld_aux1, alpha};
+      return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+    }
+    case 4: {
+      CDML_REQUIRE(aux1 != nullptr && ld_aux1 >= M, "MASK_BITS epilogue needs aux1 (packed sign mask) with a pitch of >= M words");
+      if (bf) {
+        EpiMaskBits<kBN, 1> e{static_cast<uint16_t*>(out), ld_out, static_cast<const uint32_t*>(aux1), ld_aux1, alpha};
+        return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
+      }
+      EpiMaskBits<kBN, 0> e{static_cast<uint16_t*>(out), ld_out, static_cast<const uint32_t*>(aux1), ld_aux1, alpha};
       return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);
     }
     case 100: {

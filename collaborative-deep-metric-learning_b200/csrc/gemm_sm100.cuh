@@ -154,6 +154,7 @@ struct EpiStoreF32 {
   struct State {};
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
   static constexpr bool kPrefetchNext = false;
+  static constexpr bool kRowConsts = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -199,6 +200,7 @@ struct EpiStore16 {
   struct State {};
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
   static constexpr bool kPrefetchNext = false;
+  static constexpr bool kRowConsts = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -206,6 +208,12 @@ struct EpiStore16 {
   int64_t ld;
   const float* bias;  // nullable
   float alpha;
+  // Optional packed SIGN MASK of the output (1 bit per element; chunk-major: word [nb/32][row], pitch ld_mask words >= M,
+  // bit j <-> column nb + j, set iff the pre-activation is > 0).  It is all the data-gradient GEMM of the backward pass
+  // needs of this activation (leaky' = 1 | alpha): 1/16 of the bytes of the activation itself, and every warp access is
+  // one coalesced 128-byte line (lane <-> row) here and in EpiMaskBits.
+  uint32_t* mask_out;  // nullable
+  int64_t ld_mask;
   __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1, uint32_t stg, State& st) const {
 #pragma unroll 1
     for (int c = c0; c < c1; ++c) {
@@ -216,12 +224,16 @@ struct EpiStore16 {
       const float b_lane = chunk_bias(bias, nb, s.N);
       tmem_ld_wait();
       uint32_t pk[16];
+      uint32_t bits = 0u;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float x0 = __uint_as_float(v[2 * j]) + __shfl_sync(0xffffffffu, b_lane, 2 * j);
         const float x1 = __uint_as_float(v[2 * j + 1]) + __shfl_sync(0xffffffffu, b_lane, 2 * j + 1);
+        bits |= (x0 > 0.f ? 1u : 0u) << (2 * j);
+        bits |= (x1 > 0.f ? 1u : 0u) << (2 * j + 1);
         pk[j] = pack2<kBf16>(leaky(x0, alpha), leaky(x1, alpha));
       }
+      if (mask_out != nullptr && row < s.M) mask_out[static_cast<int64_t>(nb >> 5) * ld_mask + row] = bits;
       store_chunk16(out, ld, row - static_cast<int>(threadIdx.x & 31), nb, s.M, s.N, stg, pk);
     }
   }
@@ -235,6 +247,7 @@ struct EpiL2Norm {
   struct State {};
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
   static constexpr bool kPrefetchNext = false;
+  static constexpr bool kRowConsts = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -297,6 +310,7 @@ struct EpiMaskLeaky {
     uint4 raw[4][4];   // the four 32x32 mask chunks of this warp's half-tile, in the coalesced fetch layout
   };
   static constexpr bool kPrefetchNext = false;
+  static constexpr bool kRowConsts = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -381,6 +395,63 @@ struct EpiMaskLeaky {
   }
 };
 
+// Data-gradient epilogue on the packed sign mask EpiStore16 wrote in the forward pass: out = acc * (bit ? 1 : alpha).
+// The mask of a thread's four chunks is four registers (the 16-bit activation it replaces was 64), so the loads of the
+// NEXT tile are issued before the current tile is processed (kPrefetchNext) and the TMEM reads are double-buffered: the
+// kernel is bound by its 16-bit output stream (M*N*2 bytes), not by a second M*N*2-byte mask read.
+template <int BN, int kBf16>
+struct EpiMaskBits {
+  static constexpr bool kSplitColumns = true;
+  struct State {
+    uint32_t bits[4];
+  };
+  static constexpr bool kPrefetchNext = true;
+  static constexpr bool kRowConsts = false;
+  __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
+  __device__ __forceinline__ void block_begin(uint32_t) const {}
+  __device__ __forceinline__ void block_end(uint32_t) const {}
+  uint16_t* out;
+  int64_t ld;
+  const uint32_t* mask;   // [ceil(N/32)][ld_mask] words, lane <-> row
+  int64_t ld_mask;
+  float alpha;
+  __device__ __forceinline__ void pre(State& st, int row, int n0, const GemmShape& s, int c0, int c1, uint32_t /*stg*/) const {
+    static_assert(BN == 256, "a warp owns 4 chunks of the tile");
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int nb = n0 + (c0 + cc) * 32;
+      st.bits[cc] = (c0 + cc < c1 && nb < s.N && row < s.M) ? __ldg(mask + static_cast<int64_t>(nb >> 5) * ld_mask + row) : 0u;
+    }
+  }
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1,
+                                      uint32_t stg, State& st) const {
+    const int row_base = row - static_cast<int>(threadIdx.x & 31);
+    auto ok = [&](int cc) { return c0 + cc < c1 && n0 + (c0 + cc) * 32 < s.N; };   // warp-uniform
+    auto chunk = [&](const uint32_t (&v)[32], int cc) {
+      const uint32_t b = st.bits[cc];
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float x0 = __uint_as_float(v[2 * j]) * ((b >> (2 * j)) & 1u ? 1.f : alpha);
+        const float x1 = __uint_as_float(v[2 * j + 1]) * ((b >> (2 * j + 1)) & 1u ? 1.f : alpha);
+        pk[j] = pack2<kBf16>(x0, x1);
+      }
+      store_chunk16(out, ld, row_base, n0 + (c0 + cc) * 32, s.M, s.N, stg, pk);
+    };
+    uint32_t va[32], vb[32];
+    if (ok(0)) tmem_ld_32x32(taddr + c0 * 32, va);
+#pragma unroll
+    for (int cc = 0; cc < 4; cc += 2) {
+      tmem_ld_wait();
+      if (ok(cc + 1)) tmem_ld_32x32(taddr + (c0 + cc + 1) * 32, vb);
+      if (ok(cc)) chunk(va, cc);
+      tmem_ld_wait();
+      if (cc + 2 < 4 && ok(cc + 2)) tmem_ld_32x32(taddr + (c0 + cc + 2) * 32, va);
+      if (ok(cc + 1)) chunk(vb, cc + 1);
+    }
+  }
+};
+
 // Measurement aid (epilogue codes 100/101 of cdml_gemm16): no epilogue work at all / TMEM reads only.  Separates the
 // main-loop rate from the TMEM-read and store costs when tuning.
 template <int BN, int kReadTmem>
@@ -389,6 +460,7 @@ struct EpiNull {
   struct State {};
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
   static constexpr bool kPrefetchNext = false;
+  static constexpr bool kRowConsts = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -587,8 +659,10 @@ struct ResBSmem {
   static constexpr uint32_t kBPanel = BN * kBK * 2;
   static constexpr uint32_t kMaxKb = 4;
   static constexpr uint32_t kEpiOff = kMaxKb * kBPanel + kAStages * kABytes;
-  static constexpr uint32_t kBarOff = kEpiOff + kEpiStageBytes;
-  static constexpr uint32_t kNumBars = 2 * kAStages + 2 + 4;
+  static constexpr uint32_t kRowConstOff = kEpiOff + kEpiStageBytes;   // 2 slots x 128 rows x 32 B (Epi::kRowConsts)
+  static constexpr uint32_t kRowConstSlot = kBM * 32;
+  static constexpr uint32_t kBarOff = kRowConstOff + 2 * kRowConstSlot;
+  static constexpr uint32_t kNumBars = 2 * kAStages + 2 + 4 + 2;
   static constexpr uint32_t kTotal = kBarOff + kNumBars * 8 + 16 + 1024;
 };
 
@@ -609,6 +683,8 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   const uint32_t b_empty = bar0 + 8u * (2 * kAStages + 1);
   auto tfull_bar = [&](int i) { return bar0 + 8u * (2 * kAStages + 2 + i); };
   auto tempty_bar = [&](int i) { return bar0 + 8u * (2 * kAStages + 4 + i); };
+  auto cfull_bar = [&](int i) { return bar0 + 8u * (2 * kAStages + 6 + i); };       // row constants of tile `it` are in slot it & 1
+  auto cslot = [&](int i) { return base + L::kRowConstOff + i * L::kRowConstSlot; };
   const uint32_t tmem_slot = bar0 + 8u * L::kNumBars;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
   const int warp = threadIdx.x >> 5;
@@ -630,6 +706,7 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
       mbar_init(tempty_bar(i), 8);
+      mbar_init(cfull_bar(i), 1);
     }
     fence_mbar_init();
   }
@@ -703,6 +780,30 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       }
       tc_commit(b_empty);  // the panel may be overwritten once every MMA of this unit has retired
     }
+  } else if (warp == 3) {
+   if constexpr (Epi::kRowConsts) {
+    // ===================== row-constant prefetcher (the otherwise idle fourth control warp) =====================
+    // Per-row inputs of the epilogue (mining: |a-p|^2, the two excluded guids, the anchor's running bound) are fetched for
+    // tile `it` into shared-memory slot it & 1 as soon as the epilogue has released tile it-2 -- about one tile ahead of
+    // their use.  Loaded by the epilogue warps themselves they sat on the critical path: an epilogue-bound tile starts
+    // with the accumulator already complete, so every tile paid a full L2 round trip before its first instruction.
+    int it = 0;
+    GemmShape gs;
+    gs.M = s.M, gs.N = s.N, gs.K = s.K;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int chunk = s.n_fastest ? u / s.n_tiles : u % s.m_chunks;
+      const int t0 = chunk * s.tiles_per_chunk, t1 = min(s.m_tiles, t0 + s.tiles_per_chunk);
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int as = it & 1;
+        const uint32_t ap = (it >> 1) & 1;
+        mbar_wait(tempty_bar(as), ap ^ 1, 700 + as);
+#pragma unroll
+        for (int r = lane; r < kBM; r += 32) epi.row_consts(t * kBM + r, gs, cslot(as) + r * 32);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cfull_bar(as));
+      }
+    }
+   }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;
@@ -738,7 +839,7 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     typename Epi::State est;
     if (cur.valid && active) {
       epi.cols(cur.nblk * BN, gs, ec0, ec1, stg);
-      epi.pre(est, cur.t * kBM + q * 32 + lane, cur.nblk * BN, gs, ec0, ec1, stg);
+      if constexpr (!Epi::kRowConsts) epi.pre(est, cur.t * kBM + q * 32 + lane, cur.nblk * BN, gs, ec0, ec1, stg);
     }
     while (cur.valid) {
       TileIter nxt = cur;
@@ -749,11 +850,17 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       const int as = it & 1;
       const uint32_t ap = (it >> 1) & 1;
       typename Epi::State est_next;
+      if constexpr (Epi::kRowConsts) {
+        mbar_wait(cfull_bar(as), ap, 800 + as);
+        if (active) epi.load_state(est, cslot(as) + (q * 32 + lane) * 32);
+        est_next = est;
+      }
       mbar_wait(tfull_bar(as), ap, 400 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       if (active) {
-        if (Epi::kPrefetchNext && nxt.valid) epi.pre(est_next, nxt.t * kBM + q * 32 + lane, nxt.nblk * BN, gs, ec0, ec1, stg);
+        if constexpr (!Epi::kRowConsts)
+          if (Epi::kPrefetchNext && nxt.valid) epi.pre(est_next, nxt.t * kBM + q * 32 + lane, nxt.nblk * BN, gs, ec0, ec1, stg);
         epi.run(taddr, cur.t * kBM + q * 32 + lane, cur.nblk * BN, 0, gs, ec0, ec1, stg, est);
       }
       tc_fence_before();
@@ -761,7 +868,8 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       if (lane == 0) mbar_arrive(tempty_bar(as));
       if (active && nxt.valid) {
         epi.cols(nxt.nblk * BN, gs, ec0, ec1, stg);   // the previous tile no longer reads the column cache
-        if (!Epi::kPrefetchNext) epi.pre(est_next, nxt.t * kBM + q * 32 + lane, nxt.nblk * BN, gs, ec0, ec1, stg);
+        if constexpr (!Epi::kRowConsts)
+          if (!Epi::kPrefetchNext) epi.pre(est_next, nxt.t * kBM + q * 32 + lane, nxt.nblk * BN, gs, ec0, ec1, stg);
       }
       est = est_next;
       cur = nxt;

@@ -54,6 +54,7 @@ template <int BN>
 struct EpiKnnGroupMax {
   static constexpr bool kSplitColumns = true;
   static constexpr bool kPrefetchNext = false;
+  static constexpr bool kRowConsts = false;
   struct State {};
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t epi_smem) const { col_cache_reset(epi_smem); }
@@ -127,6 +128,7 @@ struct EpiKnnCollect {
     float hr;
   };
   static constexpr bool kPrefetchNext = true;   // pre() only loads a row constant into registers
+  static constexpr bool kRowConsts = false;
   __device__ __forceinline__ void block_begin(uint32_t epi_smem) const {
     col_cache_reset(epi_smem);
     for (int w = 0; w < kKnnLogsPerCta; ++w)

@@ -23,14 +23,35 @@ template <int BN, int kVariant = 0>
 struct EpiMine {
   static constexpr bool kSplitColumns = true;
   static constexpr bool kPrefetchNext = (kVariant & 1) == 0;   // pre() only loads the anchor's constants into registers
+  // resident-B kernel: the anchor's four constants arrive through shared memory, fetched one tile ahead by the spare
+  // control warp (row_consts / load_state); the generic kernel (small batches) still calls pre()
+  static constexpr bool kRowConsts = (kVariant & 4) != 0;   // measured on B200: no gain (3.93 vs 3.89 ms clustered) and the
+                                                             // two-tile-old bound costs re-scans (5.0 vs 4.3 ms structureless)
   struct State {
     float dpi, bound_d;
     int ga, gp;
+    uint32_t bound_row;   // row of the anchor's best candidate so far (ties -> lowest row)
   };
   const float* dp;        // [B] exact |a-p|^2
   const int32_t* guid;    // [B,3] int32 guids
   unsigned long long* best;  // [B] (float bits of d) << 32 | row
   int cand;  // 1: columns are the positives' rows 3j+1, 2: the negatives' rows 3j+2
+  unsigned long long* stats;   // [0] += re-scanned (anchor, 32-column chunk) pairs
+  __device__ __forceinline__ void row_consts(int row, const GemmShape& s, uint32_t dst) const {
+    const bool row_ok = row < s.M;
+    const uint32_t inf = 0x7f800000u;
+    const uint32_t dpi = row_ok ? __float_as_uint(__ldg(dp + row)) : inf;
+    const uint32_t ga = row_ok ? static_cast<uint32_t>(__ldg(guid + 3 * row)) : 0u;
+    const uint32_t gp = row_ok ? static_cast<uint32_t>(__ldg(guid + 3 * row + 1)) : 0u;
+    const unsigned long long key = row_ok ? *(reinterpret_cast<volatile unsigned long long*>(best) + row) : ~0ull;
+    sts128(dst, dpi, ga, gp, static_cast<uint32_t>(key >> 32));
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + 16), "r"(static_cast<uint32_t>(key)) : "memory");
+  }
+  __device__ __forceinline__ void load_state(State& st, uint32_t src) const {
+    const uint4 v = lds128(src);
+    st.dpi = __uint_as_float(v.x), st.ga = static_cast<int>(v.y), st.gp = static_cast<int>(v.z), st.bound_d = __uint_as_float(v.w);
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(st.bound_row) : "r"(src + 16) : "memory");
+  }
   // the anchor's constants do not depend on the accumulator: the resident-B kernel issues them one tile ahead
   __device__ __forceinline__ void pre(State& st, int row, int /*n0*/, const GemmShape& s, int, int, uint32_t) const {
     const bool row_ok = row < s.M;
@@ -38,7 +59,9 @@ struct EpiMine {
     st.dpi = row_ok ? __ldg(dp + row) : inf;
     st.ga = row_ok ? __ldg(guid + 3 * row) : 0;
     st.gp = row_ok ? __ldg(guid + 3 * row + 1) : 0;
-    st.bound_d = row_ok ? __uint_as_float(static_cast<uint32_t>(best[row] >> 32)) : inf;   // empty key reads as NaN
+    const unsigned long long key = row_ok ? best[row] : ~0ull;
+    st.bound_d = __uint_as_float(static_cast<uint32_t>(key >> 32));   // empty key reads as NaN
+    st.bound_row = static_cast<uint32_t>(key);
   }
   // candidate guids of the warp's 128 columns, once per column block (-1 beyond N: the re-scan skips them)
   __device__ __forceinline__ void cols(int n0, const GemmShape& s, int c0, int /*c1*/, uint32_t stg) const {
@@ -59,6 +82,7 @@ struct EpiMine {
     float bound_d = st.bound_d;                                // best distance known for this anchor (any tile)
     if (!(bound_d == bound_d)) bound_d = inf;                  // empty key reads as NaN
     float s_lo = 1.f - 0.5f * bound_d;                         // a chunk matters only if it holds a score >= this
+    uint32_t brow = st.bound_row;                              // ... and a score EQUAL to it only in a row below this one
     float bd = inf;
     int br = -1;
     uint32_t va[32], vb[32];
@@ -76,12 +100,17 @@ struct EpiMine {
         u1 = umin3(u1, __float_as_uint(hi.x), __float_as_uint(hi.y));
       }
       // the chunk matters only if it holds a score in [s_lo, s_hi), i.e. 0 <= t <= s_hi - s_lo (monotone in fp32;
-      // t == +0 is a harmless false alarm: the re-scan below applies the exact conditions)
-      unsigned int hits = __ballot_sync(0xffffffffu, min(u0, u1) <= __float_as_uint(s_hi - s_lo));
+      // t == +0 is a harmless false alarm: the re-scan below applies the exact conditions).  A score that merely TIES
+      // the bound wins only with a lower row (the result is the minimum over (distance, row)): chunks whose first row lies
+      // beyond the bound's row skip the re-scan -- on near-degenerate batches (an untrained tower: every candidate within
+      // 1e-3 of the anchor, fp32 scores 6e-8 apart) ties were 3/4 of all re-scans.
+      const uint32_t mu = min(u0, u1), thr = __float_as_uint(s_hi - s_lo);
+      unsigned int hits = __ballot_sync(0xffffffffu, mu < thr || (mu == thr && static_cast<uint32_t>(3 * nb + cand) < brow));
       // Re-scan (rare once the anchors' bounds have tightened): the triggering row's 32 scores go through the warp's
       // staging slice so that lane j examines column j -- compact code (the former per-thread unrolled scan made the
       // kernel 70 KB of SASS and the epilogue instruction-cache bound), same selection: minimum d, ties -> lowest row.
       if (hits != 0u) {
+        if (lane == 0) atomicAdd(stats, static_cast<unsigned long long>(__popc(hits)));
         int g_lane;   // candidate guid of column nb + lane (column cache)
         asm volatile("ld.shared.b32 %0, [%1];" : "=r"(g_lane) : "r"(stg + kColCacheOff + 128 * cc + 4 * lane) : "memory");
         do {
@@ -105,7 +134,9 @@ struct EpiMine {
             const int col = __ffs(__ballot_sync(0xffffffffu, pass && __float_as_uint(d) == kmin)) - 1;
             if (lane == src) {
               bd = __uint_as_float(kmin), br = 3 * (nb + col) + cand;
-              s_lo = fmaxf(s_lo, 1.f - 0.5f * bd);
+              const float s_new = 1.f - 0.5f * bd;
+              if (s_new > s_lo || (s_new == s_lo && static_cast<uint32_t>(br) < brow)) brow = static_cast<uint32_t>(br);
+              s_lo = fmaxf(s_lo, s_new);
             }
           }
         } while (hits != 0u);
@@ -140,8 +171,9 @@ struct EpiMine {
 
 __global__ void mine_prepare_kernel(const float* __restrict__ E, int64_t ld, int D, const int64_t* __restrict__ guid64,
                                     int64_t B, float* __restrict__ dp, int32_t* __restrict__ guid32,
-                                    unsigned long long* __restrict__ best) {
+                                    unsigned long long* __restrict__ best, unsigned long long* __restrict__ stats) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x < 2) stats[threadIdx.x] = 0ull;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + warp; i < B; i += static_cast<int64_t>(gridDim.x) * 8) {
     const float* a = E + 3 * i * ld;
     const float* p = a + ld;
@@ -159,11 +191,14 @@ __global__ void mine_prepare_kernel(const float* __restrict__ E, int64_t ld, int
 
 __global__ void mine_finalize_kernel(const float* __restrict__ E, int64_t ld, int D,
                                      const unsigned long long* __restrict__ best, int64_t B,
-                                     int32_t* __restrict__ neg_row, float* __restrict__ d_an) {
+                                     int32_t* __restrict__ neg_row, float* __restrict__ d_an,
+                                     unsigned long long* __restrict__ stats) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned int mined = 0;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + warp; i < B; i += static_cast<int64_t>(gridDim.x) * 8) {
     const unsigned long long kb = best[i];
     const int r = kb != kNoCand ? static_cast<int>(static_cast<uint32_t>(kb)) : static_cast<int>(3 * i + 2);
+    mined += kb != kNoCand ? 1u : 0u;
     if (lane == 0) neg_row[i] = r;
     if (d_an != nullptr) {  // exact fp32 distance of the chosen negative
       const float* a = E + 3 * i * ld;
@@ -178,6 +213,7 @@ __global__ void mine_finalize_kernel(const float* __restrict__ E, int64_t ld, in
       if (lane == 0) d_an[i] = s;
     }
   }
+  if (lane == 0 && mined != 0u) atomicAdd(stats + 1, static_cast<unsigned long long>(mined));
 }
 
 }  // namespace cdml
@@ -195,26 +231,45 @@ extern "C" int cdml_mine_semihard(cdml_ctx* ctx, const void* E16, int64_t ld16, 
   const size_t bytes = static_cast<size_t>(B) * (8 + 4 + 12) + 64;
   uint8_t* ws = static_cast<uint8_t*>(ctx_scratch(ctx, bytes));
   if (ws == nullptr) return -2;
+  if (ctx->mine_stats == nullptr) CDML_CHECK_CUDA(cudaMalloc(&ctx->mine_stats, 2 * sizeof(unsigned long long)));
+  unsigned long long* stats = ctx->mine_stats;
   unsigned long long* best = reinterpret_cast<unsigned long long*>(ws);
   float* dp = reinterpret_cast<float*>(best + B);
   int32_t* guid32 = reinterpret_cast<int32_t*>(dp + B);
   const int grid = static_cast<int>(std::min<int64_t>((B + 7) / 8, ctx->num_sms * 8));
-  mine_prepare_kernel<<<grid, 256, 0, st>>>(E32, ld32, D, guid, B, dp, guid32, best);
+  mine_prepare_kernel<<<grid, 256, 0, st>>>(E32, ld32, D, guid, B, dp, guid32, best, stats);
   int rc = 0;
   const uint16_t* e16 = static_cast<const uint16_t*>(E16);
   for (int cand = 1; cand <= 2 && rc >= 0; ++cand) {
     // A: anchors = rows 0,3,6,.. (pitch 3*ld16); B: candidates = rows cand, cand+3, .. ; both K-major, K = D.
     // Variant 1 (measured best of the four on B200: 3.79 ms vs 4.17-4.25): pipelined TMEM reads, anchor constants
     // fetched after the previous tile is released (a one-tile-ahead fetch of the running bound makes it staler).
-    EpiMine<kBN, 1> epi{dp, guid32, best, cand};
-    if (resb_applicable(D) && B >= 8 * kBM)
+    EpiMine<kBN, 1> epi{dp, guid32, best, cand, stats};
+    static int rowc = -1;   // CDML_MINE_ROWCONSTS=1: anchor constants through the spare warp's shared-memory slots (A/B aid)
+    if (rowc < 0) rowc = getenv("CDML_MINE_ROWCONSTS") != nullptr ? 1 : 0;
+    if (resb_applicable(D) && B >= 8 * kBM && rowc) {
+      EpiMine<kBN, 5> epi5{dp, guid32, best, cand, stats};
+      rc = launch_gemm_resb(ctx, e16, 3 * ld16, e16 + cand * ld16, 3 * ld16, B, B, D, dtype16, epi5, st);
+    } else if (resb_applicable(D) && B >= 8 * kBM)
       rc = launch_gemm_resb(ctx, e16, 3 * ld16, e16 + cand * ld16, 3 * ld16, B, B, D, dtype16, epi, st);
     else
       rc = launch_gemm<0, 0>(ctx, e16, 3 * ld16, e16 + cand * ld16, 3 * ld16, B, B, D, dtype16, 1, epi, st);
   }
   if (rc >= 0) {
-    mine_finalize_kernel<<<grid, 256, 0, st>>>(E32, ld32, D, best, B, neg_row, d_an);
+    mine_finalize_kernel<<<grid, 256, 0, st>>>(E32, ld32, D, best, B, neg_row, d_an, stats);
     rc = cudaGetLastError() == cudaSuccess ? 0 : -2;
   }
   return rc < 0 ? rc : 0;
+}
+
+extern "C" int cdml_mine_last_stats(cdml_ctx* ctx, int64_t* out2, void* stream) {
+  CDML_REQUIRE(ctx && out2, "cdml_mine_last_stats: NULL argument");
+  out2[0] = out2[1] = 0;
+  if (ctx->mine_stats == nullptr) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long h[2];
+  CDML_CHECK_CUDA(cudaMemcpyAsync(h, ctx->mine_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CDML_CHECK_CUDA(cudaStreamSynchronize(st));
+  out2[0] = static_cast<int64_t>(h[0]), out2[1] = static_cast<int64_t>(h[1]);
+  return 0;
 }

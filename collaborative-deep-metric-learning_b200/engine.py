@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import ops
-from ._lib import BF16, EPI_L2NORM, EPI_MASK_LEAKY, EPI_STORE_16, EPI_STORE_F32, F16
+from ._lib import BF16, EPI_L2NORM, EPI_MASK_BITS, EPI_MASK_LEAKY, EPI_STORE_16, EPI_STORE_F32, F16
 
 LEAKY_ALPHA = 0.2
 
@@ -185,6 +185,8 @@ class TowerEngine:
     if train:
       B = R // 3
       buf["dz"] = [mat16(self.dims[l + 1]) for l in range(self.L)]
+      # 1 bit per hidden activation: written by the forward epilogue, read by the data-gradient epilogue (leaky')
+      buf["mask"] = [ops.sign_mask_buffer(R, self.dims[l + 1], dev) for l in range(self.L - 1)]
       buf["G"] = torch.empty((R, D), dtype=torch.float32, device=dev)
       buf["loss"] = {k: torch.empty((B,), dtype=torch.float32, device=dev) for k in ("pos_dist", "neg_dist", "hinge_dist")}
       buf["loss"]["stats"] = torch.empty((4,), dtype=torch.float32, device=dev)
@@ -221,7 +223,8 @@ class TowerEngine:
     for l in range(self.L):
       K, N = self.dims[l], self.dims[l + 1]
       if l < self.L - 1:
-        ops.gemm16(h, self.W16[l], R, N, K, 0, 1, EPI_STORE_16, buf["acts"][l], bias=self.b[l], alpha=self.alpha)
+        ops.gemm16(h, self.W16[l], R, N, K, 0, 1, EPI_STORE_16, buf["acts"][l], bias=self.b[l], alpha=self.alpha,
+                   aux0=buf["mask"][l] if train else None)
         h = buf["acts"][l]
       else:
         ops.gemm16(h, self.W16[l], R, N, K, 0, 1, EPI_L2NORM, buf["e"], bias=self.b[l], alpha=self.alpha,
@@ -302,8 +305,8 @@ class TowerEngine:
       self._weight_gradient(l, inp, dz[l], R, buf, with_bias_row=(l > 0 or input_ones))
       if l > 0:
         # data gradient + leaky' of the previous layer: dz[l-1] = (dz[l] . W_l^T) * leaky'(h_{l-1})
-        ops.gemm16(dz[l], self.W16[l], R, K_in, N_out, 0, 0, EPI_MASK_LEAKY, dz[l - 1], alpha=self.alpha,
-                   aux1=buf["acts"][l - 1])
+        ops.gemm16(dz[l], self.W16[l], R, K_in, N_out, 0, 0, EPI_MASK_BITS, dz[l - 1], alpha=self.alpha,
+                   aux1=buf["mask"][l - 1])
 
   def _weight_gradient(self, l, inp, dz, R, buf, with_bias_row):
     """dW[in,out] = inp^T[in,R] . dz[R,out]   (both operands MN-major, K = R).  With the ones column the GEMM has in+1

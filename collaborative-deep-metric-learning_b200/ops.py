@@ -7,7 +7,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import BF16, EPI_L2NORM, EPI_MASK_LEAKY, EPI_STORE_16, EPI_STORE_F32, F16, check, ptr, stream_ptr
+from ._lib import BF16, EPI_L2NORM, EPI_MASK_BITS, EPI_MASK_LEAKY, EPI_STORE_16, EPI_STORE_F32, F16, check, ptr, stream_ptr
 
 TORCH16 = {F16: torch.float16, BF16: torch.bfloat16}
 
@@ -90,12 +90,19 @@ def gemm16(A, B, M, N, K, a_mn_major, b_mn_major, epilogue, out, bias=None, alph
   used = ctypes.c_int(0)
   if ld_out is None:
     ld_out = out.stride(-2) if out.dim() >= 2 else N
+  # ld_aux1: row pitch of aux1, or -- STORE_16 with a sign-mask output in aux0 -- the mask's pitch in words
+  ld_aux1 = aux1.stride(0) if aux1 is not None else (aux0.stride(0) if (epilogue == EPI_STORE_16 and aux0 is not None) else 0)
   _count(1)
   check(_lib.load().cdml_gemm16(_ctx(A), ptr(A), int(a_mn_major), lda, ptr(B), int(b_mn_major), ldb, M, N, K,
                                 dtype16_of(A), epilogue, ptr(out), ld_out, ptr(bias), float(alpha), ptr(aux0),
-                                ptr(aux1), aux1.stride(0) if aux1 is not None else 0, num_splits, split_stride,
+                                ptr(aux1), ld_aux1, num_splits, split_stride,
                                 ctypes.byref(used), stream_ptr()))
   return used.value
+
+
+def sign_mask_buffer(rows, cols, device):
+  """Packed sign mask of a [rows, cols] activation (STORE_16's aux0 / MASK_BITS' aux1): int32 [ceil(cols/32), rows]."""
+  return torch.empty(((cols + 31) // 32, rows), dtype=torch.int32, device=device)
 
 
 def auto_splits(ref, M, N, K):
@@ -296,6 +303,14 @@ def mine_semihard(E16, E32, guid, B, margin, want_dist=True):
   check(_lib.load().cdml_mine_semihard(_ctx(E32), ptr(E16), E16.stride(0), dtype16_of(E16), ptr(E32), E32.stride(0),
                                        ptr(guid), B, D, float(margin), ptr(neg_row), ptr(d_an), stream_ptr()))
   return neg_row, d_an
+
+
+def mine_stats(ref):
+  """Diagnostics of the last mine_semihard on ref's device: {"rescans": re-scanned (anchor, 32-candidate chunk) pairs,
+  "mined": anchors that received a mined negative}.  Synchronises the current stream."""
+  out = (ctypes.c_int64 * 2)()
+  check(_lib.load().cdml_mine_last_stats(_ctx(ref), out, stream_ptr()))
+  return {"rescans": int(out[0]), "mined": int(out[1])}
 
 
 class FlatIndex(object):

@@ -232,6 +232,12 @@ class Trainer():
         raise RuntimeError("Train.run evaluater.features is None")
       eval_embeddings = predictor.run_features(self.evaluater.features, batch_size=10000, as_device=True)
       self.eval_dist = self.evaluater.mean_dist(eval_embeddings, self.evaluater.cowatches)
+      if engine.world > 1:
+        # early stopping and the best-checkpoint decision hang on this number: every rank uses rank 0's value, so the
+        # ranks leave the loop in the same step even if their copies ever differed in the last bit
+        t = torch.tensor([float(self.eval_dist)], dtype=torch.float64, device=engine.device)
+        torch.distributed.broadcast(t, src=0, group=self.pg)
+        self.eval_dist = float(t.item())
       if global_step_np <= check_stop_step:
         self.last_improve_num = self.total_eval_num
       elif self.eval_dist < self.best_eval_dist:
@@ -257,8 +263,11 @@ class Trainer():
     predictor = Prediction(sess=engine)
     fused = hasattr(self.pipe, "get_batch_indices")
     table16 = engine.prepare_table(self.pipe.device_features()) if fused else None
-    # single GPU: the whole step is one CUDA-graph launch; data-parallel steps (NCCL inside) are launched eagerly
-    replay = engine.capture_step(table16, self.batch_size, mine=self.mine_semihard) if (fused and engine.world == 1) else None
+    # the whole step is one CUDA-graph launch -- with N>1 ranks the NCCL all-reduce of the gradients is captured inside it
+    # (every rank captures and replays the same number of times: the reader serves whole rounds of `world` batches);
+    # CDML_DDP_GRAPH=0 keeps data-parallel steps eager
+    use_graph = fused and (engine.world == 1 or os.environ.get("CDML_DDP_GRAPH", "1") != "0")
+    replay = engine.capture_step(table16, self.batch_size, mine=self.mine_semihard) if use_graph else None
 
     world = engine.world
     global_step_np = 0

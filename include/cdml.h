@@ -56,10 +56,15 @@ int cdml_rows_normalize_cast(cdml_ctx* ctx, const float* in, int64_t n, int64_t 
  *      epilogue:
  *        0 STORE_F32  out fp32 [M,ld_out] = leaky(acc + bias)         (bias nullable; alpha=1 -> identity);
  *                     num_splits > 1 writes split-K partials at out + s*split_stride (reduce with cdml_sum_partials)
- *        1 STORE_16   out 16-bit [M,ld_out] = leaky(acc + bias)
+ *        1 STORE_16   out 16-bit [M,ld_out] = leaky(acc + bias); aux0 (nullable) = packed SIGN MASK out, uint32
+ *                     [ceil(N/32)][ld_aux1] (chunk-major, pitch ld_aux1 >= M words): bit j of word [c][m] is set iff
+ *                     acc + bias > 0 at column 32c+j -- all the backward pass needs of a leaky activation
  *        2 L2NORM     y = leaky(acc+bias); out fp32 = y*rsqrt(max(sum y^2,1e-12)); aux0 = rinv fp32 [M] (nullable);
  *                     aux1 = 16-bit copy [M,ld_aux1] (nullable).  Requires N <= 256.
  *        3 MASK_LEAKY out 16-bit = acc * (aux1[m,n] > 0 ? 1 : alpha)   (aux1 = 16-bit mask, ld_aux1)
+ *        4 MASK_BITS  out 16-bit = acc * (bit ? 1 : alpha), aux1 = the packed sign mask a STORE_16 forward wrote
+ *                     (same layout, pitch ld_aux1 words): the data gradient dz = (dy . W^T) * leaky'(z) of train.py:141-142
+ *                     reading 1 bit instead of 16 per element
  *      num_splits: <=0 lets the library choose (STORE_F32 only); *splits_used (nullable, host) reports it. */
 int cdml_gemm16(cdml_ctx* ctx, const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
                 int64_t M, int64_t N, int64_t K, int dtype16, int epilogue, void* out, int64_t ld_out,
@@ -136,6 +141,9 @@ int cdml_fill_column16(cdml_ctx* ctx, void* X16, int64_t rows, int64_t ld, int64
 int cdml_mine_semihard(cdml_ctx* ctx, const void* E16, int64_t ld16, int dtype16, const float* E32, int64_t ld32,
                        const int64_t* guid, int64_t B, int D, float margin, int32_t* neg_row, float* d_an,
                        void* stream);
+/* Diagnostics of the last cdml_mine_semihard on this context (synchronises `stream`): out2[0] = (anchor, 32-candidate
+ * chunk) pairs the selection epilogue had to re-scan, out2[1] = anchors that received a mined negative. */
+int cdml_mine_last_stats(cdml_ctx* ctx, int64_t* out2, void* stream);
 
 /* ---- K11-K13: exact flat KNN -- replaces faiss index.add + index.search (faiss_knn.py:116-128) with
  *      IndexFlatL2 / IndexFlatIP semantics.  X fp32 [N,d] (ldx), Q fp32 [nq,d] (ldq); metric 0 = L2 (squared,

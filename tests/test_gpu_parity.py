@@ -113,6 +113,160 @@ def test_tower_forward_embeddings_within_1e3(cd, dims, rows):
   assert rel_rows(e, want).max() < 1e-3                          # fp16 operands, fp32 accumulate: stated tolerance 1e-3
 
 
+@pytest.mark.parametrize("t16", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("R,N,K", [(1200, 5000, 256), (300, 200, 256), (2100, 333 * 8, 128)])
+def test_sign_mask_forward_and_mask_bits_data_gradient(cd, t16, R, N, K):
+  """The packed sign mask (STORE_16 aux0) is exactly `activation > 0`, bit for bit, and the MASK_BITS data gradient equals
+  the MASK_LEAKY one (which reads the 16-bit activation) bit for bit -- on the resident-B kernel (R >= 1024) and the
+  generic one, ragged N, both operand types."""
+  from cdml_b200._lib import EPI_MASK_BITS, EPI_MASK_LEAKY, EPI_STORE_16
+  gen = torch.Generator(device=cd.dev)
+  gen.manual_seed(R + N)
+  pad = lambda n: (n + 63) // 64 * 64
+  X = (torch.randn((R, pad(K)), generator=gen, device=cd.dev) * 0.3).to(t16)[:, :K]
+  W = (torch.randn((K, pad(N)), generator=gen, device=cd.dev) * 0.2).to(t16)[:, :N]          # [K,N]: MN-major B of the forward
+  bias = torch.randn((N,), generator=gen, device=cd.dev) * 0.1
+  H = torch.zeros((R, pad(N)), dtype=t16, device=cd.dev)[:, :N]
+  mask = cd.ops.sign_mask_buffer(R, N, cd.dev)
+  mask.fill_(-1)
+  cd.ops.gemm16(X, W, R, N, K, 0, 1, EPI_STORE_16, H, bias=bias, alpha=0.2, aux0=mask)
+  bits = (H > 0).cpu().numpy()
+  want = np.zeros(((N + 31) // 32, R), np.uint32)
+  for j in range(N):
+    want[j // 32] |= bits[:, j].astype(np.uint32) << np.uint32(j % 32)
+  got = mask.cpu().numpy().view(np.uint32)
+  tail = N % 32
+  if tail:                                                 # bits beyond N in the last word: columns that do not exist
+    got[-1] &= np.uint32((1 << tail) - 1)
+  assert np.array_equal(got, want)
+  # backward: dY [R,N] . W2^T with W2 = [N2,N] K-major... here: dz [R,K2] x Wb [N,K2]^T -> [R,N], masked by H's sign
+  K2 = 256
+  dz = (torch.randn((R, K2), generator=gen, device=cd.dev) * 0.1).to(t16)
+  Wb = (torch.randn((N, K2), generator=gen, device=cd.dev) * 0.1).to(t16)
+  out_a = torch.zeros((R, pad(N)), dtype=t16, device=cd.dev)[:, :N]
+  out_b = torch.zeros((R, pad(N)), dtype=t16, device=cd.dev)[:, :N]
+  cd.ops.gemm16(dz, Wb, R, N, K2, 0, 0, EPI_MASK_LEAKY, out_a, alpha=0.2, aux1=H)
+  cd.ops.gemm16(dz, Wb, R, N, K2, 0, 0, EPI_MASK_BITS, out_b, alpha=0.2, aux1=mask)
+  assert torch.equal(out_a, out_b)
+  ref = (dz.double() @ Wb.double().T) * torch.where(H > 0, 1.0, 0.2)
+  assert float((out_b.double() - ref).abs().max().item()) < 2e-2 * float(ref.abs().max().item())
+
+
+# bf16 operands (configs[2]; `--compute_dtype bf16`).  Stated tolerances, measured on B200 (profiles/r02_pytest_gpu.log):
+#   * against the bf16 PRECISION MODEL (float64 arithmetic, operands rounded to bf16 exactly where the kernels store them --
+#     "the reference computing in bf16"): median row error ~3e-5, worst row 1.0e-3 (VNet) / 1.5e-3 (4-layer wide tower).
+#     The worst rows are rounding-boundary flips: a stored activation the model rounds up and the fp32-accumulating tensor
+#     core rounds down differs by one bf16 ulp = 3.9e-3 of its value.  Gate: median <= 3e-4, max <= 2.5e-3.
+#   * bf16 itself against the unrounded float64 oracle is an 8-bit-significand property (2^-9 per operand, ~sqrt(layers)
+#     growth): measured 3.0-3.9e-3, gate 8e-3 -- OUTSIDE north_star's 1e-3, which bf16 operands cannot meet on this tower.
+#     fp16 operands (the default; TF32's significand) meet 1e-3 against float64 directly at the same tensor-core rate.
+BF16_VS_F64 = 8e-3
+BF16_VS_MODEL_MAX, BF16_VS_MODEL_MEDIAN = 2.5e-3, 3e-4
+
+
+@pytest.mark.parametrize("dims,rows", [([1500, 5000, 256], 3 * 171), ([2048, 2048, 2048, 2048, 256], 3 * 64)])
+def test_tower_forward_bf16_matches_precision_model(cd, dims, rows):
+  from cdml_b200 import _lib
+  feats = O.synth_features(rows, dims[0], 7)
+  params = O.init_tower(dims, seed=2, bias_init=0.1 if len(dims) > 3 else 0.0)
+  eng = cd.engine.TowerEngine(dims, device=cd.dev, init_params=params, dtype16=_lib.BF16)
+  e = eng.embed(dev_t(cd, feats)).cpu().numpy()
+  model = O.tower_grads_emulated16(feats, params, 0.8, "bf16")["l2_norm"]
+  want = O.tower_forward(feats, params)["l2_norm"]
+  assert np.allclose(np.linalg.norm(e, axis=1), 1.0, atol=1e-5)
+  print("bf16 forward %s: vs model %.2e, vs float64 %.2e" % (dims, rel_rows(e, model).max(), rel_rows(e, want).max()))
+  assert rel_rows(e, model).max() < BF16_VS_MODEL_MAX and np.median(rel_rows(e, model)) < BF16_VS_MODEL_MEDIAN
+  assert rel_rows(e, want).max() < BF16_VS_F64
+
+
+@pytest.mark.parametrize("dims,G,B", [([1500, 5000, 256], 2000, 512), ([2048, 2048, 2048, 2048, 256], 1500, 256)])
+def test_training_step_bf16_loss_gradients_and_adam(cd, dims, G, B):
+  """One optimisation step + a 6-step loss curve in bf16 against the bf16 precision model (and float64 at the stated
+  bf16 tolerance): the wide tower of configs[2] and the default tower with `dtype16=BF16`."""
+  from cdml_b200 import _lib
+  F, L = dims[0], len(dims) - 1
+  feats = O.synth_features(G, F, 0)
+  trip = O.synth_triplets(B, G, 1)
+  params = O.init_tower(dims, seed=2, bias_init=0.1 if L > 2 else 0.0)
+  eng = cd.engine.TowerEngine(dims, device=cd.dev, base_lr=1e-3, margin=0.8, init_params=params, dtype16=_lib.BF16)
+  table16 = eng.prepare_table(dev_t(cd, feats))
+  assert table16.dtype == torch.bfloat16
+  x = O.flatten_triplets(O.gather_rows(feats, trip))
+  tr16 = O.OracleTrainer(params, lr=1e-3, margin=0.8, emulate16="bf16")
+  tr64 = O.OracleTrainer(params, lr=1e-3, margin=0.8)
+  _, loss16, grads16 = tr16.loss_and_grads(x)
+  _, loss64, grads64 = tr64.loss_and_grads(x)
+  s = eng.train_step_indices(table16, dev_t(cd, trip)).cpu().numpy()
+  print("bf16 step %s: loss gpu %.6f model %.6f f64 %.6f" % (dims, s[0], loss16["hinge_loss"], loss64["hinge_loss"]))
+  assert abs(s[0] / loss16["hinge_loss"] - 1) < 1e-3
+  assert abs(s[0] / loss64["hinge_loss"] - 1) < BF16_VS_F64
+  for l in range(L):
+    gW, gb = eng.gW[l].cpu().numpy() / B, eng.gb[l].cpu().numpy() / B
+    rW, rb = _grad_rel(gW, grads16[l][0]), _grad_rel(gb, grads16[l][1])
+    dW_model, db_model = _grad_rel(grads16[l][0], grads64[l][0]), _grad_rel(grads16[l][1], grads64[l][1])
+    print("  layer %d: dW vs model %.2e, db vs model %.2e   (bf16 model vs float64: dW %.2e, db %.2e)" % (l, rW, rb, dW_model, db_model))
+    # rounding-boundary flips of stored activations / dz (a value the model rounds up and the kernel down, one bf16 ulp
+    # apart) are amplified like every forward error by the differences of nearly equal embeddings; the kernels are another
+    # realisation of the same rounding, gated (like the fusion towers) at 1e-2 + the model's own distance from float64
+    assert rW < 1e-2 + dW_model and rb < 1e-2 + db_model, (l, rW, rb, dW_model, db_model)
+  tr16.step(x)
+  lg, lm = [], []
+  for t in range(2, 7):
+    trip_t = O.synth_triplets(B, G, t)
+    lg.append(float(eng.train_step_indices(table16, dev_t(cd, trip_t))[0].item()))
+    lm.append(tr16.step(O.flatten_triplets(O.gather_rows(feats, trip_t)))[0])
+  print("  loss curve gpu", lg, "model", lm)
+  assert np.max(np.abs(np.array(lg) / np.array(lm) - 1)) < 2e-3
+  assert bool(torch.isfinite(eng.w).all().item())
+
+
+def test_adam_trajectory_matches_the_16bit_precision_model(cd):
+  """Ten Adam steps against the fp16 PRECISION MODEL's trajectory (same rounding points, float64 arithmetic): replaces the
+  former `max |W - W_oracle| < 2.5e-2` bound, which was the maximum possible travel.  Adam's update is sign-like, so a
+  weight whose gradient is at the noise floor may step the other way; against the precision model that floor is fp32
+  accumulation order + rounding-boundary flips, orders of magnitude below the float64-vs-fp16 distance."""
+  G, F, B = 1500, 1500, 384
+  dims = [F, 5000, 256]
+  feats = O.synth_features(G, F, 0)
+  params = O.init_tower(dims, seed=2)
+  eng = cd.engine.TowerEngine(dims, device=cd.dev, base_lr=1e-3, margin=0.8, init_params=params)
+  table16 = eng.prepare_table(dev_t(cd, feats))
+  tr = O.OracleTrainer(params, lr=1e-3, margin=0.8, emulate16="fp16")
+  for t in range(10):
+    trip = O.synth_triplets(B, G, 20 + t)
+    lg = float(eng.train_step_indices(table16, dev_t(cd, trip))[0].item())
+    lm = tr.step(O.flatten_triplets(O.gather_rows(feats, trip)))[0]
+    assert abs(lg / lm - 1) < 1e-3, (t, lg, lm)
+  for l, (W, b) in enumerate(eng.get_params()):
+    travel = tr.params[l][0] - params[l][0]
+    diff = W - tr.params[l][0]
+    rel = np.linalg.norm(diff) / np.linalg.norm(travel)
+    frac_off = float((np.abs(diff) > 1e-3).mean())                # more than ONE lr step apart after ten
+    print("adam trajectory layer %d: |dW| rel to travel %.3e, max %.3e, frac > 1 lr step %.2e" % (l, rel, np.abs(diff).max(), frac_off))
+    assert rel < 1e-1 and frac_off < 2e-2          # measured 1.9e-2 / 5.6e-4 (layer 1) and 5.4e-2 / 7.6e-3 (layer 2)
+    db_ = b - tr.params[l][1]
+    rel_b = np.linalg.norm(db_) / np.linalg.norm(tr.params[l][1] - params[l][1])
+    print("  bias: rel to travel %.3e, max %.3e, frac > 1 lr step %.2e" % (rel_b, np.abs(db_).max(), float((np.abs(db_) > 1e-3).mean())))
+    assert rel_b < 1.5e-1 and float((np.abs(db_) > 1e-3).mean()) < 2e-2
+
+
+def test_flat_knn_ids_equal_the_reference_show_knn_golden(cd, knn_golden):
+  """Ids pinned to the reference's OWN brute force (show_knn.calc_nn run by tests/golden/make_knn_golden.py): IndexFlatIP
+  and, the rows being unit vectors, IndexFlatL2 must return exactly those ids except inside fp32-noise ties."""
+  for name, (seed, N, d, nq, k, clustered) in knn_golden["cases"].items():
+    X = knn_golden["rows"](seed, N, d, clustered)
+    q = knn_golden["ids"][name + "_queries"]
+    want, gap = knn_golden["ids"][name + "_ids"], knn_golden["ids"][name + "_gap"]
+    clear = gap > 2e-6
+    for metric in ("IP", "L2"):
+      index = cd.ops.FlatIndex(dev_t(cd, X), metric)
+      D, I = index.search(dev_t(cd, X[q]), k)
+      I = I.cpu().numpy()
+      assert np.array_equal(I[clear], want[clear]), (name, metric, int((I[clear] != want[clear]).sum()))
+      assert all(set(I[i]) == set(want[i]) for i in np.flatnonzero(~clear) if gap[i] > 0), (name, metric)
+      index.close()
+
+
 def test_prediction_run_features_batches_and_tail(cd, tmp_path):
   dims = [1500, 5000, 256]
   params = O.init_tower(dims, seed=2)
@@ -457,14 +611,25 @@ def test_semihard_mining_matches_oracle_up_to_fp16_selection_noise(cd):
   dp = ((A - P) ** 2).sum(-1)
   exact = ((A - E[neg_row].astype(np.float64)) ** 2).sum(-1)
   assert np.allclose(d_an, exact, atol=1e-5)                     # reported distance is the exact fp32 one
+  # (1) against the PRECISION MODEL of the selection (same fp16-rounded operands, same d = 2 - 2s / dp / s_hi arithmetic):
+  #     the picks must be the same except where the two best candidates are closer than fp32 accumulation noise
+  model_row, model_d, model_gap = O.mine_semihard_emulated16(E, trip, margin, "fp16")
+  same16 = neg_row == model_row
+  assert same16.mean() >= 0.99, same16.mean()
+  for i in np.nonzero(~same16)[0]:
+    # fp32 accumulation (tensor core vs float64; ~1e-6 on a K=256 dot product near 1, doubled by d = 2 - 2s): near-ties
+    # of the selection distance, or a candidate within that noise of the d > dp boundary
+    sel = max(2.0 - 2.0 * float(np.dot(E16.cpu().numpy()[3 * i].astype(np.float64), E16.cpu().numpy()[neg_row[i]].astype(np.float64))), 0.0)
+    assert model_gap[i] < 2e-5 or abs(sel - model_d[i]) < 2e-5 or abs(model_d[i] - dp[i]) < 2e-5 or abs(sel - dp[i]) < 2e-5, \
+        (i, neg_row[i], model_row[i], sel, model_d[i], model_gap[i], dp[i])
+  # (2) against the float64 definition on unrounded embeddings: a different pick is only acceptable as a near-tie of the
+  #     oracle's pick within the fp16 operand rounding of the selection distances, or at a category boundary
   same = neg_row == want_row
-  assert same.mean() > 0.70                                      # candidate spacing ~1e-3 vs fp16 selection noise ~3e-4
-  tol = 4e-3                                                     # fp16 operand rounding of the selection distances
+  tol = 4e-3
   for i in np.nonzero(~same)[0]:
     r = neg_row[i]
     g = trip[r // 3, r % 3]
     assert r == 3 * i + 2 or (r % 3 != 0 and g != trip[i, 0] and g != trip[i, 1])
-    # a different pick is only acceptable as a near-tie of the oracle's pick or at a category boundary
     near_tie = abs(exact[i] - want_d[i]) < tol
     at_boundary = min(abs(exact[i] - dp[i]), abs(exact[i] - dp[i] - margin), abs(want_d[i] - dp[i]),
                       abs(want_d[i] - dp[i] - margin)) < tol
@@ -515,6 +680,7 @@ def test_full_size_training_step_batch_65536_properties(cd):
   G, F, B = 200000, 1500, 65536
   dims = [F, 5000, 256]
   eng = cd.engine.TowerEngine(dims, device=cd.dev, base_lr=1e-3, margin=0.8, seed=2)
+  eng_params0 = eng.get_params()                                    # before the step: what the forward pass used
   gen = torch.Generator(device=cd.dev)
   gen.manual_seed(7)
   table16 = torch.empty((G, eng.F_pad), dtype=torch.float16, device=cd.dev)
@@ -548,6 +714,44 @@ def test_full_size_training_step_batch_65536_properties(cd):
   assert float(mined.float().mean().item()) > 0.9
   assert bool((d_an[mined] > pos[mined] - 2e-2).all().item())                            # d(a,n) > d(a,p) up to the fp16 selection noise
   assert bool(torch.isfinite(eng.w).all().item()) and float((eng.w - w0).abs().max().item()) <= 1.01e-3   # one Adam step
+  # oracle spot check at full size (like the 1 M KNN / de-similarity tests): 256 sampled triplets -- their 768 embeddings
+  # against the float64 oracle of the forward pass on the same table rows (<= 1e-3), the loss of the sample with the
+  # kernel's own mined negatives, and the mined pick of those anchors against the precision model of the selection
+  rs = np.random.RandomState(3)
+  samp = np.sort(rs.choice(B, 256, replace=False))
+  rows = (3 * samp[:, None] + np.arange(3)[None, :]).reshape(-1)
+  x_s = x16[torch.as_tensor(rows, device=cd.dev)][:, :F].float().cpu().numpy().astype(np.float64)    # normalised fp16 table rows
+  init = eng_params0
+  fwd = O.tower_forward(x_s, init)["l2_norm"]           # the rows are unit to fp16 rounding; tower_forward re-normalises
+  e_s = e[torch.as_tensor(rows, device=cd.dev)].cpu().numpy()
+  assert rel_rows(e_s, fwd).max() < 1e-3
+  nr = neg_row.cpu().numpy()
+  E_all = e.cpu().numpy()
+  a_, p_, n_ = E_all[3 * samp], E_all[3 * samp + 1], E_all[nr[samp]]
+  hin_s = np.maximum(((a_ - p_) ** 2).sum(-1) - ((a_ - n_) ** 2).sum(-1) + 0.8, 0.0)
+  assert np.allclose(hin.cpu().numpy()[samp], hin_s, atol=2e-5)
+  fa, fp_, fn_ = fwd[0::3], fwd[1::3], O.tower_forward(x16[torch.as_tensor(nr[samp], device=cd.dev).long()][:, :F].float().cpu().numpy().astype(np.float64), init)["l2_norm"]
+  loss_s = np.maximum(((fa - fp_) ** 2).sum(-1) - ((fa - fn_) ** 2).sum(-1) + 0.8, 0.0).mean()
+  assert abs(hin_s.mean() / loss_s - 1) < 1e-3, (hin_s.mean(), loss_s)
+  e16_np = e16.float().cpu().numpy()
+  trip_np = idx.cpu().numpy()
+  cand = np.concatenate([3 * np.arange(B) + 1, 3 * np.arange(B) + 2])
+  cg = np.concatenate([trip_np[:, 1], trip_np[:, 2]])
+  agree = 0
+  C64 = e16_np[cand].astype(np.float64)
+  for i in samp[:64]:
+    sc = (C64 @ e16_np[3 * i].astype(np.float64)).astype(np.float32)
+    dpi = np.float32(((E_all[3 * i] - E_all[3 * i + 1]) ** 2).sum(dtype=np.float32))
+    d = np.maximum(np.float32(2) - np.float32(2) * sc, np.float32(0))
+    ok = (sc < np.float32(1) - np.float32(0.5) * dpi) & (d > dpi) & (cg != trip_np[i, 0]) & (cg != trip_np[i, 1])
+    dm = np.where(ok, d, np.inf)
+    best = cand[np.flatnonzero(dm == dm.min())].min()
+    # the tensor core's fp32 accumulation of a K=256 dot product near 1.0 differs from the float64 sum by up to ~1e-6
+    # (d = 2 - 2s doubles it); in this structureless regime the candidates are 1e-8 apart, so the pick itself is noise --
+    # what is checked is that the kernel's pick is within that accumulation noise of the model's minimum
+    near = abs(float(d[np.flatnonzero(cand == nr[i])[0]]) - float(dm.min())) < 2e-5
+    agree += int(best == nr[i] or near)
+  assert agree == 64, agree
 
 
 # ---------------------------------------------------------------- fusion towers (models.py:65-243)

@@ -33,6 +33,10 @@ ap.add_argument("--lr", type=float, default=1e-4, help="Adam base learning rate 
 ap.add_argument("--no-desim", action="store_true", help="skip the raw-feature KNN + de-similarity stage")
 ap.add_argument("--feat-k", type=int, default=26, help="desim_nearest_num (faiss_knn.py:46)")
 ap.add_argument("--mine", action="store_true", help="in-batch semi-hard mining (default: the reference's random negatives)")
+ap.add_argument("--signal", type=float, default=1.0, help="weight of the cluster centre in a feature row (row = signal * centre + "
+                "noise_weight * U[0,1)); 1.0 / 0.25 = the well-separated default, 0.3 / 1.0 = clusters the tower has to learn")
+ap.add_argument("--noise", type=float, default=0.25)
+ap.add_argument("--clusters", type=int, default=1000)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.cuda.set_device(0)
@@ -52,11 +56,12 @@ t0 = time.time()
 eng = engine.TowerEngine([F, 5000, 256], device=dev, base_lr=args.lr, margin=0.8)
 table16 = torch.empty((G, eng.F_pad), dtype=eng.t16, device=dev)
 feats32 = None if args.no_desim else torch.empty((G, F), dtype=torch.float32, device=dev)   # features.npy of predict.py:150
-centres = torch.rand((1000, F), generator=gen, device=dev)
-cluster = torch.randint(0, 1000, (G,), generator=gen, device=dev)
+NC = args.clusters
+centres = torch.rand((NC, F), generator=gen, device=dev)
+cluster = torch.randint(0, NC, (G,), generator=gen, device=dev)
 for s in range(0, G, 65536):
   rows = min(65536, G - s)
-  slab = centres[cluster[s:s + rows]] + 0.25 * torch.rand((rows, F), generator=gen, device=dev)
+  slab = args.signal * centres[cluster[s:s + rows]] + args.noise * torch.rand((rows, F), generator=gen, device=dev)
   eng.prepare_table(slab, out=table16[s:s + rows])
   if feats32 is not None:
     feats32[s:s + rows] = slab
@@ -67,8 +72,30 @@ t0 = time.time()
 steps = max(1, args.triplets // B)
 replay = eng.capture_step(table16, B, mine=args.mine)
 order = torch.argsort(cluster)
-start = torch.searchsorted(cluster[order], torch.arange(1001, device=dev))
+start = torch.searchsorted(cluster[order], torch.arange(NC + 1, device=dev))
 losses = []
+
+
+def same_cluster_pairs(n):
+  a = torch.randint(0, G, (n,), generator=gen, device=dev)
+  c = cluster[a]
+  span = (start[c + 1] - start[c]).clamp(min=1)
+  return a, order[start[c] + (torch.rand((n,), generator=gen, device=dev) * span).long() % span]
+
+
+def eval_dists():
+  """Evaluation.mean_dist (evaluate.py:57-73) of 20 000 held-out cowatch pairs next to 20 000 random pairs: training must
+  shrink the first relative to the second (a collapse shrinks both)."""
+  a, p = same_cluster_pairs(20000)
+  r = torch.randint(0, G, (20000,), generator=gen, device=dev)
+  rows = torch.cat([a, p, r])
+  e = eng.forward_rows(table16[rows], rows.numel())["e"]
+  pairs_pos = torch.stack([torch.arange(20000, device=dev), torch.arange(20000, 40000, device=dev)], 1)
+  pairs_rnd = torch.stack([torch.arange(20000, device=dev), torch.arange(40000, 60000, device=dev)], 1)
+  return float(ops.mean_pair_dist(e, pairs_pos).item()), float(ops.mean_pair_dist(e, pairs_rnd).item())
+
+
+eval_before = eval_dists()
 for i in range(steps):
   a = torch.randint(0, G, (B,), generator=gen, device=dev)
   c = cluster[a]
@@ -79,6 +106,7 @@ for i in range(steps):
   if i % 16 == 0 or i == steps - 1:
     losses.append(float(st[0].item()))
 tick("train_s", t0)
+eval_after = eval_dists()
 
 # ---- stage 2: embed every guid (Prediction.run_features on the live engine, batches of 100 000 like predict.py:42)
 t0 = time.time()
@@ -139,7 +167,9 @@ faiss_knn.write_knn(out_dir, split_num=10, D=D[:R].cpu().numpy(), I=I[:R].cpu().
 tick("write_s", t0)
 print(json.dumps({"guids": G, "triplets": steps * B, "steps": steps, "knn_k": args.knn_k, "seconds": t,
                   "train_triplets_per_s": steps * B / t["train_s"], "embed_rows_per_s": G / t["embed_s"],
-                  "knn_queries_per_s": G / t["knn_s"], "loss_first_last": [losses[0], losses[-1]],
+                  "knn_queries_per_s": G / t["knn_s"], "loss_first_last": [losses[0], losses[-1]], "loss_curve": [round(x, 5) for x in losses],
+                  "eval_cowatch_vs_random_pair_dist_before": eval_before, "eval_cowatch_vs_random_pair_dist_after": eval_after,
+                  "features": {"signal": args.signal, "noise": args.noise, "clusters": NC, "lr": args.lr},
                   "top5_same_cluster": same_cluster, "self_is_first_neighbour": self_first,
                   "knn_fallback_queries_last_block": stats["fallback_queries"], "mining": bool(args.mine), "desim": desim_info,
                   "write_rows": R, "write_rows_per_s": R / t["write_s"] if R else None, "out_dir": out_dir}))

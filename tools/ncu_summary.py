@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 rep, how = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "")
+digest = sys.argv[3] if len(sys.argv) > 3 else None      # `python __graft_entry__.py --digest` on the box that captured
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -50,5 +51,5 @@ for r in rows[2:]:
               "sm_clock_ghz": val(r, "smsp__cycles_elapsed.avg.per_second",
                                   {"ghz": 1.0, "mhz": 1e-3, "hz": 1e-9}.get(units[col["smsp__cycles_elapsed.avg.per_second"]].lower(), 1.0)
                                   if "smsp__cycles_elapsed.avg.per_second" in col else 1.0)})
-json.dump({"source": how, "note": "per-launch values; ncu replays each kernel cold-cache and serialised: compare shares, "
+json.dump({"source": how, "csrc_digest": digest, "note": "per-launch values; ncu replays each kernel cold-cache and serialised: compare shares, "
            "not absolutes. GB = 1e9 bytes", "kernels": out}, sys.stdout, indent=1)
