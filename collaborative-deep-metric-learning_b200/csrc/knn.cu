@@ -296,7 +296,7 @@ constexpr int kSelectBits = 20;
 template <int kPer, bool kDual>
 __global__ void __launch_bounds__(kRefineThreads)
 knn_kth_kernel(const float* __restrict__ gmax, int64_t ldg, int G, int k, int k2, const float* __restrict__ qss,
-               float slack_scale, float slack_abs, float* __restrict__ thr, float* __restrict__ thr2) {
+               float slack_scale, float slack_abs, float* __restrict__ thr, float* __restrict__ thr2, float sign2) {
   __shared__ int sh[kRefineThreads / 32];
   const int q = blockIdx.x;
   const float* g = gmax + static_cast<int64_t>(q) * ldg;
@@ -319,17 +319,95 @@ knn_kth_kernel(const float* __restrict__ gmax, int64_t ldg, int G, int k, int k2
   if (threadIdx.x == 0) {
     const float slack = slack_scale * sqrtf(qss[q]) + slack_abs;
     thr[q] = T > f2key(neg_inf()) ? key2f(T) - slack : neg_inf();
-    if (kDual) thr2[q] = T2 > f2key(neg_inf()) ? key2f(T2) - slack : neg_inf();
+    if (kDual) thr2[q] = sign2 * (T2 > f2key(neg_inf()) ? key2f(T2) - slack : neg_inf());
   }
+}
+
+// Same selection, one WARP per query (G <= 1024 group maxima: 32 keys per lane in registers, counts by one
+// __reduce_add_sync per bit).  A block per query spends its time in 2 x 20 __syncthreads for a few hundred keys: on an
+// 8-way sharded 1M index (488 groups per query) the block version took 1.02 ms per 65536 queries, 12% of the shard's time.
+template <bool kDual>
+__global__ void __launch_bounds__(256)
+knn_kth_warp_kernel(const float* __restrict__ gmax, int64_t ldg, int G, int k, int k2, const float* __restrict__ qss,
+                    int64_t nq, float slack_scale, float slack_abs, float* __restrict__ thr, float* __restrict__ thr2,
+                    float sign2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  const float* g = gmax + q * ldg;
+  uint32_t keys[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int j = lane + 32 * i;
+    keys[i] = j < G ? f2key(g[j]) : 0u;
+  }
+  uint32_t T = 0, T2 = 0;
+  for (int bit = 31; bit >= 32 - kSelectBits; --bit) {
+    const uint32_t cand = T | (1u << bit), cand2 = T2 | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) c += (keys[i] >= cand ? 1 : 0) + (kDual && keys[i] >= cand2 ? 65536 : 0);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((c & 0xffff) >= k) T = cand;
+    if (kDual && (c >> 16) >= k2) T2 = cand2;
+  }
+  if (lane == 0) {
+    const float slack = slack_scale * sqrtf(qss[q]) + slack_abs;
+    thr[q] = T > f2key(neg_inf()) ? key2f(T) - slack : neg_inf();
+    if (kDual) thr2[q] = sign2 * (T2 > f2key(neg_inf()) ? key2f(T2) - slack : neg_inf());
+  }
+}
+
+// Row-sharded index, after the collect pass: per query the k-th and the k_part-th best APPROXIMATE score among this
+// shard's nominees (truncated bisection like above; a bound may always be lower).  pair[0][q] = k-th (-inf when the
+// shard nominated fewer than k), pair[1][q] = -(k_part-th) (+inf when fewer than k_part): ONE all-reduce(MAX) of the pair
+// over the shards then yields max_s(k-th) and min_s(k_part-th), both lower bounds of the GLOBAL k-th best approximate
+// score (k_part = ceil(k / shards): if every shard holds k_part nominees above t, the index holds k).  The refine pass
+// prunes against that global bound instead of its local k-th: 8 shards then re-rank ~25 rows per query each, not ~105.
+__global__ void __launch_bounds__(256)
+knn_nominee_kth_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ cnt, int cap, int k, int k2,
+                       int64_t nq, float* __restrict__ pair) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  const int n = cnt[q];
+  float a = neg_inf(), b = neg_inf();
+  if (n <= cap && n >= min(k, k2)) {
+    const float* v = cand_val + q * cap;
+    uint32_t keys[8];
+    const bool in_regs = n <= 256;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) keys[i] = (in_regs && lane + 32 * i < n) ? f2key(v[lane + 32 * i]) : 0u;
+    uint32_t T = 0, T2 = 0;
+    for (int bit = 31; bit >= 32 - kSelectBits; --bit) {
+      const uint32_t cand = T | (1u << bit), cand2 = T2 | (1u << bit);
+      int c = 0;
+      if (in_regs) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c += (keys[i] >= cand ? 1 : 0) + (keys[i] >= cand2 ? 65536 : 0);
+      } else {
+        for (int i = lane; i < n; i += 32) {
+          const uint32_t key = f2key(v[i]);
+          c += (key >= cand ? 1 : 0) + (key >= cand2 ? 65536 : 0);
+        }
+      }
+      c = __reduce_add_sync(0xffffffffu, c);
+      if ((c & 0xffff) >= k) T = cand;
+      if ((c >> 16) >= k2) T2 = cand2;
+    }
+    if (n >= k && T > f2key(neg_inf())) a = key2f(T);
+    if (n >= k2 && T2 > f2key(neg_inf())) b = key2f(T2);
+  }
+  if (lane == 0) pair[q] = a, pair[nq + q] = -b;
 }
 
 // Collection bound from bounds agreed across index shards: thr = max(full, part) - slack(q)  (-inf when no shard had one)
 __global__ void knn_thr_combine_kernel(const float* __restrict__ full, const float* __restrict__ part,
                                        const float* __restrict__ qss, int64_t n, float slack_scale, float slack_abs,
-                                       float* __restrict__ thr) {
+                                       float* __restrict__ thr, float part_sign) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float b = fmaxf(full[i], part[i]);
+  const float b = fmaxf(full[i], part_sign * part[i]);
   thr[i] = b > neg_inf() ? b - (slack_scale * sqrtf(qss[i]) + slack_abs) : neg_inf();
 }
 
@@ -340,13 +418,15 @@ knn_refine_kernel(const float* __restrict__ Q, int64_t ldq, int d, const float* 
                   const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_val,
                   const int32_t* __restrict__ cnt, int cap, int k, int metric, float slack_scale, float slack_abs,
                   int64_t id_offset, float* __restrict__ D, int64_t* __restrict__ I, int64_t out_ld,
-                  int32_t* __restrict__ overflow, int n_all) {
+                  int32_t* __restrict__ overflow, int n_all, const float* __restrict__ prune_pair, int64_t prune_ld,
+                  const int32_t* __restrict__ handled) {
   __shared__ unsigned long long kept[kKeepCap];
   __shared__ int sh[kRefineThreads / 32];
   __shared__ uint32_t shu[2 * (kRefineThreads / 32)];
   __shared__ int n_keep;
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
+  if (handled != nullptr && handled[q] != 0) return;   // knn_refine_warp_kernel already wrote this query's list
   const int n = n_all > 0 ? 0 : cnt[q];   // n_all > 0: tiny database, every row is re-ranked exactly (no scan, no prune)
   if (n > cap) {  // too many nominees (mass ties): exact fallback handles this query
     if (tid == 0) overflow[q] = 1;
@@ -391,7 +471,13 @@ knn_refine_kernel(const float* __restrict__ Q, int64_t ldq, int d, const float* 
     __syncthreads();
   }
   const float slack = slack_scale * sqrtf(qss[q]) + slack_abs;
-  const uint32_t keep_key = n > k ? f2key(key2f(T) - slack) : 0u;
+  uint32_t keep_key = n > k ? f2key(key2f(T) - slack) : 0u;
+  if (prune_pair != nullptr) {
+    // row-sharded index: lower bound of the GLOBAL k-th best approximate score agreed across the shards (max_s of the
+    // shards' k-th best nominee, min_s of their ceil(k/W)-th best) -- a row of the true top-k scores within 2*eps of it
+    const float tg = fmaxf(prune_pair[q], -prune_pair[prune_ld + q]);
+    if (tg > neg_inf()) keep_key = max(keep_key, f2key(tg - slack));
+  }
 #pragma unroll
   for (int t = 0; t < kPer; ++t) {
     if (tid + t * kRefineThreads < n && keys[t] >= keep_key) {
@@ -490,6 +576,104 @@ knn_refine_kernel(const float* __restrict__ Q, int64_t ldq, int d, const float* 
     D[static_cast<int64_t>(q) * out_ld + i] = metric == 0 ? pos_inf() : neg_inf();
     I[static_cast<int64_t>(q) * out_ld + i] = -1;
   }
+}
+
+// Row-sharded index: a shard's query usually has a few hundred nominees of which a few dozen survive the GLOBAL prune bound.
+// One warp per query then does what the block kernel above does with 256 threads and ~40 block barriers: nominees in
+// registers (8 per lane), survivors compacted by ballot, exact fp32 re-rank four rows at a time, rank sort, emit.  Queries
+// it does not take (no global bound, > 256 nominees, > kWarpKeep survivors) are left to the block kernel via handled[q] = 0.
+constexpr int kWarpNom = 256;
+constexpr int kWarpKeep = 96;
+__global__ void __launch_bounds__(256)
+knn_refine_warp_kernel(const float* __restrict__ Q, int64_t ldq, int d, const float* __restrict__ qss,
+                       const float* __restrict__ X, int64_t ldx, const float* __restrict__ xss,
+                       const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_val,
+                       const int32_t* __restrict__ cnt, int cap, int k, int metric, float slack_scale, float slack_abs,
+                       int64_t id_offset, float* __restrict__ D, int64_t* __restrict__ I, int64_t out_ld,
+                       const float* __restrict__ prune_pair, int64_t prune_ld, int64_t nq, int32_t* __restrict__ handled) {
+  __shared__ unsigned long long kept_all[8][kWarpKeep];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (q >= nq) return;
+  unsigned long long* kept = kept_all[warp];
+  const int n = cnt[q];
+  const float tg = fmaxf(prune_pair[q], -prune_pair[prune_ld + q]);
+  if (n > kWarpNom || n > cap || !(tg > neg_inf())) {
+    if (lane == 0) handled[q] = 0;
+    return;
+  }
+  const float slack = slack_scale * sqrtf(qss[q]) + slack_abs;
+  const uint32_t keep_key = f2key(tg - slack);
+  int nk = 0;
+#pragma unroll
+  for (int t = 0; t < kWarpNom / 32; ++t) {
+    const int i = lane + 32 * t;
+    const bool pass = i < n && f2key(cand_val[q * cap + i]) >= keep_key;
+    const unsigned int m = __ballot_sync(0xffffffffu, pass);
+    const int pos = nk + __popc(m & ((1u << lane) - 1u));
+    if (pass && pos < kWarpKeep) kept[pos] = static_cast<unsigned long long>(static_cast<uint32_t>(cand_idx[q * cap + i]));
+    nk += __popc(m);
+  }
+  if (nk > kWarpKeep) {
+    if (lane == 0) handled[q] = 0;
+    return;
+  }
+  __syncwarp();
+  const float* qv = Q + q * ldq;
+  const float qn = qss[q];
+  const bool vec = (d & 3) == 0 && (ldx & 3) == 0 && (ldq & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Q)) & 15) == 0;
+  for (int i0 = 0; i0 < nk; i0 += 4) {
+    uint32_t id[4];
+    float dot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) id[c] = static_cast<uint32_t>(kept[min(i0 + c, nk - 1)]);
+    if (vec) {
+      for (int j = lane * 4; j < d; j += 128) {
+        const float4 qq = __ldg(reinterpret_cast<const float4*>(qv + j));
+        float4 xx[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xx[c] = __ldg(reinterpret_cast<const float4*>(X + static_cast<int64_t>(id[c]) * ldx + j));
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dot[c] = fmaf(qq.x, xx[c].x, fmaf(qq.y, xx[c].y, fmaf(qq.z, xx[c].z, fmaf(qq.w, xx[c].w, dot[c]))));
+      }
+    } else {
+      for (int j = lane; j < d; j += 32) {
+        const float qj = qv[j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dot[c] = fmaf(qj, X[static_cast<int64_t>(id[c]) * ldx + j], dot[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot[c] += __shfl_xor_sync(0xffffffffu, dot[c], o);
+    }
+    __syncwarp();
+    if (lane < 4 && i0 + lane < nk) {
+      const float dsel = lane == 0 ? dot[0] : lane == 1 ? dot[1] : lane == 2 ? dot[2] : dot[3];
+      const uint32_t isel = lane == 0 ? id[0] : lane == 1 ? id[1] : lane == 2 ? id[2] : id[3];
+      const float key = metric == 0 ? fmaxf(qn + xss[isel] - 2.f * dsel, 0.f) : -dsel;
+      kept[i0 + lane] = (static_cast<unsigned long long>(f2key(key)) << 32) | isel;
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < nk; i += 32) {      // rank sort on (distance key, id): the keys are distinct
+    const unsigned long long e = kept[i];
+    int rank = 0;
+    for (int j = 0; j < nk; ++j) rank += kept[j] < e ? 1 : 0;
+    if (rank < k) {
+      const float key = key2f(static_cast<uint32_t>(e >> 32));
+      D[q * out_ld + rank] = metric == 0 ? key : -key;
+      I[q * out_ld + rank] = static_cast<int64_t>(static_cast<uint32_t>(e)) + id_offset;
+    }
+  }
+  for (int i = nk + lane; i < k; i += 32) {
+    D[q * out_ld + i] = metric == 0 ? pos_inf() : neg_inf();
+    I[q * out_ld + i] = -1;
+  }
+  if (lane == 0) handled[q] = 1;
 }
 
 // ---- exact fallback: queries whose candidate list overflowed (dense near-tie bands, e.g. tight clusters) ----
@@ -715,6 +899,81 @@ knn_merge_kernel(const float* __restrict__ Dg, const int64_t* __restrict__ Ig, i
   }
 }
 
+// (D, I) lists -> one sortable 64-bit record per entry: (order-preserving distance key << 32) | global id; padding
+// (id < 0) -> ~0.  One record array makes the shard exchange ONE all-to-all of 8 bytes per entry instead of two of 4 + 8.
+__global__ void knn_pack_kernel(const float* __restrict__ D, const int64_t* __restrict__ I, int64_t n, int metric,
+                                unsigned long long* __restrict__ rec) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t id = I[i];
+  const float dv = D[i];
+  rec[i] = id < 0 ? ~0ull : ((static_cast<unsigned long long>(f2key(metric == 0 ? dv : -dv)) << 32) | static_cast<uint32_t>(id));
+}
+
+__global__ void knn_unpack_kernel(const unsigned long long* __restrict__ rec, int64_t n, int metric, float* __restrict__ D,
+                                  int64_t* __restrict__ I) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long e = rec[i];
+  if (e == ~0ull) {
+    D[i] = metric == 0 ? pos_inf() : neg_inf();
+    I[i] = -1;
+  } else {
+    const float key = key2f(static_cast<uint32_t>(e >> 32));
+    D[i] = metric == 0 ? key : -key;
+    I[i] = static_cast<int64_t>(static_cast<uint32_t>(e));
+  }
+}
+
+// k-way merge of G sorted record lists per query, one WARP per query: the lists are staged in shared memory with
+// coalesced loads, lane g holds the head of list g, every round takes the warp-minimum head (records are distinct: the
+// id is part of the key) and advances that list.  G <= 32.  [G, nq, k] records -> D, I [nq, k].
+__global__ void __launch_bounds__(256)
+knn_merge_packed_kernel(const unsigned long long* __restrict__ rec, int G, int64_t nq, int k, int metric, int warps,
+                        float* __restrict__ D, int64_t* __restrict__ I, unsigned long long* __restrict__ rec_out) {
+  extern __shared__ unsigned long long ms[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= warps) return;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * warps + warp;
+  if (q >= nq) return;
+  unsigned long long* mine = ms + static_cast<size_t>(warp) * G * k;
+  for (int g = 0; g < G; ++g)
+    for (int j = lane; j < k; j += 32) mine[g * k + j] = rec[(static_cast<int64_t>(g) * nq + q) * k + j];
+  __syncwarp();
+  int pos = 0;
+  unsigned long long head = lane < G ? mine[lane * k] : ~0ull;
+  for (int i = 0; i < k; ++i) {
+    const uint32_t hi = static_cast<uint32_t>(head >> 32);
+    const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+    const uint32_t lo = hi == mhi ? static_cast<uint32_t>(head) : 0xffffffffu;
+    const uint32_t mlo = __reduce_min_sync(0xffffffffu, lo);
+    const bool win = hi == mhi && static_cast<uint32_t>(head) == mlo && head != ~0ull;
+    const unsigned int who = __ballot_sync(0xffffffffu, win);
+    if (who == 0u) {          // every list exhausted: pad like faiss
+      if (lane == 0) {
+        if (rec_out != nullptr) {
+          rec_out[q * k + i] = ~0ull;
+        } else {
+          D[q * k + i] = metric == 0 ? pos_inf() : neg_inf();
+          I[q * k + i] = -1;
+        }
+      }
+      continue;
+    }
+    if (lane == __ffs(who) - 1) {
+      if (rec_out != nullptr) {   // merged list stays packed (one all-gather of 8-byte records instead of two of 4 + 8)
+        rec_out[q * k + i] = head;
+      } else {
+        const float key = key2f(mhi);
+        D[q * k + i] = metric == 0 ? key : -key;
+        I[q * k + i] = static_cast<int64_t>(mlo);
+      }
+      ++pos;
+      head = pos < k ? mine[lane * k + pos] : ~0ull;
+    }
+  }
+}
+
 template <typename T>
 static int dev_alloc(T** p, size_t n) {
   CDML_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
@@ -741,7 +1000,7 @@ struct cdml_index {
   int64_t qc;
   uint16_t* q16;
   float *qss, *gmax, *thr, *cand_val;
-  int32_t *cand_idx, *cnt, *overflow;
+  int32_t *cand_idx, *cnt, *overflow, *handled;
   uint4* log;          // [num_sms * 8, log_cap] warp-private candidate logs of pass B
   int32_t* log_count;  // [num_sms * 8] + 1 overflow word
   unsigned int log_cap;
@@ -751,14 +1010,19 @@ struct cdml_index {
   int64_t h_cap;
   int64_t ldg;
   int64_t stats[2];
+  // row-sharded protocol: (D, I) of one chunk before they are packed into records
+  float* Dtmp;
+  int64_t* Itmp;
+  int64_t tmp_cap;
 };
 
 static void index_free(cdml_index* ix) {
   if (ix == nullptr) return;
   cudaFree(ix->x32), cudaFree(ix->xss), cudaFree(ix->h), cudaFree(ix->x16), cudaFree(ix->xs16), cudaFree(ix->hs);
   cudaFree(ix->q16), cudaFree(ix->qss), cudaFree(ix->gmax), cudaFree(ix->thr), cudaFree(ix->cand_val);
-  cudaFree(ix->cand_idx), cudaFree(ix->cnt), cudaFree(ix->overflow);
+  cudaFree(ix->cand_idx), cudaFree(ix->cnt), cudaFree(ix->overflow), cudaFree(ix->handled);
   cudaFree(ix->log), cudaFree(ix->log_count);
+  cudaFree(ix->Dtmp), cudaFree(ix->Itmp);
   cudaFreeHost(ix->h_cnt), cudaFreeHost(ix->h_ovf), cudaFreeHost(ix->h_qss), cudaFreeHost(ix->h_logovf);
   delete ix;
 }
@@ -833,6 +1097,8 @@ static int ensure_workspace(cdml_index* ix, int64_t qc) {
   if (ix->qc >= qc) return 0;
   cudaFree(ix->q16), cudaFree(ix->qss), cudaFree(ix->gmax), cudaFree(ix->thr), cudaFree(ix->cand_val);
   cudaFree(ix->cand_idx), cudaFree(ix->cnt), cudaFree(ix->overflow), cudaFree(ix->log), cudaFree(ix->log_count);
+  cudaFree(ix->handled);
+  ix->handled = nullptr;
   ix->log = nullptr, ix->log_count = nullptr;
   ix->q16 = nullptr, ix->qss = ix->gmax = ix->thr = ix->cand_val = nullptr, ix->cand_idx = ix->cnt = ix->overflow = nullptr;
   ix->qc = 0;
@@ -846,6 +1112,7 @@ static int ensure_workspace(cdml_index* ix, int64_t qc) {
   rc |= dev_alloc(&ix->cand_idx, static_cast<size_t>(qc) * kCandCap);
   rc |= dev_alloc(&ix->cnt, qc);
   rc |= dev_alloc(&ix->overflow, qc);
+  rc |= dev_alloc(&ix->handled, qc);
   // log capacity: 2048 nominees per query on average, never less than 16K entries per epilogue warp
   const int sms = ix->ctx->num_sms;
   ix->log_cap = static_cast<unsigned int>(std::max<int64_t>(qc * 2048 / (sms * kKnnLogsPerCta), 16384));
@@ -860,11 +1127,16 @@ static int ensure_workspace(cdml_index* ix, int64_t qc) {
 //   search          (ext_full == nullptr, out_full == nullptr): bound pass + collect + refine, self-contained;
 //   bounds only     (out_full != nullptr): bound pass; writes the raw k_full-th / k_part-th best sampled scores per query;
 //   bounded search  (ext_full != nullptr): skips the bound pass, collects above max(ext_full, ext_part) - slack.
+//   row-sharded protocol (one chunk of <= 32768 queries per call, the workspace carries the nominees between the calls):
+//     phase 1 = cast + [bounded] collect + bin, then the nominee selection into nom_pair;  phase 2 = refine only, pruning
+//     against prune_pair (the all-reduced nom_pair).  part_sign = -1: the `part` bounds travel negated (packed MAX all-reduce).
 static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k, float* D, int64_t* I,
                    int64_t id_offset, void* stream, const float* ext_full, const float* ext_part, int k_part,
-                   float* out_full, float* out_part) {
+                   float* out_full, float* out_part, int phase = 0, float part_sign = 1.f, float* nom_pair = nullptr,
+                   const float* prune_pair = nullptr) {
   const bool bounds_only = out_full != nullptr;
-  CDML_REQUIRE(ctx && ix && Q && (bounds_only || (D && I)), "cdml_knn_search: NULL argument");
+  CDML_REQUIRE(phase == 0 || nq <= 32768, "cdml_knn_shard_*: one chunk of at most 32768 queries per call (got %lld)", (long long)nq);
+  CDML_REQUIRE(ctx && ix && Q && (bounds_only || phase == 1 || (D && I)), "cdml_knn_search: NULL argument");
   CDML_REQUIRE(nq >= 0 && ldq >= ix->d && k >= 1 && k <= 1024, "cdml_knn_search: bad arguments (k=%d, supported 1..1024)", k);
   CDML_REQUIRE(k <= kKeepCap / 2, "cdml_knn_search: k=%d exceeds the re-rank capacity %d", k, kKeepCap / 2);
   if (nq == 0) return 0;
@@ -872,7 +1144,7 @@ static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, in
   const int64_t chunk = std::min<int64_t>(nq, 32768);
   int rc = ensure_workspace(ix, chunk);
   if (rc) { set_error("cdml_knn_search: workspace allocation failed"); return rc; }
-  ix->stats[0] = ix->stats[1] = 0;
+  if (phase != 2) ix->stats[0] = ix->stats[1] = 0;
   const int d = ix->d;
   // rigorous bound of |fp16 tensor-core score - exact score| <= (2u+u^2)|q||x| + accumulation; u = 2^-11
   const float rel = 1.5f * 0.0009765625f + 1.2e-7f * d;            // operand rounding + fp32 accumulation
@@ -890,6 +1162,8 @@ static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, in
   for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
     const int64_t qc = std::min<int64_t>(chunk, nq - q0);
     const float* Qc = Q + q0 * ldq;
+    const bool tiny = ix->N <= kKeepCap;   // tiny database: exact re-rank of every row, no tensor-core scan
+    if (phase != 2) {
     rc = cdml_rows_normalize_cast(ctx, Qc, qc, d, ldq, 0, 0.f, ix->q16, ix->dpad, CDML_F16, nullptr, 0, nullptr, stream);
     if (rc) return rc;
     const int grid = static_cast<int>(std::min<int64_t>((qc + 7) / 8, ctx->num_sms * 8));
@@ -897,16 +1171,17 @@ static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, in
     CDML_CHECK_CUDA(cudaMemsetAsync(ix->cnt, 0, sizeof(int32_t) * qc, st));
     CDML_CHECK_CUDA(cudaMemsetAsync(ix->overflow, 0, sizeof(int32_t) * qc, st));
     CDML_CHECK_CUDA(cudaMemsetAsync(ix->log_count, 0, sizeof(int32_t) * (ctx->num_sms * kKnnLogsPerCta + 1), st));
-    const bool tiny = ix->N <= kKeepCap;   // tiny database: exact re-rank of every row, no tensor-core scan
     if (bounds_only && (tiny || !(ix->Ns > 0 && ix->Ns / 32 >= k))) {   // no usable sample: no bound from this shard
       fill_f32_kernel<<<64, 256, 0, st>>>(out_full + q0, qc, -INFINITY);
-      fill_f32_kernel<<<64, 256, 0, st>>>(out_part + q0, qc, -INFINITY);
+      fill_f32_kernel<<<64, 256, 0, st>>>(out_part + q0, qc, -INFINITY * part_sign);
       continue;
     }
+    }
     if (!tiny) {
+     if (phase != 2) {
       if (ext_full != nullptr) {
         knn_thr_combine_kernel<<<static_cast<int>((qc + 255) / 256), 256, 0, st>>>(ext_full + q0, ext_part + q0, ix->qss, qc,
-                                                                                slack_scale, slack_abs, ix->thr);
+                                                                                slack_scale, slack_abs, ix->thr, part_sign);
       } else if (ix->Ns > 0 && ix->Ns / 32 >= k) {
         const int wide = (ix->Ns / 128 >= 2 * static_cast<int64_t>(k)) ? 1 : 0;
         const int groups = wide ? static_cast<int>((ix->Ns + 255) / 256 * 2) : static_cast<int>(ix->Ns / 32);
@@ -918,13 +1193,17 @@ static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, in
         if (rc < 0) return rc;
         auto kth = [&](int kk, int kk2, float sc, float ab, float* out, float* out2) {
           const int grid = static_cast<int>(qc);
-          if (groups <= 4 * kRefineThreads) {
-            if (out2) knn_kth_kernel<4, true><<<grid, kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, sc, ab, out, out2);
-            else knn_kth_kernel<4, false><<<grid, kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, sc, ab, out, out2);
+          if (groups <= 1024) {          // one warp per query
+            const int wgrid = static_cast<int>((qc + 7) / 8);
+            if (out2) knn_kth_warp_kernel<true><<<wgrid, 256, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, qc, sc, ab, out, out2, part_sign);
+            else knn_kth_warp_kernel<false><<<wgrid, 256, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, qc, sc, ab, out, out2, part_sign);
+          } else if (groups <= 4 * kRefineThreads) {
+            if (out2) knn_kth_kernel<4, true><<<grid, kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, sc, ab, out, out2, part_sign);
+            else knn_kth_kernel<4, false><<<grid, kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, sc, ab, out, out2, part_sign);
           } else {
             constexpr int kP = kMaxGroups / kRefineThreads;
-            if (out2) knn_kth_kernel<kP, true><<<grid, kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, sc, ab, out, out2);
-            else knn_kth_kernel<kP, false><<<grid, kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, sc, ab, out, out2);
+            if (out2) knn_kth_kernel<kP, true><<<grid, kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, sc, ab, out, out2, part_sign);
+            else knn_kth_kernel<kP, false><<<grid, kRefineThreads, 0, st>>>(ix->gmax, ix->ldg, groups, kk, kk2, ix->qss, sc, ab, out, out2, part_sign);
           }
         };
         if (bounds_only) {   // raw scores: the caller combines them across shards
@@ -944,13 +1223,31 @@ static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, in
       if (rc < 0) return rc;
       knn_bin_kernel<<<dim3(4, ctx->num_sms * kKnnLogsPerCta), 256, 0, st>>>(ix->log, ix->log_count, ix->log_cap, ix->cand_idx, ix->cand_val,
                                                             ix->cnt, kCandCap);
+     }
+      if (phase == 1) {   // nominees stay in the workspace; their k-th / k_part-th best scores go to the caller's all-reduce
+        knn_nominee_kth_kernel<<<static_cast<int>((qc + 7) / 8), 256, 0, st>>>(ix->cand_val, ix->cnt, kCandCap, k,
+                                                                              std::max(1, std::min(k_part, k)), qc, nom_pair);
+        CDML_CHECK_CUDA(cudaGetLastError());
+        continue;
+      }
+      if (prune_pair != nullptr)    // the common case of a shard: few nominees, a global bound -> one warp per query
+        knn_refine_warp_kernel<<<static_cast<int>((qc + 7) / 8), 256, 0, st>>>(
+            Qc, ldq, d, ix->qss, ix->x32, d, ix->xss, ix->cand_idx, ix->cand_val, ix->cnt, kCandCap, k, ix->metric,
+            slack_scale, slack_abs, id_offset, D + q0 * k, I + q0 * k, k, prune_pair, qc, qc, ix->handled);
       knn_refine_kernel<<<static_cast<int>(qc), kRefineThreads, 0, st>>>(
           Qc, ldq, d, ix->qss, ix->x32, d, ix->xss, ix->cand_idx, ix->cand_val, ix->cnt, kCandCap, k, ix->metric,
-          slack_scale, slack_abs, id_offset, D + q0 * k, I + q0 * k, k, ix->overflow, 0);
+          slack_scale, slack_abs, id_offset, D + q0 * k, I + q0 * k, k, ix->overflow, 0, prune_pair, qc,
+          prune_pair != nullptr ? ix->handled : nullptr);
     } else {
+      if (phase == 1) {   // tiny shard: every row is re-ranked exactly in phase 2, no bound to contribute
+        fill_f32_kernel<<<64, 256, 0, st>>>(nom_pair, qc, -INFINITY);
+        fill_f32_kernel<<<64, 256, 0, st>>>(nom_pair + qc, qc, INFINITY);
+        CDML_CHECK_CUDA(cudaGetLastError());
+        continue;
+      }
       knn_refine_kernel<<<static_cast<int>(qc), kRefineThreads, 0, st>>>(
           Qc, ldq, d, ix->qss, ix->x32, d, ix->xss, ix->cand_idx, ix->cand_val, ix->cnt, kCandCap, k, ix->metric,
-          slack_scale, slack_abs, id_offset, D + q0 * k, I + q0 * k, k, ix->overflow, static_cast<int>(ix->N));
+          slack_scale, slack_abs, id_offset, D + q0 * k, I + q0 * k, k, ix->overflow, static_cast<int>(ix->N), nullptr, 0, nullptr);
       ix->stats[0] += ix->N * qc;
     }
     CDML_CHECK_CUDA(cudaGetLastError());
@@ -961,7 +1258,7 @@ static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, in
     CDML_CHECK_CUDA(cudaMemcpyAsync(ix->h_logovf + q0 / chunk, ix->log_count + ctx->num_sms * kKnnLogsPerCta, sizeof(int32_t),
                                     cudaMemcpyDeviceToHost, st));
   }
-  if (bounds_only) return 0;
+  if (bounds_only || phase == 1) return 0;
   CDML_CHECK_CUDA(cudaStreamSynchronize(st));
   // queries whose candidate list (or whose chunk's warp log) overflowed are redone exactly in fp32, all in one launch
   std::vector<int32_t> redo;
@@ -1026,6 +1323,65 @@ int cdml_knn_search_bounded(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64
                             void* stream) {
   CDML_REQUIRE(bound_full && bound_part, "cdml_knn_search_bounded: NULL bounds");
   return knn_run(ctx, ix, Q, nq, ldq, k, D, I, id_offset, stream, bound_full, bound_part, k, nullptr, nullptr);
+}
+
+// ---- row-sharded protocol, one chunk (<= 32768 queries) per call -------------------------------------------------
+int cdml_knn_shard_bounds(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k, int k_part,
+                          float* pair, void* stream) {
+  CDML_REQUIRE(pair && k_part >= 1, "cdml_knn_shard_bounds: NULL / bad argument");
+  return knn_run(ctx, ix, Q, nq, ldq, k, nullptr, nullptr, 0, stream, nullptr, nullptr, k_part, pair, pair + nq, 0, -1.f);
+}
+
+int cdml_knn_shard_collect(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k, int k_part,
+                           const float* pair, float* nom_pair, void* stream) {
+  CDML_REQUIRE(pair && nom_pair && k_part >= 1, "cdml_knn_shard_collect: NULL / bad argument");
+  return knn_run(ctx, ix, Q, nq, ldq, k, nullptr, nullptr, 0, stream, pair, pair + nq, k_part, nullptr, nullptr, 1, -1.f,
+                 nom_pair);
+}
+
+int cdml_knn_shard_refine(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k,
+                          const float* nom_pair, unsigned long long* rec, int64_t id_offset, void* stream) {
+  CDML_REQUIRE(ix && rec, "cdml_knn_shard_refine: NULL argument");
+  CDML_REQUIRE(id_offset >= 0 && id_offset + ix->N <= (1ll << 32) - 1, "cdml_knn_shard_refine: global ids must fit 32 bits");
+  if (ix->tmp_cap < nq * k) {
+    cudaFree(ix->Dtmp), cudaFree(ix->Itmp);
+    ix->Dtmp = nullptr, ix->Itmp = nullptr, ix->tmp_cap = 0;
+    if (dev_alloc(&ix->Dtmp, static_cast<size_t>(nq) * k) || dev_alloc(&ix->Itmp, static_cast<size_t>(nq) * k)) return -2;
+    ix->tmp_cap = nq * k;
+  }
+  int rc = knn_run(ctx, ix, Q, nq, ldq, k, ix->Dtmp, ix->Itmp, id_offset, stream, nullptr, nullptr, k, nullptr, nullptr, 2, -1.f,
+                   nullptr, nom_pair);
+  if (rc) return rc;
+  const int64_t n = nq * k;
+  knn_pack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ix->Dtmp, ix->Itmp, n, ix->metric, rec);
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cdml_knn_unpack_records(cdml_ctx* ctx, const unsigned long long* rec, int64_t n, int metric, float* D, int64_t* I,
+                            void* stream) {
+  CDML_REQUIRE(ctx && rec && D && I && n >= 0, "cdml_knn_unpack_records: bad argument");
+  if (n == 0) return 0;
+  knn_unpack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rec, n, metric, D, I);
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cdml_knn_merge_packed(cdml_ctx* ctx, const unsigned long long* rec, int G, int64_t nq, int k, int metric, float* D,
+                          int64_t* I, unsigned long long* rec_out, void* stream) {
+  CDML_REQUIRE(ctx && rec && ((D && I) || rec_out) && G >= 1 && G <= 32 && k >= 1 && nq >= 0,
+               "cdml_knn_merge_packed: bad argument (1 <= G <= 32)");
+  if (nq == 0) return 0;
+  const size_t per = static_cast<size_t>(G) * k * sizeof(unsigned long long);
+  CDML_REQUIRE(per <= 200 * 1024, "cdml_knn_merge_packed: G*k=%d too large for one warp's staging", G * k);
+  const int warps = static_cast<int>(std::max<size_t>(1, std::min<size_t>(8, (96 * 1024) / per)));
+  const size_t smem = per * warps;
+  if (smem > 48 * 1024)
+    CDML_CHECK_CUDA(cudaFuncSetAttribute(knn_merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  knn_merge_packed_kernel<<<static_cast<unsigned>((nq + warps - 1) / warps), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      rec, G, nq, k, metric, warps, D, I, rec_out);
+  CDML_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int cdml_knn_merge(cdml_ctx* ctx, const float* Dg, const int64_t* Ig, int G, int64_t nq, int k, int metric, float* D,

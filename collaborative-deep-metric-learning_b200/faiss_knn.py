@@ -53,19 +53,69 @@ def _device():
   return torch.device("cuda:%d" % torch.cuda.current_device())
 
 
-def sharded_search(index, xq, k, id_offset=0, metric="L2", process_group=None, merge_fn=None):
-  """Top-k of the (replicated) queries `xq` over a row-sharded index; device tensors in and out, identical on every rank.
+def sharded_search(index, xq, k, id_offset=0, metric="L2", process_group=None, merge_fn=None, gather=True,
+                   merge_packed_fn=None):
+  """Top-k of the (replicated) queries `xq` over a row-sharded index; device tensors in and out.
 
-  1. bound pass on every shard, then two tiny NCCL all-reduces agree on one collection bound per query (MAX of the
-     shards' k-th best sampled score, MIN of their ceil(k/W)-th best): together the shards nominate about as many
-     candidates as one unsharded index would, instead of W times as many;
-  2. collect + exact re-rank on every shard -> local top-k with global ids (local row + id_offset);
-  3. NCCL all-to-all: rank r receives every shard's lists for ITS slice of the queries and merges them on the GPU
-     (cdml_knn_merge, ties -> lower id); one all-gather of the merged slices completes the result."""
+  Per chunk of <= 32768 queries, one collective per phase (each an all-reduce MAX of a [2,n] fp32 pair):
+    1. bound pass on every shard -> all-reduce: max over shards of their k-th best sampled score / min of their
+       ceil(k/W)-th best -- one collection bound per query, so that together the shards nominate about as many candidates
+       as one unsharded index would instead of W times as many;
+    2. collect on every shard, k-th / ceil(k/W)-th best APPROXIMATE score among its nominees -> all-reduce: a lower bound of
+       the global k-th best approximate score;
+    3. exact fp32 re-rank of the nominees within 2 eps of that global bound only (~k rows per query over all shards, not W*k)
+       -> sorted local list as 64-bit records (distance key | global id).
+  Then ONE all-to-all: rank r receives every shard's lists for ITS slice of the queries and merges them on the GPU
+  (cdml_knn_merge_packed, ties -> lower id).  gather=True completes the result on every rank with one all-gather;
+  gather=False returns (D, I) of this rank's query slice [r*nq/W, (r+1)*nq/W) only -- what a caller that writes its own
+  knn_split files needs."""
   world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
   if world == 1:
     return index.search(xq, k, id_offset=id_offset)
-  merge_fn = merge_fn or ops.knn_merge      # (tests drive this protocol over gloo with a CPU stand-in)
+  if not hasattr(index, "shard_bounds"):
+    return _sharded_search_lists(index, xq, k, id_offset, metric, process_group, merge_fn)
+  dist = torch.distributed
+  nq = xq.shape[0]
+  k_part = -(-k // world)
+  pad = (-nq) % world                      # the all-to-all needs equal slices: pad with copies of the last query
+  if pad:
+    xq = torch.cat([xq, xq[-1:].expand(pad, -1)], 0)
+  nqp = nq + pad
+  rec = torch.empty((nqp, k), dtype=torch.int64, device=xq.device)
+  for s in range(0, nqp, index.CHUNK):
+    q = xq[s:s + index.CHUNK]
+    pair = index.shard_bounds(q, k, k_part)
+    dist.all_reduce(pair, op=dist.ReduceOp.MAX, group=process_group)
+    nom = index.shard_collect(q, k, k_part, pair)
+    dist.all_reduce(nom, op=dist.ReduceOp.MAX, group=process_group)
+    index.shard_refine(q, k, nom, rec[s:s + index.CHUNK], id_offset=id_offset)
+  got = torch.empty_like(rec)                # [W, nqp/W, k]: every shard's lists for my query slice
+  dist.all_to_all_single(got, rec, group=process_group)
+  got = got.view(world, nqp // world, k)
+  if not gather:
+    Dm, Im = (merge_packed_fn or ops.knn_merge_packed)(got, metric)   # (tests: CPU stand-in over gloo)
+    rank = dist.get_rank(process_group)
+    lo, hi = rank * (nqp // world), min((rank + 1) * (nqp // world), nq)
+    return Dm[:max(hi - lo, 0)], Im[:max(hi - lo, 0)]
+  if merge_packed_fn is not None:           # stand-in without a records output: gather the two arrays
+    Dm, Im = merge_packed_fn(got, metric)
+    D = torch.empty((nqp, k), dtype=Dm.dtype, device=Dm.device)
+    I = torch.empty((nqp, k), dtype=Im.dtype, device=Im.device)
+    dist.all_gather_into_tensor(D, Dm, group=process_group)
+    dist.all_gather_into_tensor(I, Im, group=process_group)
+    return D[:nq], I[:nq]
+  mine = ops.knn_merge_packed(got, metric, as_records=True)         # merged slice stays packed: ONE all-gather of 8 B / entry
+  allr = torch.empty((nqp, k), dtype=torch.int64, device=xq.device)
+  dist.all_gather_into_tensor(allr, mine, group=process_group)
+  D, I = ops.knn_unpack_records(allr, metric)
+  return D[:nq], I[:nq]
+
+
+def _sharded_search_lists(index, xq, k, id_offset=0, metric="L2", process_group=None, merge_fn=None):
+  """The same search with (D, I) lists instead of packed records and local pruning only (an index object that offers
+  bounds / search_bounded but not the shard_* calls: the CPU stand-in of the gloo protocol test)."""
+  world = torch.distributed.get_world_size(process_group)
+  merge_fn = merge_fn or ops.knn_merge
   bf, bp = index.bounds(xq, k, -(-k // world))
   torch.distributed.all_reduce(bf, op=torch.distributed.ReduceOp.MAX, group=process_group)
   torch.distributed.all_reduce(bp, op=torch.distributed.ReduceOp.MIN, group=process_group)

@@ -358,6 +358,35 @@ class FlatIndex(object):
                                               ptr(bound_part), ptr(D), ptr(I), int(id_offset), stream_ptr()))
     return D, I
 
+  # ---- row-sharded protocol, one chunk (<= 32768 queries) per call; see include/cdml.h
+  CHUNK = 32768
+
+  def shard_bounds(self, xq, k, k_part, pair=None):
+    nq = xq.shape[0]
+    if pair is None:
+      pair = torch.empty((2, nq), dtype=torch.float32, device=xq.device)
+    _count(4)
+    check(_lib.load().cdml_knn_shard_bounds(_ctx(xq), self._h, ptr(xq), nq, _row_major_2d(xq, "xq"), int(k), int(k_part),
+                                            ptr(pair), stream_ptr()))
+    return pair
+
+  def shard_collect(self, xq, k, k_part, pair, nom_pair=None):
+    nq = xq.shape[0]
+    if nom_pair is None:
+      nom_pair = torch.empty((2, nq), dtype=torch.float32, device=xq.device)
+    _count(6)
+    check(_lib.load().cdml_knn_shard_collect(_ctx(xq), self._h, ptr(xq), nq, _row_major_2d(xq, "xq"), int(k), int(k_part),
+                                             ptr(pair), ptr(nom_pair), stream_ptr()))
+    return nom_pair
+
+  def shard_refine(self, xq, k, nom_pair, rec, id_offset=0):
+    """rec: int64 [nq,k] slice receiving the packed records of this chunk."""
+    nq = xq.shape[0]
+    _count(2)
+    check(_lib.load().cdml_knn_shard_refine(_ctx(xq), self._h, ptr(xq), nq, _row_major_2d(xq, "xq"), int(k), ptr(nom_pair),
+                                            ptr(rec), int(id_offset), stream_ptr()))
+    return rec
+
   def last_stats(self):
     s = (ctypes.c_int64 * 2)()
     check(_lib.load().cdml_knn_last_stats(self._h, s))
@@ -373,6 +402,34 @@ class FlatIndex(object):
       self.close()
     except Exception:
       pass
+
+
+def knn_merge_packed(rec, metric="L2", as_records=False):
+  """[G,nq,k] int64 packed records (FlatIndex.shard_refine) -> global top-k D fp32 / I int64 [nq,k] (ties -> lower id), or
+  (as_records) the merged lists as int64 records [nq,k]."""
+  G, nq, k = rec.shape
+  rec = rec.contiguous()
+  m = {"L2": 0, "IP": 1}[metric]
+  _count(1)
+  if as_records:
+    out = torch.empty((nq, k), dtype=torch.int64, device=rec.device)
+    check(_lib.load().cdml_knn_merge_packed(_ctx(rec), ptr(rec), G, nq, k, m, None, None, ptr(out), stream_ptr()))
+    return out
+  D = torch.empty((nq, k), dtype=torch.float32, device=rec.device)
+  I = torch.empty((nq, k), dtype=torch.int64, device=rec.device)
+  check(_lib.load().cdml_knn_merge_packed(_ctx(rec), ptr(rec), G, nq, k, m, ptr(D), ptr(I), None, stream_ptr()))
+  return D, I
+
+
+def knn_unpack_records(rec, metric="L2"):
+  """int64 records [nq,k] -> D fp32, I int64 (padding -> inf / -1)."""
+  rec = rec.contiguous()
+  D = torch.empty(rec.shape, dtype=torch.float32, device=rec.device)
+  I = torch.empty(rec.shape, dtype=torch.int64, device=rec.device)
+  _count(1)
+  check(_lib.load().cdml_knn_unpack_records(_ctx(rec), ptr(rec), rec.numel(), {"L2": 0, "IP": 1}[metric], ptr(D), ptr(I),
+                                            stream_ptr()))
+  return D, I
 
 
 def knn_merge(Dg, Ig, metric="L2"):

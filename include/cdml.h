@@ -12,6 +12,15 @@
  *   - every compute call takes a cudaStream_t (as void*) and is asynchronous w.r.t. the host;
  *   - dtype16: 0 = fp16, 1 = bf16 (operand type of the tensor-core GEMMs; accumulation is fp32);
  *   - 16-bit / fp32 matrices handed to GEMMs need 16-byte aligned bases and row pitches.
+ *
+ * Collectives (deliberate deviation from SURVEY.md 8(b)'s draft list): there is NO cdml_nccl_init / cdml_allreduce_sum /
+ * cdml_allgather.  The exchange steps of the path -- the all-reduce of the flat gradient buffer, the all-reduce MAX of the
+ * per-query KNN bound pairs, the all-to-all of the per-shard KNN records -- are issued by the host through
+ * torch.distributed (NCCL): the task assigns that plumbing to torch ("one process per GPU with torch.distributed over
+ * NCCL/NVLink"), a second communicator inside this library would duplicate the process group's rendezvous, and NCCL calls
+ * made by torch are what CUDA-graph capture of the whole training step records.  Every entry point that sits next to a
+ * collective is shaped for it: contiguous flat buffers ([dW ; db] per layer, fp32 [2,nq] pairs, [nq,k] 64-bit records),
+ * stream-ordered, no host synchronisation between the call and the collective.
  */
 #ifndef CDML_H_
 #define CDML_H_
@@ -173,6 +182,33 @@ int cdml_knn_last_stats(cdml_index* index, int64_t* stats);
 /* Merge G per-shard results [G,nq,k] into the global top-k (ties -> lower id). */
 int cdml_knn_merge(cdml_ctx* ctx, const float* Dg, const int64_t* Ig, int G, int64_t nq, int k, int metric, float* D,
                    int64_t* I, void* stream);
+
+/* Row-sharded index, protocol with ONE collective per phase (faiss_knn.sharded_search; the three calls process one chunk of
+ * at most 32768 queries and share the index workspace, so they must follow each other on one stream):
+ *   cdml_knn_shard_bounds   pair[0][q] = k-th best sampled score of this shard, pair[1][q] = -(k_part-th best)  (-inf / +inf
+ *                           without a usable sample)                                       -> caller: all-reduce MAX of pair
+ *   cdml_knn_shard_collect  collects the rows above max(pair[0], -pair[1]) - slack and writes nom_pair[0][q] = k-th best
+ *                           approximate score among this shard's nominees, nom_pair[1][q] = -(k_part-th best)
+ *                                                                                          -> caller: all-reduce MAX of nom_pair
+ *   cdml_knn_shard_refine   exact fp32 re-rank of the nominees within 2*eps of max(nom_pair[0], -nom_pair[1]) -- a lower bound
+ *                           of the GLOBAL k-th best approximate score, so the shards together re-rank ~k rows per query, not
+ *                           shards*k -- and writes this shard's (possibly shorter than k) sorted list as 64-bit records
+ *                           rec[q][j] = (order-preserving distance key << 32) | global id, padding = ~0
+ *                                                                                          -> caller: all-to-all of rec
+ *   cdml_knn_merge_packed   k-way merge of G <= 32 record lists [G,nq,k] -> D, I [nq,k] (ties -> lower id), or -- rec_out
+ *                           non-NULL -- the merged list as records [nq,k] (the caller all-gathers ONE 8-byte array and
+ *                           cdml_knn_unpack_records turns records into D fp32 / I int64).
+ * pair / nom_pair are fp32 [2,nq]; global ids (id_offset + row) must fit 32 bits. */
+int cdml_knn_shard_bounds(cdml_ctx* ctx, cdml_index* index, const float* Q, int64_t nq, int64_t ldq, int k, int k_part,
+                          float* pair, void* stream);
+int cdml_knn_shard_collect(cdml_ctx* ctx, cdml_index* index, const float* Q, int64_t nq, int64_t ldq, int k, int k_part,
+                           const float* pair, float* nom_pair, void* stream);
+int cdml_knn_shard_refine(cdml_ctx* ctx, cdml_index* index, const float* Q, int64_t nq, int64_t ldq, int k,
+                          const float* nom_pair, unsigned long long* rec, int64_t id_offset, void* stream);
+int cdml_knn_merge_packed(cdml_ctx* ctx, const unsigned long long* rec, int G, int64_t nq, int k, int metric, float* D,
+                          int64_t* I, unsigned long long* rec_out, void* stream);
+int cdml_knn_unpack_records(cdml_ctx* ctx, const unsigned long long* rec, int64_t n, int metric, float* D, int64_t* I,
+                            void* stream);
 
 /* ---- evaluate.Evaluation.mean_dist (evaluate.py:57-73): mean_p sum_d (V[p0]-V[p1])^2, pairs int64 [P,2]. */
 int cdml_mean_pair_dist(cdml_ctx* ctx, const float* V, int64_t ld, int D, const int64_t* pairs, int64_t P,

@@ -620,6 +620,39 @@ def knn_merge(D_parts, I_parts, k, metric="L2"):
 # --------------------------------------------------------------------------- #
 # result writer (faiss_knn.py:267-283) and eval (evaluate.py:57-73)            #
 # --------------------------------------------------------------------------- #
+def f2key(x):
+  """Order-preserving fp32 -> uint32 map of the KNN kernels (csrc/knn.cu f2key): negative floats complemented, others get
+  the top bit."""
+  u = np.ascontiguousarray(x, np.float32).view(np.uint32)
+  return np.where(u & np.uint32(0x80000000), ~u, u | np.uint32(0x80000000)).astype(np.uint32)
+
+
+def key2f(k):
+  k = np.asarray(k, np.uint32)
+  return np.where(k & np.uint32(0x80000000), k & np.uint32(0x7FFFFFFF), ~k).astype(np.uint32).view(np.float32)
+
+
+def knn_pack_records(D, I, metric="L2"):
+  """(D, I) lists -> the 64-bit records a shard sends (cdml_knn_shard_refine): (f2key(distance) << 32) | global id,
+  padding (id < 0) = all ones.  Sorting records ascending sorts by (distance, id) -- descending inner product for IP."""
+  D, I = np.asarray(D, np.float32), np.asarray(I, np.int64)
+  key = f2key(D if metric == "L2" else -D).astype(np.uint64)
+  rec = (key << np.uint64(32)) | (I.astype(np.uint64) & np.uint64(0xFFFFFFFF))
+  return np.where(I < 0, np.uint64(0xFFFFFFFFFFFFFFFF), rec)
+
+
+def knn_merge_records(rec, k, metric="L2"):
+  """[G,nq,k] records -> global top-k (cdml_knn_merge_packed): ascending sort of the union, first k, unpacked."""
+  rec = np.asarray(rec, np.uint64)
+  G, nq, kk = rec.shape
+  allr = np.sort(np.transpose(rec, (1, 0, 2)).reshape(nq, G * kk), axis=1)[:, :k]
+  pad = allr == np.uint64(0xFFFFFFFFFFFFFFFF)
+  d = key2f((allr >> np.uint64(32)).astype(np.uint32))
+  D = np.where(pad, np.inf if metric == "L2" else -np.inf, d if metric == "L2" else -d).astype(np.float32)
+  I = np.where(pad, -1, (allr & np.uint64(0xFFFFFFFF)).astype(np.int64))
+  return D, I
+
+
 def format_knn_rows(begin_index, D, I, decode_map):
   """write_process: '<query_guid>,<nbr_guid>#<dist><...\\n'; skips column 0 and
   keeps a neighbour only if idx > 0 and 0.0 < dist < 1.4; dist via str(np.float32)."""

@@ -585,6 +585,48 @@ def test_sharded_two_phase_search_with_agreed_bounds(cd):
   assert_knn_matches(Dm.cpu().numpy(), Im.cpu().numpy(), Dw, Iw, 'L2', X, Q)
 
 
+@pytest.mark.parametrize("metric,W", [("L2", 4), ("L2", 8), ("IP", 3)])
+def test_sharded_record_protocol_prunes_against_the_global_bound(cd, metric, W):
+  """The three-call shard protocol emulated on one GPU (the element-wise max of the [2,nq] pairs is what the NCCL all-reduce
+  MAX does): bounds -> collect (+ nominee selection) -> refine against the GLOBAL bound -> packed records -> k-way merge.
+  Result == flat oracle; the records and the merge are bit-identical to their oracle statements; the shards' lists are
+  short (the global bound leaves ~k rows per query over all shards to re-rank, not W*k)."""
+  rng = np.random.RandomState(13)
+  N, nq, k = 48000, 640, 100
+  X = O.knn_normalize(rng.standard_normal((N, 256)).astype(np.float32))
+  if metric == "IP":
+    X = (X * rng.uniform(0.5, 2.0, size=(N, 1))).astype(np.float32)
+  Q = X[rng.choice(N, nq, replace=False)]
+  Dw, Iw = O.flat_knn(X, Q, k=k, l2_norm=False, metric=metric)
+  xq = dev_t(cd, Q)
+  shards = [(s * N // W, (s + 1) * N // W) for s in range(W)]
+  idx = [cd.ops.FlatIndex(dev_t(cd, X[lo:hi]), metric) for lo, hi in shards]
+  k_part = -(-k // W)
+  pair = torch.stack([ix.shard_bounds(xq, k, k_part) for ix in idx]).max(0).values
+  nom = torch.stack([ix.shard_collect(xq, k, k_part, pair) for ix in idx]).max(0).values
+  assert torch.isfinite(nom[1]).all()                                  # every shard nominated >= ceil(k/W) rows per query
+  rec = torch.empty((W, nq, k), dtype=torch.int64, device=cd.dev)
+  for s_, (ix, (lo, hi)) in enumerate(zip(idx, shards)):
+    ix.shard_refine(xq, k, nom, rec[s_], id_offset=lo)
+  filled = (rec != -1).sum().item() / float(nq)                        # -1 = all ones = padding
+  assert k <= filled < 2.5 * k, filled                                 # local pruning alone would fill W*k per query
+  Dm, Im = cd.ops.knn_merge_packed(rec, metric)
+  assert (Im >= 0).all().item()
+  assert_knn_matches(Dm.cpu().numpy(), Im.cpu().numpy(), Dw, Iw, metric, X, Q)
+  # the record format and the merge against their oracle statements, bit for bit
+  Do, Io = O.knn_merge_records(rec.cpu().numpy().view(np.uint64), k, metric)
+  assert np.array_equal(Im.cpu().numpy(), Io) and np.array_equal(Dm.cpu().numpy(), Do)
+  merged = cd.ops.knn_merge_packed(rec, metric, as_records=True)       # the form that is all-gathered, and its unpacking
+  Du, Iu = cd.ops.knn_unpack_records(merged, metric)
+  assert torch.equal(Du, Dm) and torch.equal(Iu, Im)
+  one = idx[0].search(xq[:64], 10, id_offset=shards[0][0])
+  packed = O.knn_pack_records(one[0].cpu().numpy(), one[1].cpu().numpy(), metric)
+  D1, I1 = O.knn_merge_records(packed[None], 10, metric)
+  assert np.array_equal(I1, one[1].cpu().numpy()) and np.array_equal(D1, one[0].cpu().numpy())
+  for ix in idx:
+    ix.close()
+
+
 def test_mean_dist_matches_oracle(cd, golden):
   from cdml_b200.evaluate import Evaluation
   ev = Evaluation(golden["gather_features"], golden["eval_cowatches"].tolist())

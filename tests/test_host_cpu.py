@@ -270,6 +270,44 @@ for nq in (300, 301):      # divisible by the world size (all-to-all path) and n
   Dm, Im = faiss_knn.sharded_search(ShardIndex(X[lo:hi]), torch.tensor(X[:nq]), 7, lo, "L2", dist.group.WORLD, merge_fn=cpu_merge)
   assert np.array_equal(Im.numpy(), Iw[:nq]) and np.allclose(Dm.numpy(), Dw[:nq], atol=1e-6), nq
   assert (Im.numpy() >= 0).all()
+# --- the same search through the record protocol (shard_bounds -> all-reduce -> shard_collect -> all-reduce -> shard_refine
+#     -> ONE all-to-all of 64-bit records -> packed merge), chunked, with padding of the query count and with gather=False
+class RecordShard(ShardIndex):
+  CHUNK = 128
+  def shard_bounds(self, xq, k, k_part):
+    bf, bp = self.bounds(xq, k, k_part)
+    return torch.stack([bf, -bp])
+  def shard_collect(self, xq, k, k_part, pair):
+    s = self._scores(xq)
+    thr = np.maximum(pair[0].numpy(), -pair[1].numpy()) - 1e-5
+    self.nom = [np.nonzero(s[i] > thr[i])[0] for i in range(len(s))]
+    pick = lambda v, kk: np.sort(v)[::-1][kk - 1] if len(v) >= kk else -np.inf
+    a = np.array([pick(s[i][self.nom[i]], k) for i in range(len(s))], np.float32)
+    b = np.array([pick(s[i][self.nom[i]], k_part) for i in range(len(s))], np.float32)
+    return torch.tensor(np.stack([a, -b]))
+  def shard_refine(self, xq, k, nom, rec, id_offset=0):
+    s = self._scores(xq)
+    T = np.maximum(nom[0].numpy(), -nom[1].numpy()) - 1e-5
+    D = np.full((len(s), k), np.inf, np.float32); I = np.full((len(s), k), -1, np.int64)
+    self.reranked = 0
+    for i in range(len(s)):
+      rows = self.nom[i][s[i][self.nom[i]] >= T[i]]
+      self.reranked += len(rows)
+      if len(rows):
+        d, ids = O.flat_knn(self.xb[rows], xq.numpy()[i:i + 1], k=min(k, len(rows)), l2_norm=False)
+        D[i, :d.shape[1]], I[i, :d.shape[1]] = d[0], rows[ids[0]] + id_offset
+    rec.copy_(torch.tensor(O.knn_pack_records(D, I).view(np.int64)))
+def cpu_merge_packed(rec, metric):
+  Dm, Im = O.knn_merge_records(rec.numpy().view(np.uint64), rec.shape[2], metric)
+  return torch.tensor(Dm), torch.tensor(Im)
+for nq in (300, 301):
+  shard = RecordShard(X[lo:hi])
+  Dm, Im = faiss_knn.sharded_search(shard, torch.tensor(X[:nq]), 7, lo, "L2", dist.group.WORLD, merge_packed_fn=cpu_merge_packed)
+  assert np.array_equal(Im.numpy(), Iw[:nq]) and np.allclose(Dm.numpy(), Dw[:nq], atol=1e-6), nq
+  assert shard.reranked < 7 * 2 * 128, shard.reranked      # the global bound keeps the re-rank near k rows per query over BOTH shards
+  Ds, Is = faiss_knn.sharded_search(shard, torch.tensor(X[:nq]), 7, lo, "L2", dist.group.WORLD, merge_packed_fn=cpu_merge_packed, gather=False)
+  per = (nq + 1) // 2
+  assert np.array_equal(Is.numpy(), Iw[rank * per:min((rank + 1) * per, nq)])
 # --- de-similarity filter with the rows split over the ranks (PRODUCT's sharded_desim, oracle-backed stand-in for cdml_desim)
 rs = np.random.RandomState(3)
 n, ke, kf = 101, 9, 6          # 101 rows: the last slice is short and padded for the all-gather
