@@ -156,10 +156,11 @@ inline bool resb_applicable(int64_t K) {
   return off == 0 && K <= 4 * kBK;
 }
 
-template <class Epi>
+template <class Epi, int kEpiWarps = 8>
 static int launch_gemm_resb(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
                             int64_t K, int dtype16, const Epi& epi, cudaStream_t stream, int n_fastest = 0) {
-  using L = ResBSmem<kBN, kResBStages>;
+  using L = ResBSmem<kBN, kResBStages, kEpiWarps, Epi::kRowConsts>;
+  static_assert(L::kTotal <= 232448, "resident-B kernel: shared memory over the 227 KB limit");
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(ctx, &ta, A, dtype16, K, M, lda, kBK, kBM);
   if (rc) return rc;
@@ -188,7 +189,7 @@ static int launch_gemm_resb(cdml_ctx* ctx, const void* A, int64_t lda, const voi
   s.tiles_per_chunk = (s.m_tiles + best - 1) / best;
   s.n_fastest = n_fastest;
   s.idesc = make_idesc_f16(dtype16 == CDML_BF16 ? 1 : 0, 0, 0, kBM, kBN);
-  auto kern = gemm_resb_tcgen05_kernel<kBN, kResBStages, Epi>;
+  auto kern = gemm_resb_tcgen05_kernel<kBN, kResBStages, Epi, kEpiWarps>;
   static bool attr_set = false;
   if (!attr_set) {
     CDML_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -196,7 +197,7 @@ static int launch_gemm_resb(cdml_ctx* ctx, const void* A, int64_t lda, const voi
   }
   const long units = static_cast<long>(s.n_tiles) * s.m_chunks;
   const int grid = static_cast<int>(units < ctx->num_sms ? units : ctx->num_sms);
-  kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, s, epi);
+  kern<<<grid, 128 + 32 * kEpiWarps, L::kTotal, stream>>>(ta, tb, s, epi);
   CDML_CHECK_CUDA(cudaGetLastError());
   if (trace_sync("gemm_resb", M, N, K, grid, stream)) return -2;
   return 1;

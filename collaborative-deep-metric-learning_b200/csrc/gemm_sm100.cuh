@@ -653,24 +653,31 @@ struct ResBShape {
   uint32_t idesc;
 };
 
-template <int BN, int kAStages>
+// kEpiWarps = 8 (two warps per TMEM lane quarter, four 32-column chunks each) or 16 (four per quarter, two chunks each:
+// the selection epilogues are bound by the LATENCY of a warp's chunk sequence, not by issue slots -- with four warps per
+// scheduler the sequence is half as long and the other warps fill its bubbles).  kRowSlots: shared-memory slots for
+// Epi::kRowConsts (0 when the epilogue does not use them).
+template <int BN, int kAStages, int kEpiWarps = 8, bool kRowSlots = false>
 struct ResBSmem {
   static constexpr uint32_t kABytes = kBM * kBK * 2;
   static constexpr uint32_t kBPanel = BN * kBK * 2;
   static constexpr uint32_t kMaxKb = 4;
   static constexpr uint32_t kEpiOff = kMaxKb * kBPanel + kAStages * kABytes;
-  static constexpr uint32_t kRowConstOff = kEpiOff + kEpiStageBytes;   // 2 slots x 128 rows x 32 B (Epi::kRowConsts)
-  static constexpr uint32_t kRowConstSlot = kBM * 32;
+  static constexpr uint32_t kEpiBytes = kEpiWarps * 2048;
+  static constexpr uint32_t kRowConstOff = kEpiOff + kEpiBytes;   // 2 slots x 128 rows x 32 B (Epi::kRowConsts)
+  static constexpr uint32_t kRowConstSlot = kRowSlots ? kBM * 32 : 0;
   static constexpr uint32_t kBarOff = kRowConstOff + 2 * kRowConstSlot;
   static constexpr uint32_t kNumBars = 2 * kAStages + 2 + 4 + 2;
   static constexpr uint32_t kTotal = kBarOff + kNumBars * 8 + 16 + 1024;
 };
 
-template <int BN, int kAStages, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, int kAStages, class Epi, int kEpiWarps = 8>
+__global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1)
 gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                          const ResBShape s, const Epi epi) {
-  using L = ResBSmem<BN, kAStages>;
+  using L = ResBSmem<BN, kAStages, kEpiWarps, Epi::kRowConsts>;
+  static_assert(kEpiWarps == 8 || kEpiWarps == 16, "two or four epilogue warps per TMEM lane quarter");
+  static_assert(kEpiWarps == 8 || Epi::kSplitColumns, "four warps per quarter split the tile's columns");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -705,7 +712,7 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     mbar_init(b_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 8);
+      mbar_init(tempty_bar(i), kEpiWarps);
       mbar_init(cfull_bar(i), 1);
     }
     fence_mbar_init();
@@ -807,8 +814,8 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
-    const uint32_t stg = base + L::kEpiOff + (warp - 4) * (Epi::kSplitColumns ? 2048u : 4096u);
+    const int half = (warp - 4) >> 2;         // which share of the tile's columns (0..kEpiWarps/4-1)
+    const uint32_t stg = base + L::kEpiOff + (warp - 4) * ((Epi::kSplitColumns || kEpiWarps == 16) ? 2048u : 4096u);
     int it = 0;
     GemmShape gs;
     gs.M = s.M, gs.N = s.N, gs.K = s.K, gs.m_tiles = s.m_tiles, gs.n_tiles = s.n_tiles, gs.num_kb = s.num_kb;
@@ -832,7 +839,8 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       }
     };
     const bool active = Epi::kSplitColumns || half == 0;
-    const int ec0 = Epi::kSplitColumns ? half * (BN / 64) : 0, ec1 = Epi::kSplitColumns ? (half + 1) * (BN / 64) : BN / 32;
+    constexpr int kChunksPerWarp = (BN / 32) / (kEpiWarps / 4);
+    const int ec0 = Epi::kSplitColumns ? half * kChunksPerWarp : 0, ec1 = Epi::kSplitColumns ? (half + 1) * kChunksPerWarp : BN / 32;
     TileIter cur;
     cur.u = blockIdx.x;
     seek(cur);

@@ -14,6 +14,18 @@ namespace cdml {
 
 constexpr unsigned long long kNoCand = ~0ull;
 
+// epilogue warps of the mining scans: 8 (two per TMEM lane quarter).  CDML_MINE_EPI_WARPS=16 selects four per quarter (A/B
+// measurement aid): measured on B200 it is SLOWER (4.28 vs 4.02 ms structureless, 4.24 vs 3.94 ms clustered for both scans) --
+// the epilogue is not short of warps; see DESIGN.md section 4.4
+static int epi_warps() {
+  static int w = -1;
+  if (w < 0) {
+    const char* e = getenv("CDML_MINE_EPI_WARPS");
+    w = (e != nullptr && e[0] == '1') ? 16 : 8;
+  }
+  return w;
+}
+
 // (1)/(2) collapse into ONE criterion: the chosen row is argmin d over valid candidates with d > dp -- if that minimum
 // is below dp+margin it is the semi-hard pick, otherwise it is exactly the closest beyond-margin pick.
 // Common path per score: d = 2-2s, keep min over (d > dp).  Only when a 32-column chunk can beat the anchor's current
@@ -250,7 +262,9 @@ extern "C" int cdml_mine_semihard(cdml_ctx* ctx, const void* E16, int64_t ld16, 
     if (resb_applicable(D) && B >= 8 * kBM && rowc) {
       EpiMine<kBN, 5> epi5{dp, guid32, best, cand, stats};
       rc = launch_gemm_resb(ctx, e16, 3 * ld16, e16 + cand * ld16, 3 * ld16, B, B, D, dtype16, epi5, st);
-    } else if (resb_applicable(D) && B >= 8 * kBM)
+    } else if (resb_applicable(D) && B >= 8 * kBM && epi_warps() == 16)
+      rc = launch_gemm_resb<EpiMine<kBN, 1>, 16>(ctx, e16, 3 * ld16, e16 + cand * ld16, 3 * ld16, B, B, D, dtype16, epi, st);
+    else if (resb_applicable(D) && B >= 8 * kBM)
       rc = launch_gemm_resb(ctx, e16, 3 * ld16, e16 + cand * ld16, 3 * ld16, B, B, D, dtype16, epi, st);
     else
       rc = launch_gemm<0, 0>(ctx, e16, 3 * ld16, e16 + cand * ld16, 3 * ld16, B, B, D, dtype16, 1, epi, st);

@@ -37,9 +37,18 @@ ap.add_argument("--signal", type=float, default=1.0, help="weight of the cluster
                 "noise_weight * U[0,1)); 1.0 / 0.25 = the well-separated default, 0.3 / 1.0 = clusters the tower has to learn")
 ap.add_argument("--noise", type=float, default=0.25)
 ap.add_argument("--clusters", type=int, default=1000)
+ap.add_argument("--knn-block", type=int, default=262144, help="queries per sharded search call")
 args = ap.parse_args()
-dev = torch.device("cuda:0")
-torch.cuda.set_device(0)
+# one process per GPU under torchrun: the feature table is replicated (every rank generates the same rows from the same
+# seed), every rank trains its own batches (NCCL all-reduce inside the captured step), embeds its slice of the guids,
+# holds its row shard of the index and ends up with the KNN lists of its slice of the queries (written as its own files)
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+dev = torch.device("cuda:%d" % local)
+torch.cuda.set_device(local)
+pg = None
+if world > 1:
+  torch.distributed.init_process_group("nccl", device_id=dev)
+  pg = torch.distributed.group.WORLD
 G, F, B = args.guids, 1500, args.batch
 gen = torch.Generator(device=dev)
 gen.manual_seed(11)
@@ -48,12 +57,14 @@ t = {}
 
 def tick(name, t0):
   torch.cuda.synchronize()
+  if world > 1:
+    torch.distributed.barrier()
   t[name] = time.time() - t0
 
 
 # ---- stage 0: resident feature table (normalised 16-bit, built slab by slab) + guid clusters so that there is a signal
 t0 = time.time()
-eng = engine.TowerEngine([F, 5000, 256], device=dev, base_lr=args.lr, margin=0.8)
+eng = engine.TowerEngine([F, 5000, 256], device=dev, base_lr=args.lr, margin=0.8, process_group=pg)
 table16 = torch.empty((G, eng.F_pad), dtype=eng.t16, device=dev)
 feats32 = None if args.no_desim else torch.empty((G, F), dtype=torch.float32, device=dev)   # features.npy of predict.py:150
 NC = args.clusters
@@ -74,6 +85,8 @@ replay = eng.capture_step(table16, B, mine=args.mine)
 order = torch.argsort(cluster)
 start = torch.searchsorted(cluster[order], torch.arange(NC + 1, device=dev))
 losses = []
+steps = max(1, steps // world)             # `triplets` is the size of the epoch: the ranks share it
+gen.manual_seed(1000 + rank)               # from here on every rank draws its own cowatch pairs
 
 
 def same_cluster_pairs(n):
@@ -108,36 +121,61 @@ for i in range(steps):
 tick("train_s", t0)
 eval_after = eval_dists()
 
-# ---- stage 2: embed every guid (Prediction.run_features on the live engine, batches of 100 000 like predict.py:42)
+# ---- stage 2: embed every guid (Prediction.run_features on the live engine, batches of 100 000 like predict.py:42); with
+#      N ranks every rank embeds its contiguous slice of the rows and one all-gather completes the query set everywhere
 t0 = time.time()
 pred = predict.Prediction(sess=eng)
+glo, ghi = rank * G // world, (rank + 1) * G // world
 emb = torch.empty((G, 256), dtype=torch.float32, device=dev)
-for s in range(0, G, 100000):
-  rows = min(100000, G - s)
+for s in range(glo, ghi, 100000):
+  rows = min(100000, ghi - s)
   x16 = table16[s:s + rows]                                   # already normalised 16-bit rows: forward only
   emb[s:s + rows].copy_(eng.forward_rows(x16, rows)["e"])
+if world > 1:
+  per = (G + world - 1) // world
+  assert G % world == 0, "--guids must be a multiple of the world size"
+  torch.distributed.all_gather_into_tensor(emb, emb[glo:ghi].clone(), group=pg)
 tick("embed_s", t0)
+if world > 1:
+  del replay
+  eng._graph_keepalive = None               # the captured step holds NCCL kernels: release it before the KNN collectives
 
-# ---- stage 3: exact top-k over all embeddings, queries = the index itself (faiss_knn.py:105-106)
+# ---- stage 3: exact top-k over all embeddings, queries = the index itself (faiss_knn.py:105-106).  N ranks: the index is
+#      row-sharded (rank r holds rows [r*G/N, (r+1)*G/N)), every block of queries goes through faiss_knn.sharded_search and
+#      leaves rank r with the lists of ITS slice of the block
 t0 = time.time()
-index = ops.FlatIndex(emb, "L2")
-D = torch.empty((G, args.knn_k), dtype=torch.float32, device=dev)
-I = torch.empty((G, args.knn_k), dtype=torch.int64, device=dev)
-for s in range(0, G, 262144):
-  rows = min(262144, G - s)
-  d_, i_ = index.search(emb[s:s + rows], args.knn_k)
-  D[s:s + rows], I[s:s + rows] = d_, i_
+index = ops.FlatIndex(emb[glo:ghi].contiguous() if world > 1 else emb, "L2")
+blk = args.knn_block if world > 1 else 262144
+nblocks = (G + blk - 1) // blk
+mine_rows = []                              # global query ids of the lists this rank ends up with
+Dl, Il = [], []
+for s in range(0, G, blk):
+  rows = min(blk, G - s)
+  d_, i_ = faiss_knn.sharded_search(index, emb[s:s + rows], args.knn_k, glo, "L2", pg, gather=False)
+  if world > 1:
+    per = -(-rows // world)
+    mine_rows.append(torch.arange(s + rank * per, s + min((rank + 1) * per, rows), device=dev))
+  else:
+    mine_rows.append(torch.arange(s, s + rows, device=dev))
+  Dl.append(d_), Il.append(i_)
   if os.environ.get("CYCLE_DEBUG"):
     print("block %d: stats %s, ids out of range %d, emb finite %s, loss %s" % (s, index.last_stats(), int(((i_ < -1) | (i_ >= G)).sum().item()),
           bool(torch.isfinite(emb[s:s + rows]).all().item()), losses[-3:]), file=sys.stderr, flush=True)
+D, I, qrows = torch.cat(Dl), torch.cat(Il), torch.cat(mine_rows)
+del Dl, Il
 stats = index.last_stats()
 tick("knn_s", t0)
-same_cluster = float((cluster[I[:, 1:6]] == cluster[:, None]).float().mean().item())
-self_first = float((I[:, 0] == torch.arange(G, device=dev)).float().mean().item())
+same_cluster = (cluster[I[:, 1:6]] == cluster[qrows][:, None]).float().mean()
+self_first = (I[:, 0] == qrows).float().mean()
+if world > 1:
+  both = torch.stack([same_cluster, self_first]) / world
+  torch.distributed.all_reduce(both, group=pg)
+  same_cluster, self_first = both[0], both[1]
+same_cluster, self_first = float(same_cluster.item()), float(self_first.item())
 
 # ---- stage 3b: raw-feature KNN (faiss_knn.py:378) and the de-similarity filter of the embedding lists (iter_desim_mp)
 desim_info = None
-if not args.no_desim:
+if not args.no_desim and world == 1:
   t0 = time.time()
   index.close()
   torch.nn.functional.normalize(feats32, dim=1, out=feats32)            # calc_knn(l2_norm=True): plumbing-level normalisation of the synthetic rows
@@ -158,18 +196,32 @@ if not args.no_desim:
                 "feature_knn_fallback_queries_last_block": fstats["fallback_queries"]}
   I = I_desim
 
-# ---- stage 4: knn_split* files (write_knn format) for the first `write_rows` queries
+# ---- stage 4: knn_split* files (write_knn format) for the first `write_rows` queries this rank holds
 t0 = time.time()
 out_dir = args.out or tempfile.mkdtemp(prefix="cdml_cycle_")
-R = min(args.write_rows, G)
-dm = {i: "g%08d" % i for i in range(G)} if R else {}
-faiss_knn.write_knn(out_dir, split_num=10, D=D[:R].cpu().numpy(), I=I[:R].cpu().numpy(), prefix="knn_split", decode_map=dm)
+R = min(args.write_rows, int(qrows.numel()))
+if R:
+  q0 = int(qrows[0].item())
+  assert bool((qrows[:R] == torch.arange(q0, q0 + R, device=dev)).all().item()) or world > 1
+  dm = {i: "g%08d" % i for i in range(G)} if world == 1 else None
+  if world == 1:
+    faiss_knn.write_knn(out_dir, split_num=10, D=D[:R].cpu().numpy(), I=I[:R].cpu().numpy(), prefix="knn_split", decode_map=dm)
+  else:       # every rank writes its own split file of the rows it holds (consecutive global query ids within a block)
+    table = faiss_knn.GuidTable({i: "g%08d" % i for i in range(G)})
+    os.makedirs(out_dir, exist_ok=True)
+    first_block = min(R, int((qrows[:R] - qrows[0] == torch.arange(R, device=dev)).sum().item()))
+    faiss_knn.write_process(out_dir, rank, q0, D[:first_block].cpu().numpy(), I[:first_block].cpu().numpy(), "knn_split", decode_map=table)
+    R = first_block
 tick("write_s", t0)
-print(json.dumps({"guids": G, "triplets": steps * B, "steps": steps, "knn_k": args.knn_k, "seconds": t,
-                  "train_triplets_per_s": steps * B / t["train_s"], "embed_rows_per_s": G / t["embed_s"],
+if rank == 0:
+  print(json.dumps({"guids": G, "triplets": steps * B * world, "steps_per_rank": steps, "n_gpus": world, "knn_k": args.knn_k, "seconds": t,
+                  "train_triplets_per_s": steps * B * world / t["train_s"], "embed_rows_per_s": G / t["embed_s"],
                   "knn_queries_per_s": G / t["knn_s"], "loss_first_last": [losses[0], losses[-1]], "loss_curve": [round(x, 5) for x in losses],
                   "eval_cowatch_vs_random_pair_dist_before": eval_before, "eval_cowatch_vs_random_pair_dist_after": eval_after,
                   "features": {"signal": args.signal, "noise": args.noise, "clusters": NC, "lr": args.lr},
                   "top5_same_cluster": same_cluster, "self_is_first_neighbour": self_first,
                   "knn_fallback_queries_last_block": stats["fallback_queries"], "mining": bool(args.mine), "desim": desim_info,
-                  "write_rows": R, "write_rows_per_s": R / t["write_s"] if R else None, "out_dir": out_dir}))
+                  "write_rows_per_rank": R, "write_rows_per_s": R / t["write_s"] if R else None, "out_dir": out_dir}))
+if world > 1:
+  torch.distributed.barrier()
+  torch.distributed.destroy_process_group()
