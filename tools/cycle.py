@@ -33,9 +33,9 @@ ap.add_argument("--lr", type=float, default=1e-4, help="Adam base learning rate 
 ap.add_argument("--no-desim", action="store_true", help="skip the raw-feature KNN + de-similarity stage")
 ap.add_argument("--feat-k", type=int, default=26, help="desim_nearest_num (faiss_knn.py:46)")
 ap.add_argument("--mine", action="store_true", help="in-batch semi-hard mining (default: the reference's random negatives)")
-ap.add_argument("--signal", type=float, default=1.0, help="weight of the cluster centre in a feature row (row = signal * centre + "
+ap.add_argument("--centre-weight", type=float, default=1.0, help="weight of the cluster centre in a feature row (row = signal * centre + "
                 "noise_weight * U[0,1)); 1.0 / 0.25 = the well-separated default, 0.3 / 1.0 = clusters the tower has to learn")
-ap.add_argument("--noise", type=float, default=0.25)
+ap.add_argument("--noise-weight", type=float, default=0.25)
 ap.add_argument("--clusters", type=int, default=1000)
 ap.add_argument("--knn-block", type=int, default=262144, help="queries per sharded search call")
 args = ap.parse_args()
@@ -72,7 +72,7 @@ centres = torch.rand((NC, F), generator=gen, device=dev)
 cluster = torch.randint(0, NC, (G,), generator=gen, device=dev)
 for s in range(0, G, 65536):
   rows = min(65536, G - s)
-  slab = args.signal * centres[cluster[s:s + rows]] + args.noise * torch.rand((rows, F), generator=gen, device=dev)
+  slab = args.centre_weight * centres[cluster[s:s + rows]] + args.noise_weight * torch.rand((rows, F), generator=gen, device=dev)
   eng.prepare_table(slab, out=table16[s:s + rows])
   if feats32 is not None:
     feats32[s:s + rows] = slab
@@ -218,7 +218,7 @@ if rank == 0:
                   "train_triplets_per_s": steps * B * world / t["train_s"], "embed_rows_per_s": G / t["embed_s"],
                   "knn_queries_per_s": G / t["knn_s"], "loss_first_last": [losses[0], losses[-1]], "loss_curve": [round(x, 5) for x in losses],
                   "eval_cowatch_vs_random_pair_dist_before": eval_before, "eval_cowatch_vs_random_pair_dist_after": eval_after,
-                  "features": {"signal": args.signal, "noise": args.noise, "clusters": NC, "lr": args.lr},
+                  "features": {"signal": args.centre_weight, "noise": args.noise_weight, "clusters": NC, "lr": args.lr},
                   "top5_same_cluster": same_cluster, "self_is_first_neighbour": self_first,
                   "knn_fallback_queries_last_block": stats["fallback_queries"], "mining": bool(args.mine), "desim": desim_info,
                   "write_rows_per_rank": R, "write_rows_per_s": R / t["write_s"] if R else None, "out_dir": out_dir}))
