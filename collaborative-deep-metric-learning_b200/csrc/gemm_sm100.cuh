@@ -155,6 +155,7 @@ struct EpiStoreF32 {
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
   static constexpr bool kPrefetchNext = false;
   static constexpr bool kRowConsts = false;
+  static constexpr bool kEarlyRelease = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -201,6 +202,7 @@ struct EpiStore16 {
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
   static constexpr bool kPrefetchNext = false;
   static constexpr bool kRowConsts = false;
+  static constexpr bool kEarlyRelease = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -248,6 +250,7 @@ struct EpiL2Norm {
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
   static constexpr bool kPrefetchNext = false;
   static constexpr bool kRowConsts = false;
+  static constexpr bool kEarlyRelease = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -311,6 +314,7 @@ struct EpiMaskLeaky {
   };
   static constexpr bool kPrefetchNext = false;
   static constexpr bool kRowConsts = false;
+  static constexpr bool kEarlyRelease = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -407,6 +411,7 @@ struct EpiMaskBits {
   };
   static constexpr bool kPrefetchNext = true;
   static constexpr bool kRowConsts = false;
+  static constexpr bool kEarlyRelease = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -461,6 +466,7 @@ struct EpiNull {
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
   static constexpr bool kPrefetchNext = false;
   static constexpr bool kRowConsts = false;
+  static constexpr bool kEarlyRelease = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -869,11 +875,16 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       if (active) {
         if constexpr (!Epi::kRowConsts)
           if (Epi::kPrefetchNext && nxt.valid) epi.pre(est_next, nxt.t * kBM + q * 32 + lane, nxt.nblk * BN, gs, ec0, ec1, stg);
+        // kEarlyRelease: the epilogue hands the accumulator buffer back itself, right after its LAST TMEM read (it still
+        // has that chunk to process from registers): the MMA of the tile after next starts that much earlier
+        if constexpr (Epi::kEarlyRelease) est.release_bar = tempty_bar(as);
         epi.run(taddr, cur.t * kBM + q * 32 + lane, cur.nblk * BN, 0, gs, ec0, ec1, stg, est);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (!(Epi::kEarlyRelease && active)) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      }
       if (active && nxt.valid) {
         epi.cols(nxt.nblk * BN, gs, ec0, ec1, stg);   // the previous tile no longer reads the column cache
         if constexpr (!Epi::kRowConsts)

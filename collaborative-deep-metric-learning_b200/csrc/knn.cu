@@ -55,6 +55,7 @@ struct EpiKnnGroupMax {
   static constexpr bool kSplitColumns = true;
   static constexpr bool kPrefetchNext = false;
   static constexpr bool kRowConsts = false;
+  static constexpr bool kEarlyRelease = false;
   struct State {};
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t epi_smem) const { col_cache_reset(epi_smem); }
@@ -126,9 +127,11 @@ struct EpiKnnCollect {
   unsigned int warp_cap;
   struct State {
     float hr;
+    uint32_t release_bar;   // resident-B kernel: the accumulator buffer's "empty" barrier (0: the kernel arrives itself)
   };
   static constexpr bool kPrefetchNext = true;   // pre() only loads a row constant into registers
   static constexpr bool kRowConsts = false;
+  static constexpr bool kEarlyRelease = true;  
   __device__ __forceinline__ void block_begin(uint32_t epi_smem) const {
     col_cache_reset(epi_smem);
     for (int w = 0; w < kKnnLogsPerCta; ++w)
@@ -145,6 +148,7 @@ struct EpiKnnCollect {
   // the row's half norm does not depend on the accumulator (issued one tile ahead by the resident-B kernel)
   __device__ __forceinline__ void pre(State& st, int row, int, const GemmShape& s, int, int, uint32_t) const {
     st.hr = row < s.M ? __ldg(h + row) : pos_inf();   // rows beyond M: score -inf, never pass
+    st.release_bar = 0u;
   }
   // the bounds of the warp's 128 columns (queries), once per column block; beyond N: +inf, never pass
   __device__ __forceinline__ void cols(int n0, const GemmShape& s, int c0, int /*c1*/, uint32_t stg) const {
@@ -214,6 +218,11 @@ struct EpiKnnCollect {
       if (ok0) chunk(va, cc);
       tmem_ld_wait();
       if (ok2) tmem_ld_32x32(taddr + (c0 + cc + 2) * 32, va);
+      if (cc + 2 >= 4 && st.release_bar != 0u) {   // the last TMEM read of this warp has landed: hand the buffer back now
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(st.release_bar);
+      }
       if (ok1) chunk(vb, cc + 1);
     }
     __syncwarp();

@@ -43,7 +43,9 @@ struct EpiMine {
     float dpi, bound_d;
     int ga, gp;
     uint32_t bound_row;   // row of the anchor's best candidate so far (ties -> lowest row)
+    uint32_t release_bar; // resident-B kernel: the accumulator buffer's "empty" barrier (0: the kernel arrives itself)
   };
+  static constexpr bool kEarlyRelease = true;
   const float* dp;        // [B] exact |a-p|^2
   const int32_t* guid;    // [B,3] int32 guids
   unsigned long long* best;  // [B] (float bits of d) << 32 | row
@@ -63,6 +65,7 @@ struct EpiMine {
     const uint4 v = lds128(src);
     st.dpi = __uint_as_float(v.x), st.ga = static_cast<int>(v.y), st.gp = static_cast<int>(v.z), st.bound_d = __uint_as_float(v.w);
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(st.bound_row) : "r"(src + 16) : "memory");
+    st.release_bar = 0u;
   }
   // the anchor's constants do not depend on the accumulator: the resident-B kernel issues them one tile ahead
   __device__ __forceinline__ void pre(State& st, int row, int /*n0*/, const GemmShape& s, int, int, uint32_t) const {
@@ -74,6 +77,7 @@ struct EpiMine {
     const unsigned long long key = row_ok ? best[row] : ~0ull;
     st.bound_d = __uint_as_float(static_cast<uint32_t>(key >> 32));   // empty key reads as NaN
     st.bound_row = static_cast<uint32_t>(key);
+    st.release_bar = 0u;
   }
   // candidate guids of the warp's 128 columns, once per column block (-1 beyond N: the re-scan skips them)
   __device__ __forceinline__ void cols(int n0, const GemmShape& s, int c0, int /*c1*/, uint32_t stg) const {
@@ -164,6 +168,11 @@ struct EpiMine {
         if (ok(cc)) chunk(va, cc);
         tmem_ld_wait();
         if (cc + 2 < 4 && ok(cc + 2)) tmem_ld_32x32(taddr + (c0 + cc + 2) * 32, va);
+        if (cc + 2 >= 4 && st.release_bar != 0u) {   // every TMEM read of this warp has landed: release the buffer now
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(st.release_bar);
+        }
         if (ok(cc + 1)) chunk(vb, cc + 1);
       }
     } else {
@@ -174,6 +183,11 @@ struct EpiMine {
           tmem_ld_wait();
           chunk(va, cc);
         }
+      }
+      if (st.release_bar != 0u) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(st.release_bar);
       }
     }
     if (br >= 0)

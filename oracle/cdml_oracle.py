@@ -22,12 +22,23 @@ Pinning status (see DESIGN.md "Oracle"):
   * fusion towers (fusion_spec / graph_forward / graph_backward): **parity
     unpinned** like the chain tower (TensorFlow ops); cross-checked by torch
     autograd of the same forward to 1e-12.
-  * tower forward/backward, TF1 Adam, flat KNN: **parity unpinned** -- the
-    arithmetic lives in tensorflow-gpu==1.13.1 and faiss-gpu==1.5.x
-    (README.md:19-22), neither vendored nor installable here.  The oracle
-    restates their published semantics and is cross-checked by torch autograd,
-    finite differences and a second, independent exact-KNN statement
-    (show_knn.py:63-68).
+  * exact flat KNN ids (flat_knn, L2 and IP): pinned against the ids returned
+    by the reference's OWN brute force, show_knn.calc_nn (show_knn.py:63-79),
+    executed in the build container under cv2/matplotlib import shims
+    (tests/golden/make_knn_golden.py -> knn_ids_golden.npz), and against
+    scikit-learn's brute-force NearestNeighbors as a third statement.  faiss
+    itself (faiss-gpu==1.5.x, README.md:22) is not installable here: distances
+    and the -1/inf padding follow its published IndexFlat semantics.
+  * tower forward/backward, TF1 Adam / Momentum / LARS (tensorflow r1.13 form),
+    clip_by_norm, l2_regularizer: **parity unpinned** -- the arithmetic lives
+    in tensorflow-gpu==1.13.1 (README.md:19-21), neither vendored nor
+    installable here.  The oracle restates the published semantics and is
+    cross-checked by torch autograd, torch's Nesterov SGD, finite differences
+    and closed forms.
+  * precision models (tower_grads_emulated16, mine_semihard_emulated16,
+    OracleTrainer(emulate16=...)): the same statements with operands rounded
+    to fp16 / bf16 exactly where the kernels store them -- what the GPU tests
+    gate the 16-bit kernels against next to the unrounded float64 oracle.
 
 Every function cites the reference file:line it follows.  Default dtype is
 float64 ("what the maths says"); pass ``dtype=np.float32`` for the bit-level

@@ -14,7 +14,7 @@ col = {h: i for i, h in enumerate(hdr)}
 
 
 def val(r, name, scale=1.0):
-  if name not in col or r[col[name]] in ("", "n/a"):
+  if name not in col or r[col[name]] in ("", "n/a", "no data"):
     return None
   x = float(r[col[name]].replace(",", ""))
   u = units[col[name]]
@@ -45,6 +45,7 @@ for r in rows[2:]:
               "warps_active_pct": val(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
               "inst_executed": val(r, "smsp__inst_executed.sum"),
               "tensor_pipe_active_pct": val(r, "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active"),
+              "tensor_cycles_active_pct": val(r, "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"),
               "lts_hit_rate_pct": val(r, "lts__t_sector_hit_rate.pct"),
               "shared_bank_conflicts": val(r, "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
               "registers_per_thread": val(r, "launch__registers_per_thread"),
