@@ -1136,7 +1136,8 @@ static int ensure_workspace(cdml_index* ix, int64_t qc) {
 //   search          (ext_full == nullptr, out_full == nullptr): bound pass + collect + refine, self-contained;
 //   bounds only     (out_full != nullptr): bound pass; writes the raw k_full-th / k_part-th best sampled scores per query;
 //   bounded search  (ext_full != nullptr): skips the bound pass, collects above max(ext_full, ext_part) - slack.
-//   row-sharded protocol (one chunk of <= 32768 queries per call, the workspace carries the nominees between the calls):
+//   row-sharded protocol (one chunk of <= 65536 queries per call, the workspace carries the nominees between the calls;
+//   a larger chunk than the self-contained search's 32768 because every chunk costs the shards two all-reduces):
 //     phase 1 = cast + [bounded] collect + bin, then the nominee selection into nom_pair;  phase 2 = refine only, pruning
 //     against prune_pair (the all-reduced nom_pair).  part_sign = -1: the `part` bounds travel negated (packed MAX all-reduce).
 static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k, float* D, int64_t* I,
@@ -1144,13 +1145,14 @@ static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, in
                    float* out_full, float* out_part, int phase = 0, float part_sign = 1.f, float* nom_pair = nullptr,
                    const float* prune_pair = nullptr) {
   const bool bounds_only = out_full != nullptr;
-  CDML_REQUIRE(phase == 0 || nq <= 32768, "cdml_knn_shard_*: one chunk of at most 32768 queries per call (got %lld)", (long long)nq);
+  CDML_REQUIRE((phase == 0 && !(bounds_only && part_sign < 0.f)) || nq <= 65536,
+               "cdml_knn_shard_*: one chunk of at most 65536 queries per call (got %lld)", (long long)nq);
   CDML_REQUIRE(ctx && ix && Q && (bounds_only || phase == 1 || (D && I)), "cdml_knn_search: NULL argument");
   CDML_REQUIRE(nq >= 0 && ldq >= ix->d && k >= 1 && k <= 1024, "cdml_knn_search: bad arguments (k=%d, supported 1..1024)", k);
   CDML_REQUIRE(k <= kKeepCap / 2, "cdml_knn_search: k=%d exceeds the re-rank capacity %d", k, kKeepCap / 2);
   if (nq == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t chunk = std::min<int64_t>(nq, 32768);
+  const int64_t chunk = std::min<int64_t>(nq, (phase != 0 || (bounds_only && part_sign < 0.f)) ? 65536 : 32768);
   int rc = ensure_workspace(ix, chunk);
   if (rc) { set_error("cdml_knn_search: workspace allocation failed"); return rc; }
   if (phase != 2) ix->stats[0] = ix->stats[1] = 0;
@@ -1334,7 +1336,7 @@ int cdml_knn_search_bounded(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64
   return knn_run(ctx, ix, Q, nq, ldq, k, D, I, id_offset, stream, bound_full, bound_part, k, nullptr, nullptr);
 }
 
-// ---- row-sharded protocol, one chunk (<= 32768 queries) per call -------------------------------------------------
+// ---- row-sharded protocol, one chunk (<= 65536 queries) per call -------------------------------------------------
 int cdml_knn_shard_bounds(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k, int k_part,
                           float* pair, void* stream) {
   CDML_REQUIRE(pair && k_part >= 1, "cdml_knn_shard_bounds: NULL / bad argument");

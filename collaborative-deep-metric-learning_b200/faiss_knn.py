@@ -57,7 +57,7 @@ def sharded_search(index, xq, k, id_offset=0, metric="L2", process_group=None, m
                    merge_packed_fn=None):
   """Top-k of the (replicated) queries `xq` over a row-sharded index; device tensors in and out.
 
-  Per chunk of <= 32768 queries, one collective per phase (each an all-reduce MAX of a [2,n] fp32 pair):
+  Per chunk of <= 65536 queries, one collective per phase (each an all-reduce MAX of a [2,n] fp32 pair):
     1. bound pass on every shard -> all-reduce: max over shards of their k-th best sampled score / min of their
        ceil(k/W)-th best -- one collection bound per query, so that together the shards nominate about as many candidates
        as one unsharded index would instead of W times as many;

@@ -358,8 +358,8 @@ class FlatIndex(object):
                                               ptr(bound_part), ptr(D), ptr(I), int(id_offset), stream_ptr()))
     return D, I
 
-  # ---- row-sharded protocol, one chunk (<= 32768 queries) per call; see include/cdml.h
-  CHUNK = 32768
+  # ---- row-sharded protocol, one chunk (<= 65536 queries) per call; see include/cdml.h
+  CHUNK = 65536
 
   def shard_bounds(self, xq, k, k_part, pair=None):
     nq = xq.shape[0]

@@ -184,7 +184,7 @@ int cdml_knn_merge(cdml_ctx* ctx, const float* Dg, const int64_t* Ig, int G, int
                    int64_t* I, void* stream);
 
 /* Row-sharded index, protocol with ONE collective per phase (faiss_knn.sharded_search; the three calls process one chunk of
- * at most 32768 queries and share the index workspace, so they must follow each other on one stream):
+ * at most 65536 queries and share the index workspace, so they must follow each other on one stream):
  *   cdml_knn_shard_bounds   pair[0][q] = k-th best sampled score of this shard, pair[1][q] = -(k_part-th best)  (-inf / +inf
  *                           without a usable sample)                                       -> caller: all-reduce MAX of pair
  *   cdml_knn_shard_collect  collects the rows above max(pair[0], -pair[1]) - slack and writes nom_pair[0][q] = k-th best
