@@ -13,6 +13,7 @@
 namespace cdml {
 
 constexpr unsigned long long kNoCand = ~0ull;
+constexpr int kMassHits = 4;   // rows of a warp hitting in one chunk from which the per-thread re-scan takes over
 
 // epilogue warps of the mining scans: 8 (two per TMEM lane quarter).  CDML_MINE_EPI_WARPS=16 selects four per quarter (A/B
 // measurement aid): measured on B200 it is SLOWER (4.28 vs 4.02 ms structureless, 4.24 vs 3.94 ms clustered for both scans) --
@@ -125,7 +126,34 @@ struct EpiMine {
       // Re-scan (rare once the anchors' bounds have tightened): the triggering row's 32 scores go through the warp's
       // staging slice so that lane j examines column j -- compact code (the former per-thread unrolled scan made the
       // kernel 70 KB of SASS and the epilogue instruction-cache bound), same selection: minimum d, ties -> lowest row.
-      if (hits != 0u) {
+      if (hits != 0u && __popc(hits) >= kMassHits) {
+        // Many rows of the warp hit at once -- the first visits of a scan, when the anchors' bounds are still loose (all
+        // 32 rows on the very first): one cooperative re-scan per row would serialise up to 32 x ~70 warp instructions.
+        // Here every hitting THREAD scans its own 32 scores in registers, all rows in parallel, with exactly the same
+        // conditions and tie rule (minimum d, lowest column).  The guids of the 32 columns are broadcast reads of the
+        // column cache.  Used only above kMassHits rows, so the unrolled code stays off the common path's instruction stream.
+        if (lane == 0) atomicAdd(stats, static_cast<unsigned long long>(__popc(hits)));
+        if ((hits >> lane) & 1u) {
+          uint32_t kbest = 0xffffffffu;
+          int cbest = -1;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            int g;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(g) : "r"(stg + kColCacheOff + 128 * cc + 4 * j) : "memory");
+            const float sc = __uint_as_float(v[j]);
+            const float d = fmaxf(fmaf(-2.f, sc, 2.f), 0.f);
+            const bool pass = sc < s_hi && sc >= s_lo && d > dpi && d < bd && g != ga && g != gp && g >= 0;
+            if (pass && __float_as_uint(d) < kbest) kbest = __float_as_uint(d), cbest = j;
+          }
+          if (cbest >= 0) {
+            bd = __uint_as_float(kbest), br = 3 * (nb + cbest) + cand;
+            const float s_new = 1.f - 0.5f * bd;
+            if (s_new > s_lo || (s_new == s_lo && static_cast<uint32_t>(br) < brow)) brow = static_cast<uint32_t>(br);
+            s_lo = fmaxf(s_lo, s_new);
+          }
+        }
+        __syncwarp();
+      } else if (hits != 0u) {
         if (lane == 0) atomicAdd(stats, static_cast<unsigned long long>(__popc(hits)));
         int g_lane;   // candidate guid of column nb + lane (column cache)
         asm volatile("ld.shared.b32 %0, [%1];" : "=r"(g_lane) : "r"(stg + kColCacheOff + 128 * cc + 4 * lane) : "memory");
