@@ -554,7 +554,10 @@ def main():
                   "note": "host INDEX triplets in, loss out; the feature table stays resident in HBM (SURVEY 8b). The drop-in "
                           "get_batch() float path (host features in) is timed separately: key get_batch_e2e"},
           "gpu_launches": int(launches), "clocks": clocks, "loss_last_step": loss_last,
-          "tflops_per_gpu": flop_triplet * value / world / 1e12}
+          "tflops_per_gpu": flop_triplet * value / world / 1e12,
+          "knn_summary": None,       # second BASELINE metric: filled below, kept EARLY in the line (record tails are truncated)
+          "roofline_summary": {"kernel": roofline["kernel"], "frac": roofline["frac"], "achieved": roofline["achieved"],
+                               "peak": roofline["peak"], "unit": roofline["unit"], "step_tensor_frac": roofline["step_tensor_frac"]}}
 
   # ---- N>1: what the ranks computed, not only how fast (weights bit-identical after the timed steps)
   if world > 1:
@@ -751,7 +754,9 @@ def main():
                                           "(rows of the index)" % (N, d, world, nq)},
                    "ms": kms, "tflops": 2.0 * nq * N * d / kms / 1e9, "e2e": {"value": ke2e, "unit": "queries/s",
                    "h2d_bytes": nq * d * 4, "d2h_bytes": nq * k * 12},
-                   "candidates_per_query_rank0": st["candidates"] / nq, "fallback_queries_rank0": st["fallback_queries"],
+                   # (N>1: the shard protocol defers its overflow check and keeps no host-side counters)
+                   "candidates_per_query_rank0": st["candidates"] / nq if world == 1 else None,
+                   "fallback_queries_rank0": st["fallback_queries"] if world == 1 else None,
                    "self_is_first_neighbour": self_first,
                    "roofline": {"bound": "tensor", "achieved": 2.0 * nq * N * d / kms / 1e9 / world,
                                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s (per GPU)",

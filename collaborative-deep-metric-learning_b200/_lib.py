@@ -58,7 +58,7 @@ _SIGNATURES = {
   "cdml_knn_merge": (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P, _P]),
   "cdml_knn_shard_bounds": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P]),
   "cdml_knn_shard_collect": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P]),
-  "cdml_knn_shard_refine": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, c_int64, _P]),
+  "cdml_knn_shard_refine": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, c_int64, _P, _P]),
   "cdml_knn_merge_packed": (c_int, [_P, _P, c_int, c_int64, c_int, c_int, _P, _P, _P, _P]),
   "cdml_knn_unpack_records": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P]),
   "cdml_mean_pair_dist": (c_int, [_P, _P, c_int64, c_int, _P, c_int64, _P, _P]),

@@ -908,6 +908,13 @@ knn_merge_kernel(const float* __restrict__ Dg, const int64_t* __restrict__ Ig, i
   }
 }
 
+__global__ void knn_any_overflow_kernel(const int32_t* __restrict__ overflow, int64_t n, const int32_t* __restrict__ log_overflow,
+                                        int32_t* __restrict__ flag) {
+  int any = (threadIdx.x == 0 && *log_overflow != 0) ? 1 : 0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) any |= overflow[i] != 0 ? 1 : 0;
+  if (__syncthreads_or(any) && threadIdx.x == 0) *flag = 1;
+}
+
 // (D, I) lists -> one sortable 64-bit record per entry: (order-preserving distance key << 32) | global id; padding
 // (id < 0) -> ~0.  One record array makes the shard exchange ONE all-to-all of 8 bytes per entry instead of two of 4 + 8.
 __global__ void knn_pack_kernel(const float* __restrict__ D, const int64_t* __restrict__ I, int64_t n, int metric,
@@ -1143,7 +1150,7 @@ static int ensure_workspace(cdml_index* ix, int64_t qc) {
 static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k, float* D, int64_t* I,
                    int64_t id_offset, void* stream, const float* ext_full, const float* ext_part, int k_part,
                    float* out_full, float* out_part, int phase = 0, float part_sign = 1.f, float* nom_pair = nullptr,
-                   const float* prune_pair = nullptr) {
+                   const float* prune_pair = nullptr, int32_t* defer_flag = nullptr) {
   const bool bounds_only = out_full != nullptr;
   CDML_REQUIRE((phase == 0 && !(bounds_only && part_sign < 0.f)) || nq <= 65536,
                "cdml_knn_shard_*: one chunk of at most 65536 queries per call (got %lld)", (long long)nq);
@@ -1270,6 +1277,14 @@ static int knn_run(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, in
                                     cudaMemcpyDeviceToHost, st));
   }
   if (bounds_only || phase == 1) return 0;
+  if (defer_flag != nullptr) {
+    // deferred check (row-sharded protocol): no host synchronisation here.  Whether ANY query of this call overflowed its
+    // candidate list or a warp log goes into the caller's device word; the caller looks at it once, after the exchange
+    // that follows, and only then repeats the search synchronously (exact fallback) -- the common case never stalls.
+    knn_any_overflow_kernel<<<1, 1024, 0, st>>>(ix->overflow, nq, ix->log_count + ctx->num_sms * kKnnLogsPerCta, defer_flag);
+    CDML_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   CDML_CHECK_CUDA(cudaStreamSynchronize(st));
   // queries whose candidate list (or whose chunk's warp log) overflowed are redone exactly in fp32, all in one launch
   std::vector<int32_t> redo;
@@ -1351,7 +1366,8 @@ int cdml_knn_shard_collect(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_
 }
 
 int cdml_knn_shard_refine(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t nq, int64_t ldq, int k,
-                          const float* nom_pair, unsigned long long* rec, int64_t id_offset, void* stream) {
+                          const float* nom_pair, unsigned long long* rec, int64_t id_offset, int32_t* overflow_flag,
+                          void* stream) {
   CDML_REQUIRE(ix && rec, "cdml_knn_shard_refine: NULL argument");
   CDML_REQUIRE(id_offset >= 0 && id_offset + ix->N <= (1ll << 32) - 1, "cdml_knn_shard_refine: global ids must fit 32 bits");
   if (ix->tmp_cap < nq * k) {
@@ -1361,7 +1377,7 @@ int cdml_knn_shard_refine(cdml_ctx* ctx, cdml_index* ix, const float* Q, int64_t
     ix->tmp_cap = nq * k;
   }
   int rc = knn_run(ctx, ix, Q, nq, ldq, k, ix->Dtmp, ix->Itmp, id_offset, stream, nullptr, nullptr, k, nullptr, nullptr, 2, -1.f,
-                   nullptr, nom_pair);
+                   nullptr, nom_pair, overflow_flag);
   if (rc) return rc;
   const int64_t n = nq * k;
   knn_pack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ix->Dtmp, ix->Itmp, n, ix->metric, rec);

@@ -54,7 +54,7 @@ def _device():
 
 
 def sharded_search(index, xq, k, id_offset=0, metric="L2", process_group=None, merge_fn=None, gather=True,
-                   merge_packed_fn=None):
+                   merge_packed_fn=None, _sync_refine=False):
   """Top-k of the (replicated) queries `xq` over a row-sharded index; device tensors in and out.
 
   Per chunk of <= 65536 queries, one collective per phase (each an all-reduce MAX of a [2,n] fp32 pair):
@@ -68,7 +68,10 @@ def sharded_search(index, xq, k, id_offset=0, metric="L2", process_group=None, m
   Then ONE all-to-all: rank r receives every shard's lists for ITS slice of the queries and merges them on the GPU
   (cdml_knn_merge_packed, ties -> lower id).  gather=True completes the result on every rank with one all-gather;
   gather=False returns (D, I) of this rank's query slice [r*nq/W, (r+1)*nq/W) only -- what a caller that writes its own
-  knn_split files needs."""
+  knn_split files needs.
+  The whole protocol is enqueued without a host round trip: a query whose candidate list overflows (dense near-tie bands)
+  only sets a device flag, the ranks agree on it with one 4-byte all-reduce after the exchange, and in that rare case the
+  search is repeated with the synchronous refine that redoes such queries exactly."""
   world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
   if world == 1:
     return index.search(xq, k, id_offset=id_offset)
@@ -82,16 +85,27 @@ def sharded_search(index, xq, k, id_offset=0, metric="L2", process_group=None, m
     xq = torch.cat([xq, xq[-1:].expand(pad, -1)], 0)
   nqp = nq + pad
   rec = torch.empty((nqp, k), dtype=torch.int64, device=xq.device)
+  deferred = merge_packed_fn is None and not _sync_refine       # (the CPU stand-in of the gloo test has no deferred mode)
+  flag = torch.zeros((1,), dtype=torch.int32, device=xq.device) if deferred else None
   for s in range(0, nqp, index.CHUNK):
     q = xq[s:s + index.CHUNK]
     pair = index.shard_bounds(q, k, k_part)
     dist.all_reduce(pair, op=dist.ReduceOp.MAX, group=process_group)
     nom = index.shard_collect(q, k, k_part, pair)
     dist.all_reduce(nom, op=dist.ReduceOp.MAX, group=process_group)
-    index.shard_refine(q, k, nom, rec[s:s + index.CHUNK], id_offset=id_offset)
+    if deferred:
+      index.shard_refine(q, k, nom, rec[s:s + index.CHUNK], id_offset=id_offset, overflow_flag=flag)
+    else:
+      index.shard_refine(q, k, nom, rec[s:s + index.CHUNK], id_offset=id_offset)
   got = torch.empty_like(rec)                # [W, nqp/W, k]: every shard's lists for my query slice
   dist.all_to_all_single(got, rec, group=process_group)
   got = got.view(world, nqp // world, k)
+  if deferred:
+    out = _finish_sharded(got, nq, nqp, k, world, metric, process_group, gather, xq.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=process_group)
+    if int(flag.item()) != 0:                # some shard overflowed somewhere: redo with the exact fallback (rare)
+      return sharded_search(index, xq[:nq], k, id_offset, metric, process_group, merge_fn, gather, merge_packed_fn, _sync_refine=True)
+    return out
   if not gather:
     Dm, Im = (merge_packed_fn or ops.knn_merge_packed)(got, metric)   # (tests: CPU stand-in over gloo)
     rank = dist.get_rank(process_group)
@@ -106,6 +120,21 @@ def sharded_search(index, xq, k, id_offset=0, metric="L2", process_group=None, m
     return D[:nq], I[:nq]
   mine = ops.knn_merge_packed(got, metric, as_records=True)         # merged slice stays packed: ONE all-gather of 8 B / entry
   allr = torch.empty((nqp, k), dtype=torch.int64, device=xq.device)
+  dist.all_gather_into_tensor(allr, mine, group=process_group)
+  D, I = ops.knn_unpack_records(allr, metric)
+  return D[:nq], I[:nq]
+
+
+def _finish_sharded(got, nq, nqp, k, world, metric, process_group, gather, device):
+  """Merge of the received record lists (+ all-gather and unpack when every rank wants the whole result)."""
+  dist = torch.distributed
+  if not gather:
+    Dm, Im = ops.knn_merge_packed(got, metric)
+    rank = dist.get_rank(process_group)
+    lo, hi = rank * (nqp // world), min((rank + 1) * (nqp // world), nq)
+    return Dm[:max(hi - lo, 0)], Im[:max(hi - lo, 0)]
+  mine = ops.knn_merge_packed(got, metric, as_records=True)         # merged slice stays packed: ONE all-gather of 8 B / entry
+  allr = torch.empty((nqp, k), dtype=torch.int64, device=device)
   dist.all_gather_into_tensor(allr, mine, group=process_group)
   D, I = ops.knn_unpack_records(allr, metric)
   return D[:nq], I[:nq]

@@ -379,12 +379,14 @@ class FlatIndex(object):
                                              ptr(pair), ptr(nom_pair), stream_ptr()))
     return nom_pair
 
-  def shard_refine(self, xq, k, nom_pair, rec, id_offset=0):
-    """rec: int64 [nq,k] slice receiving the packed records of this chunk."""
+  def shard_refine(self, xq, k, nom_pair, rec, id_offset=0, overflow_flag=None):
+    """rec: int64 [nq,k] slice receiving the packed records of this chunk.  overflow_flag (device int32 [1]): deferred
+    overflow check -- no host synchronisation; the word becomes 1 if a query overflowed (the caller then repeats the
+    search without the flag)."""
     nq = xq.shape[0]
-    _count(2)
+    _count(3)
     check(_lib.load().cdml_knn_shard_refine(_ctx(xq), self._h, ptr(xq), nq, _row_major_2d(xq, "xq"), int(k), ptr(nom_pair),
-                                            ptr(rec), int(id_offset), stream_ptr()))
+                                            ptr(rec), int(id_offset), ptr(overflow_flag), stream_ptr()))
     return rec
 
   def last_stats(self):

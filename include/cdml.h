@@ -195,6 +195,10 @@ int cdml_knn_merge(cdml_ctx* ctx, const float* Dg, const int64_t* Ig, int G, int
  *                           shards*k -- and writes this shard's (possibly shorter than k) sorted list as 64-bit records
  *                           rec[q][j] = (order-preserving distance key << 32) | global id, padding = ~0
  *                                                                                          -> caller: all-to-all of rec
+ *                           overflow_flag NULL: synchronises the stream and redoes queries whose candidate list overflowed
+ *                           exactly (like cdml_knn_search).  Non-NULL (device int32): NO host synchronisation -- the word is
+ *                           set to 1 if any query overflowed and the caller, after its exchange, repeats the search with
+ *                           NULL in that (rare) case; the common case runs the whole protocol without a host round trip
  *   cdml_knn_merge_packed   k-way merge of G <= 32 record lists [G,nq,k] -> D, I [nq,k] (ties -> lower id), or -- rec_out
  *                           non-NULL -- the merged list as records [nq,k] (the caller all-gathers ONE 8-byte array and
  *                           cdml_knn_unpack_records turns records into D fp32 / I int64).
@@ -204,7 +208,8 @@ int cdml_knn_shard_bounds(cdml_ctx* ctx, cdml_index* index, const float* Q, int6
 int cdml_knn_shard_collect(cdml_ctx* ctx, cdml_index* index, const float* Q, int64_t nq, int64_t ldq, int k, int k_part,
                            const float* pair, float* nom_pair, void* stream);
 int cdml_knn_shard_refine(cdml_ctx* ctx, cdml_index* index, const float* Q, int64_t nq, int64_t ldq, int k,
-                          const float* nom_pair, unsigned long long* rec, int64_t id_offset, void* stream);
+                          const float* nom_pair, unsigned long long* rec, int64_t id_offset, int32_t* overflow_flag,
+                          void* stream);
 int cdml_knn_merge_packed(cdml_ctx* ctx, const unsigned long long* rec, int G, int64_t nq, int k, int metric, float* D,
                           int64_t* I, unsigned long long* rec_out, void* stream);
 int cdml_knn_unpack_records(cdml_ctx* ctx, const unsigned long long* rec, int64_t n, int metric, float* D, int64_t* I,

@@ -627,6 +627,48 @@ def test_sharded_record_protocol_prunes_against_the_global_bound(cd, metric, W):
     ix.close()
 
 
+def test_sharded_refine_deferred_overflow_check(cd):
+  """The deferred form of cdml_knn_shard_refine (no host synchronisation): same records as the synchronous form and a
+  clear flag on ordinary data; on an index of near-identical rows (every query's candidate list overflows) the flag is
+  raised -- the caller then repeats the search synchronously, which redoes those queries exactly."""
+  rng = np.random.RandomState(17)
+  N, nq, k = 30000, 300, 50
+  X = O.knn_normalize(rng.standard_normal((N, 256)).astype(np.float32))
+  xq = dev_t(cd, X[:nq])
+  ix = cd.ops.FlatIndex(dev_t(cd, X), "L2")
+  pair = ix.shard_bounds(xq, k, k)
+  nom = ix.shard_collect(xq, k, k, pair)
+  rec_sync = torch.empty((nq, k), dtype=torch.int64, device=cd.dev)
+  ix.shard_refine(xq, k, nom, rec_sync)
+  nom = ix.shard_collect(xq, k, k, pair)
+  rec_def = torch.empty((nq, k), dtype=torch.int64, device=cd.dev)
+  flag = torch.zeros((1,), dtype=torch.int32, device=cd.dev)
+  ix.shard_refine(xq, k, nom, rec_def, overflow_flag=flag)
+  assert int(flag.item()) == 0 and torch.equal(rec_def, rec_sync)
+  Dm, Im = cd.ops.knn_merge_packed(rec_def[None], "L2")
+  Dw, Iw = O.flat_knn(X, X[:nq], k=k, l2_norm=False)
+  assert_knn_matches(Dm.cpu().numpy(), Im.cpu().numpy(), Dw, Iw, "L2", X, X[:nq])
+  ix.close()
+  # a collapsed index: 30 000 rows within 1e-4 of one direction -> every row is a nominee of every query
+  base = O.knn_normalize(rng.standard_normal((1, 256)).astype(np.float32))
+  Xc = O.knn_normalize((base + 1e-4 * rng.standard_normal((N, 256))).astype(np.float32))
+  xqc = dev_t(cd, Xc[:64])
+  ixc = cd.ops.FlatIndex(dev_t(cd, Xc), "L2")
+  pair = ixc.shard_bounds(xqc, k, k)
+  nom = ixc.shard_collect(xqc, k, k, pair)
+  rec = torch.empty((64, k), dtype=torch.int64, device=cd.dev)
+  flag.zero_()
+  ixc.shard_refine(xqc, k, nom, rec, overflow_flag=flag)
+  assert int(flag.item()) == 1
+  nom = ixc.shard_collect(xqc, k, k, pair)
+  ixc.shard_refine(xqc, k, nom, rec)                                     # synchronous form: exact fallback inside
+  assert ixc.last_stats()["fallback_queries"] > 0
+  Dm, Im = cd.ops.knn_merge_packed(rec[None], "L2")
+  Dw, Iw = O.flat_knn(Xc, Xc[:64], k=k, l2_norm=False)
+  assert np.allclose(Dm.cpu().numpy(), Dw, atol=2e-6)                    # near-ties everywhere: distances, not ids
+  ixc.close()
+
+
 def test_mean_dist_matches_oracle(cd, golden):
   from cdml_b200.evaluate import Evaluation
   ev = Evaluation(golden["gather_features"], golden["eval_cowatches"].tolist())

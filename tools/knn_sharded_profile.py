@@ -49,13 +49,15 @@ dist.all_reduce(pair, op=dist.ReduceOp.MAX); marks.append(("all_reduce pair", ev
 nom = index.shard_collect(Q, k, k_part, pair); marks.append(("shard_collect", ev()))
 dist.all_reduce(nom, op=dist.ReduceOp.MAX); marks.append(("all_reduce nom", ev()))
 rec = torch.empty((nq, k), dtype=torch.int64, device=dev)
-index.shard_refine(Q, k, nom, rec, id_offset=lo); marks.append(("shard_refine (host sync inside)", ev()))
+flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+index.shard_refine(Q, k, nom, rec, id_offset=lo, overflow_flag=flag); marks.append(("shard_refine (deferred check)", ev()))
 got = torch.empty_like(rec)
 dist.all_to_all_single(got, rec); marks.append(("all_to_all records", ev()))
 mine = ops.knn_merge_packed(got.view(world, nq // world, k), "L2", as_records=True); marks.append(("merge", ev()))
 allr = torch.empty((nq, k), dtype=torch.int64, device=dev)
 dist.all_gather_into_tensor(allr, mine); marks.append(("all_gather", ev()))
 D, I = ops.knn_unpack_records(allr, "L2"); marks.append(("unpack", ev()))
+dist.all_reduce(flag, op=dist.ReduceOp.MAX); marks.append(("all_reduce overflow flag", ev()))
 torch.cuda.synchronize()
 t_host = (time.perf_counter() - t_host0) * 1e3
 if rank == 0:
