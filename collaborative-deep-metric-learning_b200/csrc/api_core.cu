@@ -16,7 +16,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int make_tmap_2d(cdml_ctx* ctx, CUtensorMap* map, const void* ptr, int dtype16, uint64_t inner, uint64_t outer,
-                 uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+                 uint64_t ld, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
   CDML_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand base %p is not 16-byte aligned", ptr);
   CDML_REQUIRE((ld * 2) % 16 == 0, "TMA operand pitch %llu elements is not a multiple of 16 bytes",
                (unsigned long long)ld);
@@ -27,7 +27,8 @@ int make_tmap_2d(cdml_ctx* ctx, CUtensorMap* map, const void* ptr, int dtype16, 
   cuuint32_t estr[2] = {1, 1};
   CUresult r = ctx->encode_tiled(map, dtype16 == CDML_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                                  2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CDML_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu)", (int)r,
                (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);

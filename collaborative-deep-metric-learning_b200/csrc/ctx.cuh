@@ -23,7 +23,8 @@ void* ctx_scratch(cdml_ctx* ctx, size_t bytes);
 
 namespace cdml {
 // 2-D tensor map over a row-major 16-bit matrix: `inner` contiguous elements, `outer` rows of pitch ld elements.
-// 128-byte swizzle, zero fill out of bounds.
+// 128-byte swizzle (operand tiles) or 64-byte swizzle (the 32 x 64-byte store boxes of the epilogues); zero fill / clipping
+// out of bounds.
 int make_tmap_2d(cdml_ctx* ctx, CUtensorMap* map, const void* ptr, int dtype16, uint64_t inner, uint64_t outer,
-                 uint64_t ld, uint32_t box_inner, uint32_t box_outer);
+                 uint64_t ld, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes = 128);
 }  // namespace cdml

@@ -159,7 +159,7 @@ inline bool resb_applicable(int64_t K) {
 template <class Epi, int kEpiWarps = 8>
 static int launch_gemm_resb(cdml_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
                             int64_t K, int dtype16, const Epi& epi, cudaStream_t stream, int n_fastest = 0) {
-  using L = ResBSmem<kBN, kResBStages, kEpiWarps, Epi::kRowConsts>;
+  using L = ResBSmem<kBN, kResBStages, kEpiWarps, Epi::kRowConsts, Epi::kTmaStore ? 2 : 1>;
   static_assert(L::kTotal <= 232448, "resident-B kernel: shared memory over the 227 KB limit");
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(ctx, &ta, A, dtype16, K, M, lda, kBK, kBM);

@@ -56,6 +56,25 @@ static int dispatch_epilogue(cdml_ctx* ctx, const void* A, int64_t lda, const vo
     }
     case 4: {
       CDML_REQUIRE(aux1 != nullptr && ld_aux1 >= M, "MASK_BITS epilogue needs aux1 (packed sign mask) with a pitch of >= M words");
+      if constexpr (AMN == 0 && BMN == 0) {
+        // resident-B kernel with TMA stores of the output (CDML_TMA_STORE=0: the staged global stores, A/B aid)
+        static int tma_on = -1;
+        if (tma_on < 0) {
+          const char* e = getenv("CDML_TMA_STORE");
+          tma_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+        }
+        if (tma_on && num_splits <= 1 && resb_applicable(K) && M >= 8 * kBM && (ld_out * 2) % 16 == 0) {
+          CUtensorMap om;
+          int rc = make_tmap_2d(ctx, &om, out, dtype16, N, M, ld_out, 32, 32, 64);
+          if (rc) return rc;
+          if (bf) {
+            EpiMaskBitsTma<kBN, 1> e{om, static_cast<const uint32_t*>(aux1), ld_aux1, alpha};
+            return launch_gemm_resb(ctx, A, lda, B, ldb, M, N, K, dtype16, e, stream, 1);
+          }
+          EpiMaskBitsTma<kBN, 0> e{om, static_cast<const uint32_t*>(aux1), ld_aux1, alpha};
+          return launch_gemm_resb(ctx, A, lda, B, ldb, M, N, K, dtype16, e, stream, 1);
+        }
+      }
       if (bf) {
         EpiMaskBits<kBN, 1> e{static_cast<uint16_t*>(out), ld_out, static_cast<const uint32_t*>(aux1), ld_aux1, alpha};
         return launch_any<AMN, BMN>(ctx, A, lda, B, ldb, M, N, K, dtype16, 1, e, stream);

@@ -156,6 +156,7 @@ struct EpiStoreF32 {
   static constexpr bool kPrefetchNext = false;
   static constexpr bool kRowConsts = false;
   static constexpr bool kEarlyRelease = false;
+  static constexpr bool kTmaStore = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -203,6 +204,7 @@ struct EpiStore16 {
   static constexpr bool kPrefetchNext = false;
   static constexpr bool kRowConsts = false;
   static constexpr bool kEarlyRelease = false;
+  static constexpr bool kTmaStore = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -251,6 +253,7 @@ struct EpiL2Norm {
   static constexpr bool kPrefetchNext = false;
   static constexpr bool kRowConsts = false;
   static constexpr bool kEarlyRelease = false;
+  static constexpr bool kTmaStore = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -315,6 +318,7 @@ struct EpiMaskLeaky {
   static constexpr bool kPrefetchNext = false;
   static constexpr bool kRowConsts = false;
   static constexpr bool kEarlyRelease = false;
+  static constexpr bool kTmaStore = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -412,6 +416,7 @@ struct EpiMaskBits {
   static constexpr bool kPrefetchNext = true;
   static constexpr bool kRowConsts = false;
   static constexpr bool kEarlyRelease = false;
+  static constexpr bool kTmaStore = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -457,6 +462,84 @@ struct EpiMaskBits {
   }
 };
 
+// The same epilogue with TMA stores (resident-B kernel only: the tensor map lives in the kernel's __grid_constant__
+// parameter).  A warp writes its 32 x 32 chunk into its staging slice exactly as store_chunk16 does -- that XOR pattern IS
+// the 64-byte TMA swizzle of a [32 rows x 64 bytes] box -- and one lane hands the box to the TMA engine instead of the warp
+// reading it back and issuing 4 x 32 sixteen-byte global stores: half the shared-memory traffic and a quarter of the LSU
+// instructions of the staged path, full 64-byte row pieces, M / N tails clipped by the tensor map.
+template <int BN, int kBf16>
+struct EpiMaskBitsTma {
+  static constexpr bool kSplitColumns = true;
+  struct State {
+    uint32_t bits[4];
+    uint32_t release_bar;   // the accumulator buffer's "empty" barrier (kEarlyRelease)
+  };
+  static constexpr bool kPrefetchNext = true;
+  static constexpr bool kRowConsts = false;
+  static constexpr bool kEarlyRelease = true;
+  static constexpr bool kTmaStore = true;    // two 2 KB staging slices per warp: a box is written while the previous one drains
+  __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
+  __device__ __forceinline__ void block_begin(uint32_t) const {}
+  __device__ __forceinline__ void block_end(uint32_t) const {}
+  CUtensorMap out_map;    // [M rows, N cols] 16-bit, box 32 x 32, SWIZZLE_64B
+  const uint32_t* mask;   // [ceil(N/32)][ld_mask] words, lane <-> row
+  int64_t ld_mask;
+  float alpha;
+  __device__ __forceinline__ void pre(State& st, int row, int n0, const GemmShape& s, int c0, int c1, uint32_t /*stg*/) const {
+    static_assert(BN == 256, "a warp owns 4 chunks of the tile");
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int nb = n0 + (c0 + cc) * 32;
+      st.bits[cc] = (c0 + cc < c1 && nb < s.N && row < s.M) ? __ldg(mask + static_cast<int64_t>(nb >> 5) * ld_mask + row) : 0u;
+    }
+    st.release_bar = 0u;
+  }
+  __device__ __forceinline__ void run(uint32_t taddr, int row, int n0, int /*split*/, const GemmShape& s, int c0, int c1,
+                                      uint32_t stg0, State& st) const {
+    const int lane = threadIdx.x & 31;
+    const int row_base = row - lane;
+    auto ok = [&](int cc) { return c0 + cc < c1 && n0 + (c0 + cc) * 32 < s.N; };   // warp-uniform
+    auto chunk = [&](const uint32_t (&v)[32], int cc) {
+      const uint32_t b = st.bits[cc];
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float x0 = __uint_as_float(v[2 * j]) * ((b >> (2 * j)) & 1u ? 1.f : alpha);
+        const float x1 = __uint_as_float(v[2 * j + 1]) * ((b >> (2 * j + 1)) & 1u ? 1.f : alpha);
+        pk[j] = pack2<kBf16>(x0, x1);
+      }
+      const uint32_t stg = stg0 + (cc & 1) * 2048u;
+      if (lane == 0) bulk_wait_read1();      // the box written to this slice two chunks ago has left shared memory
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts128(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&out_map, stg, n0 + (c0 + cc) * 32, row_base);
+        bulk_commit();
+      }
+    };
+    uint32_t va[32], vb[32];
+    if (ok(0)) tmem_ld_32x32(taddr + c0 * 32, va);
+#pragma unroll
+    for (int cc = 0; cc < 4; cc += 2) {
+      tmem_ld_wait();
+      if (ok(cc + 1)) tmem_ld_32x32(taddr + (c0 + cc + 1) * 32, vb);
+      if (ok(cc)) chunk(va, cc);
+      tmem_ld_wait();
+      if (cc + 2 < 4 && ok(cc + 2)) tmem_ld_32x32(taddr + (c0 + cc + 2) * 32, va);
+      if (cc + 2 >= 4 && st.release_bar != 0u) {   // last TMEM read of this warp has landed: hand the buffer back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(st.release_bar);
+      }
+      if (ok(cc + 1)) chunk(vb, cc + 1);
+    }
+  }
+};
+
 // Measurement aid (epilogue codes 100/101 of cdml_gemm16): no epilogue work at all / TMEM reads only.  Separates the
 // main-loop rate from the TMEM-read and store costs when tuning.
 template <int BN, int kReadTmem>
@@ -467,6 +550,7 @@ struct EpiNull {
   static constexpr bool kPrefetchNext = false;
   static constexpr bool kRowConsts = false;
   static constexpr bool kEarlyRelease = false;
+  static constexpr bool kTmaStore = false;
   __device__ __forceinline__ void cols(int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t) const {}
   __device__ __forceinline__ void block_end(uint32_t) const {}
@@ -663,13 +747,13 @@ struct ResBShape {
 // the selection epilogues are bound by the LATENCY of a warp's chunk sequence, not by issue slots -- with four warps per
 // scheduler the sequence is half as long and the other warps fill its bubbles).  kRowSlots: shared-memory slots for
 // Epi::kRowConsts (0 when the epilogue does not use them).
-template <int BN, int kAStages, int kEpiWarps = 8, bool kRowSlots = false>
+template <int BN, int kAStages, int kEpiWarps = 8, bool kRowSlots = false, int kStageSlices = 1>
 struct ResBSmem {
   static constexpr uint32_t kABytes = kBM * kBK * 2;
   static constexpr uint32_t kBPanel = BN * kBK * 2;
   static constexpr uint32_t kMaxKb = 4;
   static constexpr uint32_t kEpiOff = kMaxKb * kBPanel + kAStages * kABytes;
-  static constexpr uint32_t kEpiBytes = kEpiWarps * 2048;
+  static constexpr uint32_t kEpiBytes = kEpiWarps * 2048 * kStageSlices;
   static constexpr uint32_t kRowConstOff = kEpiOff + kEpiBytes;   // 2 slots x 128 rows x 32 B (Epi::kRowConsts)
   static constexpr uint32_t kRowConstSlot = kRowSlots ? kBM * 32 : 0;
   static constexpr uint32_t kBarOff = kRowConstOff + 2 * kRowConstSlot;
@@ -680,8 +764,8 @@ struct ResBSmem {
 template <int BN, int kAStages, class Epi, int kEpiWarps = 8>
 __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1)
 gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                         const ResBShape s, const Epi epi) {
-  using L = ResBSmem<BN, kAStages, kEpiWarps, Epi::kRowConsts>;
+                         const ResBShape s, const __grid_constant__ Epi epi) {
+  using L = ResBSmem<BN, kAStages, kEpiWarps, Epi::kRowConsts, Epi::kTmaStore ? 2 : 1>;
   static_assert(kEpiWarps == 8 || kEpiWarps == 16, "two or four epilogue warps per TMEM lane quarter");
   static_assert(kEpiWarps == 8 || Epi::kSplitColumns, "four warps per quarter split the tile's columns");
   extern __shared__ uint8_t smem_raw[];
@@ -821,7 +905,7 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     // ===================== epilogue =====================
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;         // which share of the tile's columns (0..kEpiWarps/4-1)
-    const uint32_t stg = base + L::kEpiOff + (warp - 4) * ((Epi::kSplitColumns || kEpiWarps == 16) ? 2048u : 4096u);
+    const uint32_t stg = base + L::kEpiOff + (warp - 4) * (Epi::kTmaStore ? 4096u : (Epi::kSplitColumns || kEpiWarps == 16) ? 2048u : 4096u);
     int it = 0;
     GemmShape gs;
     gs.M = s.M, gs.N = s.N, gs.K = s.K, gs.m_tiles = s.m_tiles, gs.n_tiles = s.n_tiles, gs.num_kb = s.num_kb;
@@ -893,6 +977,9 @@ gemm_resb_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       est = est_next;
       cur = nxt;
       ++it;
+    }
+    if constexpr (Epi::kTmaStore) {
+      if (lane == 0) bulk_wait_all();    // this warp's last boxes are in global memory before the CTA retires
     }
   }
 

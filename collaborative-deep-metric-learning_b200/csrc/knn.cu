@@ -56,6 +56,7 @@ struct EpiKnnGroupMax {
   static constexpr bool kPrefetchNext = false;
   static constexpr bool kRowConsts = false;
   static constexpr bool kEarlyRelease = false;
+  static constexpr bool kTmaStore = false;
   struct State {};
   __device__ __forceinline__ void pre(State&, int, int, const GemmShape&, int, int, uint32_t) const {}
   __device__ __forceinline__ void block_begin(uint32_t epi_smem) const { col_cache_reset(epi_smem); }
@@ -131,7 +132,8 @@ struct EpiKnnCollect {
   };
   static constexpr bool kPrefetchNext = true;   // pre() only loads a row constant into registers
   static constexpr bool kRowConsts = false;
-  static constexpr bool kEarlyRelease = true;  
+  static constexpr bool kEarlyRelease = true;
+  static constexpr bool kTmaStore = false;
   __device__ __forceinline__ void block_begin(uint32_t epi_smem) const {
     col_cache_reset(epi_smem);
     for (int w = 0; w < kKnnLogsPerCta; ++w)

@@ -47,6 +47,7 @@ struct EpiMine {
     uint32_t release_bar; // resident-B kernel: the accumulator buffer's "empty" barrier (0: the kernel arrives itself)
   };
   static constexpr bool kEarlyRelease = true;
+  static constexpr bool kTmaStore = false;
   const float* dp;        // [B] exact |a-p|^2
   const int32_t* guid;    // [B,3] int32 guids
   unsigned long long* best;  // [B] (float bits of d) << 32 | row

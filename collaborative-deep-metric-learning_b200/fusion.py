@@ -19,7 +19,7 @@ import json
 import torch
 
 from . import ops
-from ._lib import EPI_L2NORM, EPI_MASK_LEAKY, EPI_STORE_16, F16
+from ._lib import EPI_L2NORM, EPI_MASK_BITS, EPI_MASK_LEAKY, EPI_STORE_16, F16
 from .engine import LEAKY_ALPHA, TowerEngine, _pad64
 
 
@@ -134,6 +134,9 @@ class GraphEngine(TowerEngine):
         buf["val"][i] = mat16(self.widths[i], train and feeds_fc)
     if train:
       B = R // 3
+      # single-use fc outputs that feed an fc: their data gradient applies leaky' in the GEMM epilogue and needs only the
+      # SIGN of the activation -- one bit per element, written by the forward epilogue (TowerEngine does the same)
+      buf["mask"] = {s: ops.sign_mask_buffer(R, self.widths[s], dev) for s in self._masked_nodes()}
       buf["dz"] = {i: mat16(self.widths[i], False) for i in self.fcs}
       buf["grad"] = {}     # materialised node gradients / data-gradient temporaries, allocated on first use
       buf["dzo"] = mat16(D, False)
@@ -148,6 +151,12 @@ class GraphEngine(TowerEngine):
                                      dtype=torch.float32, device=dev)
     self._store_buffers(key, buf)
     return buf
+
+  def _masked_nodes(self):
+    """fc outputs whose only consumer is an fc: the targets of the MASK_BITS data-gradient epilogue (backward_rows)."""
+    spec = self.spec
+    return [e["src"] for i, e in enumerate(spec) if e["op"] == "fc" and spec[e["src"]]["op"] == "fc"
+            and len(self.consumers[e["src"]]) == 1 and e["src"] != self.fused_out]
 
   def _scratch(self, buf, key, cols):
     m = buf["grad"].get(key)
@@ -171,7 +180,8 @@ class GraphEngine(TowerEngine):
           ops.gemm16(val[e["src"]], self.W16[l], R, N, K, 0, 1, EPI_L2NORM, buf["e"], bias=self.b[l], alpha=self.alpha,
                      aux0=buf["rinv"], aux1=want_e16)
         else:
-          ops.gemm16(val[e["src"]], self.W16[l], R, N, K, 0, 1, EPI_STORE_16, val[i], bias=self.b[l], alpha=self.alpha)
+          ops.gemm16(val[e["src"]], self.W16[l], R, N, K, 0, 1, EPI_STORE_16, val[i], bias=self.b[l], alpha=self.alpha,
+                     aux0=buf["mask"].get(i) if train else None)
       elif op == "mul":
         ops.ew16(ops.EW_MUL, val[e["src"][0]], val[e["src"][1]], val[i])
       elif op == "add":
@@ -275,7 +285,7 @@ class GraphEngine(TowerEngine):
           continue
         if spec[s]["op"] == "fc" and len(self.consumers[s]) == 1:
           # data gradient + leaky' of the producing layer in one epilogue: dz[s] = (dz[i] . W^T) * leaky'(h_s)
-          ops.gemm16(dz[i], self.W16[l], R, K_in, N_out, 0, 0, EPI_MASK_LEAKY, buf["dz"][s], alpha=self.alpha, aux1=val[s])
+          ops.gemm16(dz[i], self.W16[l], R, K_in, N_out, 0, 0, EPI_MASK_BITS, buf["dz"][s], alpha=self.alpha, aux1=buf["mask"][s])
           dz[s] = buf["dz"][s]
         else:
           tmp = self._scratch(buf, ("d", i), K_in)
