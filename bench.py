@@ -9,7 +9,10 @@ HBM.  A step = gather -> tower fwd -> mining -> hinge loss -> bwd -> Adam (+ NCC
 buffer when N>1; weak scaling: every rank keeps batch 65536).  `value` is timed with CUDA events with the index
 triplets already on the device; `e2e` times the same step through the public API from pinned HOST index buffers with
 the H2D copy and the D2H read of the loss inside the timed region.  The second BASELINE metric (KNN top-100
-queries/sec on a 1M-item index) is reported in the `knn` object of the same line.
+queries/sec on a 1M-item index) is reported in `knn_summary` (scalars, early in the line) and the `knn` object.
+Further keys: `roofline` / `roofline_summary`, `cpu_baseline`, `clocks`, `get_batch_e2e` (host float features in),
+`config0_batch1024`, `mining_regimes` (N=1), `weights_identical_across_ranks`, `strong_scaling` (N>1), `desim`.
+  --tower vnet|wide|resnet   --dtype fp16|bf16   --features uniform|clustered   --scaling weak|strong   --no-extras
 """
 import argparse
 import json
