@@ -212,6 +212,24 @@ def test_checkpoint_write_is_atomic_and_carries_hyper(lib, tmp_path, monkeypatch
   assert "fully_connected/weights" in z.files and "fully_connected_1/biases" in z.files
 
 
+def test_engine_buffer_cache_never_evicts_what_a_captured_graph_points_at(lib):
+  """TowerEngine._store_buffers (host policy, no GPU needed): the (rows, train=True) buffers of a captured CUDA graph are
+  pinned for the life of the engine; everything else is an LRU of four entries -- eval batch, eval tail, predict batch,
+  predict tail with different row counts must not push the training buffers out (round 1 cleared the whole cache)."""
+  from cdml_b200.engine import TowerEngine
+  eng = object.__new__(TowerEngine)
+  eng._bufs, eng._pinned_bufs = {}, set()
+  eng._store_buffers((3 * 64, True), "train")
+  eng._pinned_bufs.add((3 * 64, True))                      # what capture_step does
+  for rows in (100, 7, 250, 50, 1000, 33, 10000):
+    eng._store_buffers((rows, False), "infer%d" % rows)
+  assert eng._bufs[(3 * 64, True)] == "train"
+  loose = [k for k in eng._bufs if k not in eng._pinned_bufs]
+  assert loose == [(50, False), (1000, False), (33, False), (10000, False)]       # the four most recent, oldest first
+  eng._store_buffers((3 * 32, True), "train-unpinned")      # a training shape without a graph is evictable like the rest
+  assert (50, False) not in eng._bufs and (3 * 64, True) in eng._bufs
+
+
 def test_imitation_data_matches_reference_stream(lib, golden):
   from cdml_b200 import imitation_data
   np.random.seed(1234)
