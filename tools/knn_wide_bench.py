@@ -1,5 +1,6 @@
 """Raw-feature KNN (d > 256: the generic GEMM kernel, both operands streamed): python tools/knn_wide_bench.py [N] [nq] [d] [k]
-CDML_KNN_WIDE_CHUNK=<queries per pass> selects the query block size (default 8192)."""
+(The CDML_KNN_WIDE_CHUNK sweep of profiles/r02_knn_wide_chunk_sweep.log used an experimental build; the committed library
+ignores the variable and searches 32768 queries per pass.)"""
 import os
 import sys
 
@@ -29,5 +30,5 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 print("raw-feature knn N=%d nq=%d d=%d k=%d chunk=%s: %.2f ms  %.0f queries/s  %.1f TFLOP/s  self-first %.4f  stats=%s" % (
-    N, nq, d, k, os.environ.get("CDML_KNN_WIDE_CHUNK", "8192"), ms, nq / ms * 1e3, 2.0 * nq * N * d / ms / 1e9,
+    N, nq, d, k, os.environ.get("CDML_KNN_WIDE_CHUNK", "32768 (library default)"), ms, nq / ms * 1e3, 2.0 * nq * N * d / ms / 1e9,
     float((I[:, 0] == torch.arange(nq, device=dev)).float().mean().item()), index.last_stats()))
