@@ -228,6 +228,53 @@ def test_emulated16_selection_model_is_the_mining_definition_on_rounded_operands
     assert min(abs(d16[i] - dp[i]), abs(d[i] - dp[i])) < 2e-3 or gap[i] < 2e-3, i
 
 
+def test_knn_record_format_orders_like_distance_then_id():
+  """The 64-bit shard records (cdml_knn_shard_refine / cdml_knn_merge_packed): f2key is an order-preserving bijection of
+  fp32 onto uint32 (negative floats included: inner products), records sort by (distance, id), padding sorts last, and a
+  merge of per-shard lists equals the (D, I)-list merge knn_merge."""
+  rng = np.random.RandomState(8)
+  x = np.concatenate([rng.standard_normal(2000).astype(np.float32) * 3, np.array([0.0, -0.0, 1e-30, -1e-30, np.inf, -np.inf], np.float32)])
+  k = O.f2key(x)
+  nz = ~((x == 0) & np.signbit(x))                                            # -0.0 == 0.0 as floats, adjacent as keys
+  order = np.argsort(x[nz], kind="stable")
+  assert np.all(np.diff(k[nz][order].astype(np.int64)) >= 0)                  # monotone
+  z = O.f2key(np.array([0.0, -0.0], np.float32)).astype(np.int64)
+  assert z[0] - z[1] == 1
+  back = O.key2f(k)
+  assert np.array_equal(back.view(np.uint32), x.view(np.uint32))              # exact inverse, bit for bit
+  for metric in ("L2", "IP"):
+    G, nq, kk = 3, 17, 5
+    vals = rng.rand(G, nq, kk).astype(np.float32) * (1.0 if metric == "L2" else -1.0) + (0.0 if metric == "L2" else 0.5)
+    vals = np.sort(vals, axis=2) if metric == "L2" else -np.sort(-vals, axis=2)
+    ids = rng.permutation(G * nq * kk).reshape(G, nq, kk).astype(np.int64)
+    ids[1, :, 3:] = -1                                                        # a short list: padded
+    vals[1, :, 3:] = np.inf if metric == "L2" else -np.inf
+    rec = np.stack([O.knn_pack_records(vals[g], ids[g], metric) for g in range(G)])
+    assert np.all(np.diff(rec[0].astype(np.float64), axis=1) > 0)             # a sorted list gives ascending records
+    assert np.all(rec[1, :, 3:] == np.uint64(0xFFFFFFFFFFFFFFFF))
+    Dm, Im = O.knn_merge_records(rec, kk, metric)
+    Dw, Iw = O.knn_merge([vals[g] for g in range(G)], [ids[g] for g in range(G)], kk, metric)
+    assert np.array_equal(Im, Iw) and np.array_equal(Dm, Dw)
+
+
+def test_emulated16_trainer_tracks_the_float64_trainer():
+  """OracleTrainer(emulate16=...) -- the precision model the GPU trajectory test gates against -- is the float64 trainer with
+  rounded operands: fp16 stays within a few 1e-4 of its loss, bf16 within a few 1e-3, and both train."""
+  feats = O.synth_features(300, 24, 0)
+  params = O.init_tower([24, 32, 16], seed=2, dtype=np.float64)
+  tr = {name: O.OracleTrainer(params, lr=1e-2, margin=0.8, emulate16=e) for name, e in (("f64", None), ("fp16", "fp16"), ("bf16", "bf16"))}
+  first = {}
+  for t in range(12):
+    x = O.flatten_triplets(O.gather_rows(feats, O.synth_triplets(64, 300, 5 + t)))
+    for name, trainer in tr.items():
+      loss = trainer.step(x)[0]
+      first.setdefault(name, loss)
+      last = loss if name != "f64" else loss
+      tr[name].last = loss
+  assert abs(tr["fp16"].last / tr["f64"].last - 1) < 2e-3 and abs(tr["bf16"].last / tr["f64"].last - 1) < 2e-2
+  assert all(tr[n].last < first[n] for n in tr)
+
+
 def test_semihard_mining_definition():
   rng = np.random.RandomState(5)
   B, D = 40, 16
